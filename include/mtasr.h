@@ -1,0 +1,172 @@
+/* mtasr.h -- C ABI of the B200-native encoder + serialized-CTC hot path (libmtasr.so, sm_100a).
+ *
+ * The reference (Hao-Shi-SBINT/Multi-talker-ASR-with-LLMs) has no FFI/plugin layer: its hot path calls
+ * torch/ATen and HF `transformers` directly.  The boundary a maintainer binds is therefore this
+ * header, loaded with ctypes from the Python classes that mirror the reference's own
+ * (WavLMModel / Separator / CTC / HybridLoss).  Each entry point names the reference call site it replaces.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no sync, no allocation);
+ *   - the caller owns every buffer including workspaces;
+ *   - return 0 on success, negative MTASR_ERR_* otherwise; mtasr_last_error_string() gives the reason
+ *     (thread-local); nothing throws across the boundary;
+ *   - bf16 = __nv_bfloat16 bit pattern (uint16_t), f32 = float, i64 = int64_t, i32 = int32_t.
+ */
+#ifndef MTASR_H_
+#define MTASR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTASR_OK 0
+#define MTASR_ERR_INVALID_ARG (-1)
+#define MTASR_ERR_UNSUPPORTED (-2)
+#define MTASR_ERR_LAUNCH (-3)
+#define MTASR_ERR_DRIVER (-4)
+
+#define MTASR_DT_BF16 0
+#define MTASR_DT_F32 1
+
+int mtasr_version(void);
+const char* mtasr_last_error_string(void);
+/* Number of kernels this library has enqueued since load (process-wide; used by bench.py `gpu_launches`). */
+int64_t mtasr_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Dense contraction on tcgen05 tensor cores (TMA-fed, TMEM accumulators, fp32 accumulate, bf16 operands).
+ *   C[b][m][n] = epilogue( alpha * sum_k A[b][m][k] * B[b][n][k] )
+ * Replaces every F.linear / F.conv1d / bmm on the path: hf:100-105 (projection), hf:82-90 (pos-conv as implicit
+ * GEMM), hf:206-228 (q/k/v/out projections and QK^T / PV), hf:288-295 (FFN), hf:709-727 (conv layers 1-6 as
+ * implicit GEMM over a strided channels-last view), hf:803-807 (adapter convs), ref:models/separator.py:158-165,
+ * ref:models/ctc.py:139,180,190 (ctc_lo) and all of their backward contractions.
+ *
+ * Operand addressing (element units, bf16):
+ *  A, K-major (a_major=0):   A(b,m,k) = a[b0*a_sb0 + b1*a_sb1 + (m + tap/a_phase)*a_ld + (tap%a_phase)*a_inner + c]
+ *                            with k = tap*a_inner + c, c < a_inner.  Plain GEMM: a_inner=K, a_phase=1.
+ *                            Implicit conv1d on channels-last x[b][l][c]: a_inner=C_in, a_phase=stride,
+ *                            a_ld=stride*C_in, K=kernel*C_in (a_inner % 64 == 0 required when K > a_inner).
+ *  A, MN-major (a_major=1):  A(b,m,k) = a[b0*a_sb0 + b1*a_sb1 + k*a_ld + m]
+ *  B, K-major (b_major=0):   B(b,n,k) = bm[b0*b_sb0 + b1*b_sb1 + n*b_ld + k]
+ *  B, MN-major (b_major=1):  B(b,n,k) = bm[b0*b_sb0 + b1*b_sb1 + k*b_ld + n]
+ *  b = b1*batch0 + b0.  A batch stride of 0 broadcasts the operand over that batch dimension.
+ *  a_rows / b_rows: number of addressable rows per batch (TMA zero-fills beyond them; defaults: see gemm.cu).
+ *  Alignment: base pointers and all strides (bytes) multiples of 16.
+ *
+ * Epilogue (per element, in this order): v = alpha*acc; v += bias[b0*bias_sb0 + n]; aux[..] = v (optional, bf16,
+ * the pre-activation); v = act(v); v += residual[..]; if accumulate: v += C_old; C = v.
+ *  act 3 / act 4 are the backward forms: v *= gelu'(residual) / v *= (residual > 0), with `residual` holding the
+ *  saved pre-activation (GELU) or activation output (ReLU) instead of being added.
+ *  mode 1 (LSE partials, ref:models/ctc.py:53 log_softmax fused): nothing is written to C; for every row and
+ *    N-tile writes {max, sum exp(v-max), argmax index} to lse_part[(b*M+m)*n_tiles + n_tile] (float4, .w unused).
+ *  mode 2 (softmax regeneration for the backward): C = exp(v - row_vec[b*M+m]) * row_scale[b*M+m].
+ */
+typedef struct mtasr_gemm_desc {
+  int32_t M, N, K;
+  int32_t batch0, batch1;
+  int32_t a_major, b_major;
+  int32_t block_n; /* 64, 128 or 256; 0 = choose */
+  const void* a;
+  int64_t a_ld, a_sb0, a_sb1;
+  int32_t a_inner, a_phase;
+  int64_t a_rows;
+  const void* b;
+  int64_t b_ld, b_sb0, b_sb1;
+  int64_t b_rows;
+  void* c;
+  int32_t c_dtype;
+  int64_t c_ld, c_sb0, c_sb1;
+  void* aux; /* bf16, same layout as c, optional */
+  const float* bias;
+  int64_t bias_sb0;
+  const void* residual;
+  int32_t res_dtype;
+  int64_t r_ld, r_sb0, r_sb1;
+  int32_t act; /* 0 none, 1 gelu(erf), 2 relu, 3 gelu-backward, 4 relu-backward */
+  float alpha;
+  int32_t accumulate;
+  int32_t mode;
+  const float* row_vec;
+  const float* row_scale;
+  float* lse_part;
+} mtasr_gemm_desc;
+
+int mtasr_gemm_bf16(const mtasr_gemm_desc* desc, void* stream);
+/* Number of N tiles mtasr_gemm_bf16 will use for (N, block_n) -- sizes the mode-1 partials buffer. */
+int mtasr_gemm_n_tiles(int32_t N, int32_t block_n);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Serialized CTC (one head at a time; ref:models/ctc.py:44-65, torch.nn.CTCLoss(reduction='none',
+ * zero_infinity=True, blank=V-1) semantics).  "Compact lattice columns": glog (B,T,Lp) f32 holds logits of column
+ * 0 = blank and 1+l = label l of utterance b; lse (B,T) is the row log-sum-exp over the whole vocabulary.
+ * ys (B, ys_ld) i64 padded labels, hlens/ylens (B) i64.  Lp >= max_label_len + 1, max_label_len <= 255.
+ */
+/* padded state count SP = 32*NS used to size alpha_ws (B*T*SP f32); -1 if max_label_len unsupported */
+int mtasr_ctc_state_pad(int32_t max_label_len);
+/* alpha recursion: nll_out (B) = per-utterance loss with infeasible rows zeroed, nll_raw (B) keeps +inf. */
+int mtasr_ctc_alpha_fwd(const float* glog, const float* lse, const int64_t* ys, const int64_t* hlens,
+                        const int64_t* ylens, int32_t B, int32_t T, int32_t Lp, int32_t ys_ld, int32_t max_label_len,
+                        float* alpha_ws, double* coff_ws, float* nll_out, float* nll_raw, void* stream);
+/* beta recursion + gradient: dG (B,T,Lp) = gout[b] * d nll_b / d lp(t, column) (= -gout*occupancy),
+ * rowscale (B,T) = gout[b] on valid frames of feasible utterances else 0 (scales the dense softmax term). */
+int mtasr_ctc_beta_bwd(const float* glog, const float* lse, const int64_t* ys, const int64_t* hlens,
+                       const int64_t* ylens, int32_t B, int32_t T, int32_t Lp, int32_t ys_ld, int32_t max_label_len,
+                       const float* alpha_ws, const double* coff_ws, const float* nll_raw, const float* gout,
+                       float* dG, float* rowscale, void* stream);
+/* Combine the mode-1 GEMM partials: lse (rows) f32 and/or argmax (rows) i64 (first maximal index, like
+ * torch.argmax -- ref:models/ctc.py:190). */
+int mtasr_lse_finalize(const float* part, int64_t rows, int32_t n_tiles, float* lse, int64_t* argmax, void* stream);
+/* Greedy collapse of ref:models/modeling_speech_encoder_decoder_llama.py:902-972 on (B,T) i64 argmax ids:
+ * out (B,T) i64 right-padded with pad_id, lengths (B) i32. */
+int mtasr_ctc_collapse(const int64_t* ids, int32_t B, int32_t T, int64_t blank_id, int64_t pad_id, int64_t* out,
+                       int32_t* lengths, void* stream);
+/* dense (B,T,V) f32 <-> compact lattice columns (B,T,Lp) f32 (scatter ADDS into dense). */
+int mtasr_ctc_gather_cols(const float* dense, const int64_t* ys, const int64_t* ylens, int32_t B, int32_t T, int32_t V,
+                          int32_t Lp, int32_t ys_ld, int64_t blank, float* out, void* stream);
+int mtasr_ctc_scatter_cols(const float* src, const int64_t* ys, const int64_t* ylens, int32_t B, int32_t T, int32_t V,
+                           int32_t Lp, int32_t ys_ld, int64_t blank, float* dense, void* stream);
+/* rows of the head weight (V,D) bf16 / bias (V) f32 touched by each lattice -> wg (B,Lp,D) bf16, bg (B,Lp) f32;
+ * and the reverse scatter-add of their gradients (f32 atomics). */
+int mtasr_ctc_gather_rows(const void* w_bf16, const float* bias, const int64_t* ys, const int64_t* ylens, int32_t B,
+                          int32_t Lp, int32_t D, int32_t ys_ld, int64_t blank, void* wg_bf16, float* bg, void* stream);
+int mtasr_ctc_scatter_rows(const float* dwg, const float* dbg, const int64_t* ys, const int64_t* ylens, int32_t B,
+                           int32_t Lp, int32_t D, int32_t ys_ld, int64_t blank, float* dw, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * HBM-bound row kernels (128-bit vectorised, one warp per row).
+ */
+/* LayerNorm over the last dim D (<=1024, %8): hf:100-105, hf:355-366, hf:314-329, hf:720-727 (post_gelu=1),
+ * ref:models/separator.py:158-165.  x f32|bf16 -> y_bf16 and/or y_f32; mean/rstd (rows) saved for backward. */
+int mtasr_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, float eps, int64_t rows,
+                        int32_t D, int32_t post_gelu, void* y_bf16, float* y_f32, float* mean, float* rstd, void* stream);
+/* dx (+ dres) as f32 and/or bf16; dgamma/dbeta are ACCUMULATED (atomics) -- zero them first. */
+int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
+                        const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D, float* dx_f32,
+                        void* dx_bf16, float* dgamma, float* dbeta, void* stream);
+int mtasr_cast_f32_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* out[n] = sum_m x[m][n] (bias gradients) */
+int mtasr_colsum(const void* x, int32_t dtype, int64_t M, int32_t N, int64_t ld, float* out, void* stream);
+/* softmax(S*scale + gate[b,h,q]*table[h,k-q+T-1]) over keys k < klen[b] (hf:167-180 + hf:206-228 fused);
+ * S (B,H,T,Tp) f32, gate (B,H,T) f32, table (H,2T-1) f32, klen (B) i32 or NULL, P (B,H,T,Tp) bf16. */
+int mtasr_attn_softmax_fwd(const float* S, const float* gate, const float* table, const int32_t* klen, int32_t B,
+                           int32_t H, int32_t T, int32_t Tp, float scale, void* P_bf16, void* stream);
+/* dS = scale * P*(dP - rowdot) bf16; dgate (B,H,T); dtable (H,2T-1) ACCUMULATED (zero it first). */
+int mtasr_attn_softmax_bwd(const void* P_bf16, const float* dP, const float* gate, const float* table, int32_t B,
+                           int32_t H, int32_t T, int32_t Tp, float scale, void* dS_bf16, float* dgate, float* dtable,
+                           void* stream);
+/* y (B,Tpad,D) bf16 = zero-pad(x (B,T,D), pad_l rows left), rows t >= vlen[b] zeroed when vlen != NULL. */
+int mtasr_pad_cast(const void* x, int32_t x_dtype, int32_t B, int32_t T, int32_t D, int32_t pad_l, int32_t Tpad,
+                   const int32_t* vlen, void* y_bf16, void* stream);
+/* GLU over channel halves of channels-last rows (hf:803-807): x (rows, 2C) -> y (rows, C). */
+int mtasr_glu_fwd(const void* x, int32_t x_dtype, int64_t rows, int32_t C, void* y_bf16, float* y_f32, void* stream);
+int mtasr_glu_bwd(const void* x, int32_t x_dtype, const void* dy, int32_t dy_dtype, int64_t rows, int32_t C,
+                  void* dx_bf16, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTASR_H_ */

@@ -1,0 +1,37 @@
+// Library-wide plumbing of the C ABI: version, thread-local error string, device properties.
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace mtasr {
+
+static thread_local char g_err[1024] = "";
+
+char* last_error_buf() { return g_err; }
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int num_sms() {
+  static int n = 0;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  });
+  return n;
+}
+
+}  // namespace mtasr
+
+extern "C" int mtasr_version(void) { return 100; }
+extern "C" const char* mtasr_last_error_string(void) { return mtasr::last_error_buf(); }

@@ -1,0 +1,89 @@
+// Shared helpers for the mtasr C-ABI library (sm_100a only).
+#pragma once
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/mtasr.h"
+
+namespace mtasr {
+
+// Thread-local last-error string, returned through mtasr_last_error_string().
+char* last_error_buf();
+int set_error(int code, const char* fmt, ...);
+
+#define MTASR_CHECK_ARG(cond, ...)                                  \
+  do {                                                              \
+    if (!(cond)) return ::mtasr::set_error(MTASR_ERR_INVALID_ARG, __VA_ARGS__); \
+  } while (0)
+
+#define MTASR_CHECK_LAUNCH(name)                                                                   \
+  do {                                                                                             \
+    cudaError_t e__ = cudaGetLastError();                                                          \
+    if (e__ != cudaSuccess)                                                                        \
+      return ::mtasr::set_error(MTASR_ERR_LAUNCH, "%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+  } while (0)
+
+int num_sms();
+extern std::atomic<long long> g_launches;
+#define MTASR_COUNT_LAUNCH() ::mtasr::g_launches.fetch_add(1)
+
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&v);
+  return __bfloat1622float2(t);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// erf-based GELU (HF "gelu" == torch.nn.functional.gelu default) and its derivative.
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// log(exp(a)+exp(b)) that tolerates -inf on either side.
+__device__ __forceinline__ float logaddexp_f(float a, float b) {
+  const float m = fmaxf(a, b);
+  if (m == -INFINITY) return -INFINITY;
+  return m + log1pf(__expf(fminf(a, b) - m));
+}
+
+// Block-wide sum for blockDim.x <= 1024 (result broadcast to all threads).
+__device__ __forceinline__ float block_sum(float v, float* red /* >= 33 floats */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    float t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+}  // namespace mtasr

@@ -1,0 +1,531 @@
+// Serialized-CTC kernels: per-(utterance, speaker) alpha/beta recursion, greedy collapse, LSE finalisation.
+//
+// Layout ("compact lattice columns"): for one CTC head, glog[b][t][c] holds the LOGITS of only the columns the
+// lattice of utterance b can touch: c = 0 is the blank, c = 1 + l is label y[b][l] (l < L_b).  lse[b][t] is the
+// log-sum-exp of the full vocabulary row, so lp(t, c) = glog[b][t][c] - lse[b][t] is what torch's
+// log_softmax + CTCLoss (ref:models/ctc.py:53-54) would read at (t, b, ext[s]).  The (B,T,V) tensor never exists.
+//
+// One warp per utterance; lane i owns NS consecutive extended states s = i*NS .. i*NS+NS-1 in registers, the
+// s-1 / s-2 neighbours of its first two states come from lane i-1 by shuffle.  The recursion is kept NORMALISED
+// (every step subtracts the warp-wide max, the running offset is accumulated in double), so fp32 state values stay
+// O(1) and loss/gradients match the fp64 oracle to ~1e-6 instead of the ~1e-5 of an unnormalised fp32 lattice.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace mtasr {
+
+static constexpr float NEG_INF = -INFINITY;
+
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  if (m == NEG_INF) return NEG_INF;
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+
+// ------------------------------------------------------------------------------------------------ alpha
+template <int NS>
+__global__ void __launch_bounds__(128)
+ctc_alpha_kernel(const float* __restrict__ glog, const float* __restrict__ lse, const long long* __restrict__ ys,
+                 const long long* __restrict__ hlens, const long long* __restrict__ ylens, int B, int T, int Lp,
+                 int ys_ld, float* __restrict__ alpha_ws, double* __restrict__ coff_ws, float* __restrict__ nll_out,
+                 float* __restrict__ nll_raw) {
+  constexpr int SP = 32 * NS;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  int Tb = static_cast<int>(hlens[b]);
+  Tb = Tb < 0 ? 0 : (Tb > T ? T : Tb);
+  const int L = static_cast<int>(ylens[b]);
+  const int S = 2 * L + 1;
+  const long long* y = ys + static_cast<long long>(b) * ys_ld;
+
+  int col[NS];
+  bool ok[NS], skip[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int s = lane * NS + j;
+    ok[j] = s < S;
+    col[j] = (s & 1) ? (s >> 1) + 1 : 0;
+    skip[j] = ok[j] && (s & 1) && s >= 3 && (y[s >> 1] != y[(s >> 1) - 1]);
+  }
+  if (Tb == 0) {
+    if (lane == 0) {
+      const float v = L == 0 ? 0.f : INFINITY;
+      nll_raw[b] = v;
+      nll_out[b] = isinf(v) ? 0.f : v;
+    }
+    return;
+  }
+  const float* g = glog + static_cast<long long>(b) * T * Lp;
+  const float* ls = lse + static_cast<long long>(b) * T;
+  float* aw = alpha_ws + static_cast<long long>(b) * T * SP;
+  double* cw = coff_ws + static_cast<long long>(b) * T;
+
+  float a[NS];
+  float nxt[NS];
+  {
+    const float l0 = ls[0];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      const int s = lane * NS + j;
+      a[j] = (ok[j] && s <= 1) ? g[col[j]] - l0 : NEG_INF;
+    }
+  }
+  double coff = 0.0;
+  // prefetch t = 1
+  if (Tb > 1) {
+    const float l1 = ls[1];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) nxt[j] = ok[j] ? g[Lp + col[j]] - l1 : NEG_INF;
+  }
+  for (int t = 0; t < Tb; ++t) {
+    if (t > 0) {
+      float cur[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) cur[j] = nxt[j];
+      if (t + 1 < Tb) {
+        const float l1 = ls[t + 1];
+        const float* gr = g + static_cast<long long>(t + 1) * Lp;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) nxt[j] = ok[j] ? gr[col[j]] - l1 : NEG_INF;
+      }
+      float pm1 = __shfl_up_sync(0xffffffffu, a[NS - 1], 1);
+      float pm2 = __shfl_up_sync(0xffffffffu, a[NS - 2], 1);
+      if (lane == 0) { pm1 = NEG_INF; pm2 = NEG_INF; }
+      float na[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const float s1 = j >= 1 ? a[j - 1] : pm1;
+        const float s2 = j >= 2 ? a[j - 2] : (j == 1 ? pm1 : pm2);
+        na[j] = ok[j] ? cur[j] + lse3(a[j], s1, skip[j] ? s2 : NEG_INF) : NEG_INF;
+      }
+#pragma unroll
+      for (int j = 0; j < NS; ++j) a[j] = na[j];
+    }
+    // normalise
+    float m = NEG_INF;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) m = fmaxf(m, a[j]);
+    m = warp_max(m);
+    if (m == NEG_INF) m = 0.f;  // dead lattice: stays -inf, nll becomes +inf below
+#pragma unroll
+    for (int j = 0; j < NS; ++j) a[j] -= m;
+    coff += static_cast<double>(m);
+    float4* dst = reinterpret_cast<float4*>(aw + static_cast<long long>(t) * SP + lane * NS);
+    if constexpr (NS % 4 == 0) {
+#pragma unroll
+      for (int j = 0; j < NS; j += 4) dst[j >> 2] = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) aw[static_cast<long long>(t) * SP + lane * NS + j] = a[j];
+    }
+    if (lane == 0) cw[t] = coff;
+  }
+  float e1 = NEG_INF, e2 = NEG_INF;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int s = lane * NS + j;
+    if (s == S - 1) e1 = a[j];
+    if (s == S - 2) e2 = a[j];
+  }
+  e1 = warp_max(e1);
+  e2 = warp_max(e2);
+  if (lane == 0) {
+    const float tail = logaddexp_f(e1, e2);
+    const float v = tail == NEG_INF ? INFINITY : static_cast<float>(-(coff + static_cast<double>(tail)));
+    nll_raw[b] = v;
+    nll_out[b] = isinf(v) ? 0.f : v;  // zero_infinity=True (ref:models/ctc.py:31,44-46)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ beta + grad
+// dG[b][t][c] = -gout[b] * occupancy(t, c);  rowscale[b][t] = gout[b] for valid frames of feasible utterances.
+// The dense part of d nll/d logits (softmax * rowscale) is regenerated by the vocab GEMM (mode 2).
+template <int NS>
+__global__ void __launch_bounds__(128)
+ctc_beta_grad_kernel(const float* __restrict__ glog, const float* __restrict__ lse, const long long* __restrict__ ys,
+                     const long long* __restrict__ hlens, const long long* __restrict__ ylens, int B, int T, int Lp,
+                     int ys_ld, const float* __restrict__ alpha_ws, const double* __restrict__ coff_ws,
+                     const float* __restrict__ nll_raw, const float* __restrict__ gout, float* __restrict__ dG,
+                     float* __restrict__ rowscale) {
+  constexpr int SP = 32 * NS;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  int Tb = static_cast<int>(hlens[b]);
+  Tb = Tb < 0 ? 0 : (Tb > T ? T : Tb);
+  const int L = static_cast<int>(ylens[b]);
+  const int S = 2 * L + 1;
+  const long long* y = ys + static_cast<long long>(b) * ys_ld;
+  const float nll = nll_raw[b];
+  const bool feasible = !isinf(nll) && Tb > 0;
+  const float go = gout[b];
+  float* rs = rowscale + static_cast<long long>(b) * T;
+  for (int t = lane; t < T; t += 32) rs[t] = (feasible && t < Tb) ? go : 0.f;
+  float* dg = dG + static_cast<long long>(b) * T * Lp;
+  // zero everything this utterance does not write below
+  for (long long i = lane; i < static_cast<long long>(T) * Lp; i += 32) {
+    const int t = static_cast<int>(i / Lp), c = static_cast<int>(i - static_cast<long long>(t) * Lp);
+    if (!feasible || t >= Tb || c > L) dg[i] = 0.f;
+  }
+  if (!feasible) return;
+
+  int col[NS];
+  bool ok[NS], skip[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const int s = lane * NS + j;
+    ok[j] = s < S;
+    col[j] = (s & 1) ? (s >> 1) + 1 : 0;
+    skip[j] = ok[j] && (s & 1) && (s + 2 < S) && (y[s >> 1] != y[(s >> 1) + 1]);
+  }
+  const float* g = glog + static_cast<long long>(b) * T * Lp;
+  const float* ls = lse + static_cast<long long>(b) * T;
+  const float* aw = alpha_ws + static_cast<long long>(b) * T * SP;
+  const double* cw = coff_ws + static_cast<long long>(b) * T;
+
+  float bt[NS];
+  float lp[NS], nxt[NS];
+  double boff = 0.0;
+  {
+    const float l0 = ls[Tb - 1];
+    const float* gr = g + static_cast<long long>(Tb - 1) * Lp;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) nxt[j] = ok[j] ? gr[col[j]] - l0 : NEG_INF;
+  }
+  for (int t = Tb - 1; t >= 0; --t) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) lp[j] = nxt[j];
+    if (t > 0) {
+      const float l1 = ls[t - 1];
+      const float* gr = g + static_cast<long long>(t - 1) * Lp;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) nxt[j] = ok[j] ? gr[col[j]] - l1 : NEG_INF;
+    }
+    if (t == Tb - 1) {
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const int s = lane * NS + j;
+        bt[j] = (ok[j] && (s == S - 1 || s == S - 2)) ? lp[j] : NEG_INF;
+      }
+    } else {
+      float np1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
+      float np2 = __shfl_down_sync(0xffffffffu, bt[1], 1);
+      if (lane == 31) { np1 = NEG_INF; np2 = NEG_INF; }
+      float nb[NS];
+#pragma unroll
+      for (int j = 0; j < NS; ++j) {
+        const float s1 = j + 1 < NS ? bt[j + 1 < NS ? j + 1 : 0] : np1;
+        const float s2 = j + 2 < NS ? bt[j + 2 < NS ? j + 2 : 0] : (j + 2 == NS ? np1 : np2);
+        nb[j] = ok[j] ? lp[j] + lse3(bt[j], s1, skip[j] ? s2 : NEG_INF) : NEG_INF;
+      }
+#pragma unroll
+      for (int j = 0; j < NS; ++j) bt[j] = nb[j];
+    }
+    float m = NEG_INF;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) m = fmaxf(m, bt[j]);
+    m = warp_max(m);
+    if (m == NEG_INF) m = 0.f;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) bt[j] -= m;
+    boff += static_cast<double>(m);
+    // occupancy: exp(alpha + beta - lp + nll) with the three O(|nll|) offsets combined in double
+    const float shift = static_cast<float>(cw[t] + boff + static_cast<double>(nll));
+    const float* ar = aw + static_cast<long long>(t) * SP + lane * NS;
+    float blank_occ = 0.f;
+    float* dgr = dg + static_cast<long long>(t) * Lp;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      if (ok[j]) {
+        const float e = ar[j] + bt[j] - lp[j] + shift;
+        const float occ = (ar[j] == NEG_INF || bt[j] == NEG_INF) ? 0.f : __expf(e);
+        if (col[j] == 0) blank_occ += occ;
+        else dgr[col[j]] = -go * occ;
+      }
+    }
+    blank_occ = warp_sum(blank_occ);
+    if (lane == 0) dgr[0] = -go * blank_occ;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LSE finalise
+// Combine the per-N-tile {max, sumexp, argmax} partials written by the vocab GEMM (mode 1).  One warp per row.
+__global__ void lse_finalize_kernel(const float4* __restrict__ part, int rows, int n_tiles, float* __restrict__ lse,
+                                    long long* __restrict__ argmax) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* p = part + row * n_tiles;
+  float m = NEG_INF, s = 0.f;
+  int idx = 0x7fffffff;
+  for (int i = lane; i < n_tiles; i += 32) {
+    const float4 v = p[i];
+    const int vi = __float_as_int(v.z);
+    if (v.x > m) {
+      s = s * __expf(m - v.x) + v.y;
+      m = v.x;
+      idx = vi;
+    } else {
+      s += v.y * __expf(v.x - m);
+      if (v.x == m && vi < idx) idx = vi;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, m, o);
+    const float os = __shfl_xor_sync(0xffffffffu, s, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    const float nm = fmaxf(m, om);
+    const float sa = m == NEG_INF ? 0.f : s * __expf(m - nm);
+    const float sb = om == NEG_INF ? 0.f : os * __expf(om - nm);
+    if (om > m || (om == m && oi < idx)) idx = oi;
+    m = nm;
+    s = sa + sb;
+  }
+  if (lane == 0) {
+    if (lse) lse[row] = m + __logf(s);
+    if (argmax) argmax[row] = idx;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ collapse
+// Greedy collapse of ref:models/modeling_speech_encoder_decoder_llama.py:902-972: drop pad, drop blank, drop a token
+// equal to the most recent non-blank/non-pad token.  One warp per row, 32 frames per step, ballot + popc ranking.
+__global__ void ctc_collapse_kernel(const long long* __restrict__ ids, int B, int T, long long blank_id,
+                                    long long pad_id, long long* __restrict__ out, int* __restrict__ lengths) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const long long* row = ids + static_cast<long long>(b) * T;
+  long long* o = out + static_cast<long long>(b) * T;
+  long long carry = 0;
+  bool have_carry = false;
+  int n = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    const long long tok = t < T ? row[t] : pad_id;
+    const bool valid = t < T && tok != pad_id && tok != blank_id;
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const unsigned below = vmask & ((1u << lane) - 1u);
+    const int src = below ? 31 - __clz(below) : 0;
+    const long long prev_in = __shfl_sync(0xffffffffu, tok, src);
+    bool keep = false;
+    if (valid) {
+      if (below) keep = prev_in != tok;
+      else keep = !have_carry || carry != tok;
+    }
+    const unsigned kmask = __ballot_sync(0xffffffffu, keep);
+    if (keep) o[n + __popc(kmask & ((1u << lane) - 1u))] = tok;
+    n += __popc(kmask);
+    if (vmask) {
+      carry = __shfl_sync(0xffffffffu, tok, 31 - __clz(vmask));
+      have_carry = true;
+    }
+  }
+  for (int t = n + lane; t < T; t += 32) o[t] = pad_id;
+  if (lane == 0) lengths[b] = n;
+}
+
+// ------------------------------------------------------------------------------------------------ gathers
+// dense (B,T,V) fp32 logits -> compact lattice columns (B,T,Lp): c=0 blank, c=1+l label l, rest 0.
+__global__ void ctc_gather_cols_kernel(const float* __restrict__ dense, const long long* __restrict__ ys,
+                                       const long long* __restrict__ ylens, int B, int T, int V, int Lp, int ys_ld,
+                                       long long blank, float* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * T * Lp;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % Lp);
+  const long long bt = i / Lp;
+  const int b = static_cast<int>(bt / T);
+  const int L = static_cast<int>(ylens[b]);
+  float v = 0.f;
+  if (c == 0) v = dense[bt * V + blank];
+  else if (c <= L) v = dense[bt * V + ys[static_cast<long long>(b) * ys_ld + c - 1]];
+  out[i] = v;
+}
+
+// dense[b][t][col(c)] += src[b][t][c] for the lattice columns (inverse of the gather; repeated labels accumulate).
+__global__ void ctc_scatter_cols_kernel(const float* __restrict__ src, const long long* __restrict__ ys,
+                                        const long long* __restrict__ ylens, int B, int T, int V, int Lp, int ys_ld,
+                                        long long blank, float* __restrict__ dense) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(B) * T * Lp;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % Lp);
+  const long long bt = i / Lp;
+  const int b = static_cast<int>(bt / T);
+  const int L = static_cast<int>(ylens[b]);
+  if (c > L) return;
+  const long long v = c == 0 ? blank : ys[static_cast<long long>(b) * ys_ld + c - 1];
+  atomicAdd(dense + bt * V + v, src[i]);
+}
+
+// Rows of the (V, D) head weight needed by each utterance's lattice -> Wg (B, Lp, D) bf16 (+ bias -> bg (B, Lp)).
+__global__ void ctc_gather_rows_kernel(const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+                                       const long long* __restrict__ ys, const long long* __restrict__ ylens, int B,
+                                       int Lp, int D, int ys_ld, long long blank, __nv_bfloat16* __restrict__ wg,
+                                       float* __restrict__ bg) {
+  const int b = blockIdx.x / Lp, c = blockIdx.x % Lp;
+  const int L = static_cast<int>(ylens[b]);
+  long long v = -1;
+  if (c == 0) v = blank;
+  else if (c <= L) v = ys[static_cast<long long>(b) * ys_ld + c - 1];
+  __nv_bfloat16* dst = wg + (static_cast<long long>(b) * Lp + c) * D;
+  for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (v >= 0) u = *reinterpret_cast<const uint4*>(w + v * D + i);
+    *reinterpret_cast<uint4*>(dst + i) = u;
+  }
+  if (threadIdx.x == 0 && bg) bg[static_cast<long long>(b) * Lp + c] = (v >= 0 && bias) ? bias[v] : 0.f;
+}
+
+// dW[v(b,c)][:] += dWg[b][c][:]; db[v] += dbg[b][c]  (fp32 atomics; <= B*(L+1) rows touched).
+__global__ void ctc_scatter_rows_kernel(const float* __restrict__ dwg, const float* __restrict__ dbg,
+                                        const long long* __restrict__ ys, const long long* __restrict__ ylens, int B,
+                                        int Lp, int D, int ys_ld, long long blank, float* __restrict__ dw,
+                                        float* __restrict__ db) {
+  const int b = blockIdx.x / Lp, c = blockIdx.x % Lp;
+  const int L = static_cast<int>(ylens[b]);
+  if (c > L) return;
+  const long long v = c == 0 ? blank : ys[static_cast<long long>(b) * ys_ld + c - 1];
+  const float* src = dwg + (static_cast<long long>(b) * Lp + c) * D;
+  for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(dw + v * D + i, src[i]);
+  if (threadIdx.x == 0 && db && dbg) atomicAdd(db + v, dbg[static_cast<long long>(b) * Lp + c]);
+}
+
+static int pick_ns(int max_states) {
+  if (max_states <= 64) return 2;
+  if (max_states <= 128) return 4;
+  if (max_states <= 256) return 8;
+  if (max_states <= 512) return 16;
+  return -1;
+}
+
+}  // namespace mtasr
+
+using namespace mtasr;
+
+extern "C" int mtasr_ctc_state_pad(int32_t max_label_len) {
+  const int ns = pick_ns(2 * max_label_len + 1);
+  return ns < 0 ? -1 : 32 * ns;
+}
+
+extern "C" int mtasr_ctc_alpha_fwd(const float* glog, const float* lse, const int64_t* ys, const int64_t* hlens,
+                                   const int64_t* ylens, int32_t B, int32_t T, int32_t Lp, int32_t ys_ld,
+                                   int32_t max_label_len, float* alpha_ws, double* coff_ws, float* nll_out,
+                                   float* nll_raw, void* stream) {
+  MTASR_CHECK_ARG(glog && lse && hlens && ylens && alpha_ws && coff_ws && nll_out && nll_raw, "ctc_alpha_fwd: null pointer");
+  MTASR_CHECK_ARG(ys || max_label_len == 0, "ctc_alpha_fwd: null labels");
+  MTASR_CHECK_ARG(B > 0 && T > 0 && Lp >= max_label_len + 1, "ctc_alpha_fwd: bad sizes B=%d T=%d Lp=%d Lmax=%d", B, T, Lp, max_label_len);
+  const int ns = pick_ns(2 * max_label_len + 1);
+  if (ns < 0) return set_error(MTASR_ERR_UNSUPPORTED, "ctc_alpha_fwd: label length %d > 255 not supported", max_label_len);
+  const int wpb = 4;
+  dim3 grid((B + wpb - 1) / wpb), block(32 * wpb);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long* y = reinterpret_cast<const long long*>(ys);
+  const long long* hl = reinterpret_cast<const long long*>(hlens);
+  const long long* yl = reinterpret_cast<const long long*>(ylens);
+  switch (ns) {
+    case 2: ctc_alpha_kernel<2><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_out, nll_raw); break;
+    case 4: ctc_alpha_kernel<4><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_out, nll_raw); break;
+    case 8: ctc_alpha_kernel<8><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_out, nll_raw); break;
+    default: ctc_alpha_kernel<16><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_out, nll_raw); break;
+  }
+  g_launches.fetch_add(1);
+  MTASR_CHECK_LAUNCH("ctc_alpha_fwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_ctc_beta_bwd(const float* glog, const float* lse, const int64_t* ys, const int64_t* hlens,
+                                  const int64_t* ylens, int32_t B, int32_t T, int32_t Lp, int32_t ys_ld,
+                                  int32_t max_label_len, const float* alpha_ws, const double* coff_ws,
+                                  const float* nll_raw, const float* gout, float* dG, float* rowscale, void* stream) {
+  MTASR_CHECK_ARG(glog && lse && hlens && ylens && alpha_ws && coff_ws && nll_raw && gout && dG && rowscale, "ctc_beta_bwd: null pointer");
+  MTASR_CHECK_ARG(B > 0 && T > 0 && Lp >= max_label_len + 1, "ctc_beta_bwd: bad sizes");
+  const int ns = pick_ns(2 * max_label_len + 1);
+  if (ns < 0) return set_error(MTASR_ERR_UNSUPPORTED, "ctc_beta_bwd: label length %d > 255 not supported", max_label_len);
+  const int wpb = 4;
+  dim3 grid((B + wpb - 1) / wpb), block(32 * wpb);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long* y = reinterpret_cast<const long long*>(ys);
+  const long long* hl = reinterpret_cast<const long long*>(hlens);
+  const long long* yl = reinterpret_cast<const long long*>(ylens);
+  switch (ns) {
+    case 2: ctc_beta_grad_kernel<2><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_raw, gout, dG, rowscale); break;
+    case 4: ctc_beta_grad_kernel<4><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_raw, gout, dG, rowscale); break;
+    case 8: ctc_beta_grad_kernel<8><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_raw, gout, dG, rowscale); break;
+    default: ctc_beta_grad_kernel<16><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_raw, gout, dG, rowscale); break;
+  }
+  g_launches.fetch_add(1);
+  MTASR_CHECK_LAUNCH("ctc_beta_bwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_lse_finalize(const float* part, int64_t rows, int32_t n_tiles, float* lse, int64_t* argmax,
+                                  void* stream) {
+  MTASR_CHECK_ARG(part && rows > 0 && n_tiles > 0 && (lse || argmax), "lse_finalize: bad arguments");
+  const int wpb = 8;
+  lse_finalize_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), 32 * wpb, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float4*>(part), static_cast<int>(rows), n_tiles, lse, reinterpret_cast<long long*>(argmax));
+  g_launches.fetch_add(1);
+  MTASR_CHECK_LAUNCH("lse_finalize");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_ctc_collapse(const int64_t* ids, int32_t B, int32_t T, int64_t blank_id, int64_t pad_id,
+                                  int64_t* out, int32_t* lengths, void* stream) {
+  MTASR_CHECK_ARG(ids && out && lengths && B > 0 && T > 0, "ctc_collapse: bad arguments");
+  const int wpb = 4;
+  ctc_collapse_kernel<<<(B + wpb - 1) / wpb, 32 * wpb, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(ids), B, T, blank_id, pad_id, reinterpret_cast<long long*>(out), lengths);
+  g_launches.fetch_add(1);
+  MTASR_CHECK_LAUNCH("ctc_collapse");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_ctc_gather_cols(const float* dense, const int64_t* ys, const int64_t* ylens, int32_t B, int32_t T,
+                                     int32_t V, int32_t Lp, int32_t ys_ld, int64_t blank, float* out, void* stream) {
+  MTASR_CHECK_ARG(dense && ylens && out && B > 0 && T > 0 && V > 0 && Lp > 0, "ctc_gather_cols: bad arguments");
+  const long long total = static_cast<long long>(B) * T * Lp;
+  ctc_gather_cols_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dense, reinterpret_cast<const long long*>(ys), reinterpret_cast<const long long*>(ylens), B, T, V, Lp, ys_ld, blank, out);
+  g_launches.fetch_add(1);
+  MTASR_CHECK_LAUNCH("ctc_gather_cols");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_ctc_scatter_cols(const float* src, const int64_t* ys, const int64_t* ylens, int32_t B, int32_t T,
+                                      int32_t V, int32_t Lp, int32_t ys_ld, int64_t blank, float* dense, void* stream) {
+  MTASR_CHECK_ARG(src && ylens && dense && B > 0 && T > 0 && V > 0 && Lp > 0, "ctc_scatter_cols: bad arguments");
+  const long long total = static_cast<long long>(B) * T * Lp;
+  ctc_scatter_cols_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<const long long*>(ys), reinterpret_cast<const long long*>(ylens), B, T, V, Lp, ys_ld, blank, dense);
+  g_launches.fetch_add(1);
+  MTASR_CHECK_LAUNCH("ctc_scatter_cols");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_ctc_gather_rows(const void* w_bf16, const float* bias, const int64_t* ys, const int64_t* ylens,
+                                     int32_t B, int32_t Lp, int32_t D, int32_t ys_ld, int64_t blank, void* wg_bf16,
+                                     float* bg, void* stream) {
+  MTASR_CHECK_ARG(w_bf16 && ylens && wg_bf16 && B > 0 && Lp > 0 && D > 0 && D % 8 == 0, "ctc_gather_rows: bad arguments");
+  ctc_gather_rows_kernel<<<B * Lp, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(w_bf16), bias, reinterpret_cast<const long long*>(ys),
+      reinterpret_cast<const long long*>(ylens), B, Lp, D, ys_ld, blank, reinterpret_cast<__nv_bfloat16*>(wg_bf16), bg);
+  g_launches.fetch_add(1);
+  MTASR_CHECK_LAUNCH("ctc_gather_rows");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_ctc_scatter_rows(const float* dwg, const float* dbg, const int64_t* ys, const int64_t* ylens,
+                                      int32_t B, int32_t Lp, int32_t D, int32_t ys_ld, int64_t blank, float* dw,
+                                      float* db, void* stream) {
+  MTASR_CHECK_ARG(dwg && ylens && dw && B > 0 && Lp > 0 && D > 0, "ctc_scatter_rows: bad arguments");
+  ctc_scatter_rows_kernel<<<B * Lp, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dwg, dbg, reinterpret_cast<const long long*>(ys), reinterpret_cast<const long long*>(ylens), B, Lp, D, ys_ld, blank, dw, db);
+  g_launches.fetch_add(1);
+  MTASR_CHECK_LAUNCH("ctc_scatter_rows");
+  return MTASR_OK;
+}

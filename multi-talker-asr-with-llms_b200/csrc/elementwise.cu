@@ -1,0 +1,477 @@
+// HBM-bound row kernels of the hot path: LayerNorm fwd/bwd (+GELU), casts, column sums, attention softmax with
+// the gated relative-position bias folded in (fwd/bwd), padding copies, GLU.  All use 128-bit accesses, one warp
+// per row, grid-stride over rows with grids sized to a multiple of the SM count.
+#include "common.cuh"
+
+namespace mtasr {
+
+static constexpr int MAXV = 32;  // per-lane register budget for one row: D <= 32*32 = 1024
+
+__device__ __forceinline__ void ld8(const void* base, int dtype, long long idx, float (&o)[8]) {
+  if (dtype == MTASR_DT_BF16) {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+    float2 t;
+    t = unpack_bf16x2(u.x); o[0] = t.x; o[1] = t.y;
+    t = unpack_bf16x2(u.y); o[2] = t.x; o[3] = t.y;
+    t = unpack_bf16x2(u.z); o[4] = t.x; o[5] = t.y;
+    t = unpack_bf16x2(u.w); o[6] = t.x; o[7] = t.y;
+  } else {
+    const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+}
+__device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ void st8_f32(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm fwd
+// y = LN(x) * gamma + beta, optional GELU after (conv feature layers, hf:726).  Outputs bf16 and/or fp32.
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, long long rows, int D, int post_gelu,
+                     __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  const int nchunk = D >> 3;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    float r[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int n = 0; n < MAXV / 8; ++n) {
+      const int c = lane + 32 * n;
+      float t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (c < nchunk) ld8(x, x_dtype, row * D + c * 8, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { r[n * 8 + j] = t[j]; s += t[j]; }
+    }
+    const float mean = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int n = 0; n < MAXV / 8; ++n) {
+      if (lane + 32 * n < nchunk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = r[n * 8 + j] - mean; q += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / D + eps);
+#pragma unroll
+    for (int n = 0; n < MAXV / 8; ++n) {
+      const int c = lane + 32 * n;
+      if (c < nchunk) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = (r[n * 8 + j] - mean) * rstd * gamma[c * 8 + j] + beta[c * 8 + j];
+          o[j] = post_gelu ? gelu_f(t) : t;
+        }
+        if (y_bf16) st8_bf16(y_bf16 + row * D + c * 8, o);
+        if (y_f32) st8_f32(y_f32 + row * D + c * 8, o);
+      }
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm bwd
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; optional + dres (residual-stream gradient).
+// dgamma / dbeta: per-lane register partials over the rows a warp visits, combined in smem, one atomicAdd per column
+// per CTA (gamma/beta grads must be zero-initialised by the caller).
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                     const float* __restrict__ dres, long long rows, int D, float* __restrict__ dx_f32,
+                     __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float sm[];  // 2 * D floats
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  const int nchunk = D >> 3;
+  float ag[MAXV], ab[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const float mu = mean[row], rs = rstd[row];
+    float g[MAXV], xh[MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int n = 0; n < MAXV / 8; ++n) {
+      const int c = lane + 32 * n;
+      if (c < nchunk) {
+        float a[8], b[8];
+        ld8(dy, dy_dtype, row * D + c * 8, a);
+        ld8(x, x_dtype, row * D + c * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xhat = (b[j] - mu) * rs;
+          const float gg = a[j] * gamma[c * 8 + j];
+          xh[n * 8 + j] = xhat;
+          g[n * 8 + j] = gg;
+          s1 += gg;
+          s2 += gg * xhat;
+          ag[n * 8 + j] += a[j] * xhat;
+          ab[n * 8 + j] += a[j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int n = 0; n < MAXV / 8; ++n) {
+      const int c = lane + 32 * n;
+      if (c < nchunk) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (g[n * 8 + j] - s1 - xh[n * 8 + j] * s2);
+        if (dres) {
+          float d[8];
+          ld8(dres, MTASR_DT_F32, row * D + c * 8, d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += d[j];
+        }
+        if (dx_f32) st8_f32(dx_f32 + row * D + c * 8, o);
+        if (dx_bf16) st8_bf16(dx_bf16 + row * D + c * 8, o);
+      }
+    }
+  }
+  if (dgamma || dbeta) {
+#pragma unroll
+    for (int n = 0; n < MAXV / 8; ++n) {
+      const int c = lane + 32 * n;
+      if (c < nchunk) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(&sm[c * 8 + j], ag[n * 8 + j]);
+          atomicAdd(&sm[D + c * 8 + j], ab[n * 8 + j]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      if (dgamma) atomicAdd(dgamma + i, sm[i]);
+      if (dbeta) atomicAdd(dbeta + i, sm[D + i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cast / colsum
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n8) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float t[8];
+    ld8(x, MTASR_DT_F32, i * 8, t);
+    st8_bf16(y + i * 8, t);
+  }
+}
+__global__ void cast_tail_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long start,
+                                 long long n) {
+  const long long i = start + threadIdx.x;
+  if (i < n) y[i] = f2bf(x[i]);
+}
+
+// out[n] (+)= sum_m x[m][n]; CTA = 32 columns x 8 row-lanes... each thread owns one column, strides rows.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ x, int dtype, long long M, int N, long long ld, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (col < N) {
+    for (long long m = static_cast<long long>(blockIdx.y) * 8 + ry; m < M; m += static_cast<long long>(gridDim.y) * 8) {
+      s += dtype == MTASR_DT_BF16 ? bf2f(reinterpret_cast<const __nv_bfloat16*>(x)[m * ld + col])
+                                  : reinterpret_cast<const float*>(x)[m * ld + col];
+    }
+  }
+  red[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][cx];
+    atomicAdd(out + col, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention softmax
+// P[b,h,q,k] = softmax_k( S[b,h,q,k]*scale + gate[b,h,q] * table[h, k-q+T-1] )  for k < klen[b], else 0.
+// Replaces the materialised (B*H,T,T) gated position bias of hf:167-180 + the masked softmax inside
+// F.multi_head_attention_forward (hf:206-228): the bias is Toeplitz (hf:243-271), so only table (H, 2T-1) and
+// gate (B,H,T) are read.  One warp per (b,h,q) row.
+__global__ void __launch_bounds__(256)
+attn_softmax_fwd_kernel(const float* __restrict__ S, const float* __restrict__ gate, const float* __restrict__ table,
+                        const int* __restrict__ klen, int B, int H, int T, int Tp, float scale,
+                        __nv_bfloat16* __restrict__ P) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  const long long rows = static_cast<long long>(B) * H * T;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const int q = static_cast<int>(row % T);
+    const int h = static_cast<int>((row / T) % H);
+    const int b = static_cast<int>(row / (static_cast<long long>(T) * H));
+    const int kl = klen ? min(klen[b], T) : T;
+    const float g = gate[row];
+    const float* srow = S + row * Tp;
+    const float* trow = table + static_cast<long long>(h) * (2 * T - 1) + (T - 1 - q);
+    __nv_bfloat16* prow = P + row * Tp;
+    float m = -INFINITY;
+    for (int k = lane; k < kl; k += 32) m = fmaxf(m, srow[k] * scale + g * trow[k]);
+    m = warp_max(m);
+    float s = 0.f;
+    for (int k = lane; k < kl; k += 32) s += __expf(srow[k] * scale + g * trow[k] - m);
+    s = warp_sum(s);
+    const float inv = kl > 0 ? 1.f / s : 0.f;
+    for (int k = lane; k < Tp; k += 32) {
+      float p = 0.f;
+      if (k < kl) p = __expf(srow[k] * scale + g * trow[k] - m) * inv;
+      prow[k] = f2bf(p);
+    }
+  }
+}
+
+// dS = P * (dP - sum_k P dP) (bf16 out, already multiplied by `scale` for the dQ/dK contractions);
+// dgate[b,h,q] = sum_k dZ * table; dtable[h, k-q+T-1] += dZ * gate (smem accumulation per CTA, CTAs are per-head).
+__global__ void __launch_bounds__(256)
+attn_softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict__ dP,
+                        const float* __restrict__ gate, const float* __restrict__ table, int B, int H, int T, int Tp,
+                        float scale, int rows_per_cta, __nv_bfloat16* __restrict__ dS, float* __restrict__ dgate,
+                        float* __restrict__ dtable) {
+  extern __shared__ float acc[];  // 2T-1
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int h = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * T - 1; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const long long bq0 = static_cast<long long>(blockIdx.x) * rows_per_cta;
+  const long long bq_end = min(bq0 + rows_per_cta, static_cast<long long>(B) * T);
+  const float* trow_h = table + static_cast<long long>(h) * (2 * T - 1);
+  for (long long bq = bq0 + warp; bq < bq_end; bq += nw) {
+    const int b = static_cast<int>(bq / T), q = static_cast<int>(bq % T);
+    const long long row = (static_cast<long long>(b) * H + h) * T + q;
+    const __nv_bfloat16* prow = P + row * Tp;
+    const float* dprow = dP + row * Tp;
+    __nv_bfloat16* dsrow = dS + row * Tp;
+    const float g = gate[row];
+    float dot = 0.f;
+    for (int k = lane; k < T; k += 32) dot += bf2f(prow[k]) * dprow[k];
+    dot = warp_sum(dot);
+    float dg = 0.f;
+    const float* trow = trow_h + (T - 1 - q);
+    float* arow = acc + (T - 1 - q);
+    for (int k = lane; k < Tp; k += 32) {
+      float dz = 0.f;
+      if (k < T) {
+        dz = bf2f(prow[k]) * (dprow[k] - dot);
+        dg += dz * trow[k];
+        atomicAdd(arow + k, dz * g);
+      }
+      dsrow[k] = f2bf(dz * scale);
+    }
+    dg = warp_sum(dg);
+    if (lane == 0) dgate[row] = dg;
+  }
+  __syncthreads();
+  float* dt = dtable + static_cast<long long>(h) * (2 * T - 1);
+  for (int i = threadIdx.x; i < 2 * T - 1; i += blockDim.x)
+    if (acc[i] != 0.f) atomicAdd(dt + i, acc[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ pad / GLU / mask
+// y[b][pad_l + t][:] = bf16(x[b][t][:]) with zero rows on both sides (pos-conv / adapter "same" padding).
+__global__ void pad_cast_kernel(const void* __restrict__ x, int x_dtype, int B, int T, int D, int pad_l, int Tpad,
+                                const int* __restrict__ vlen, __nv_bfloat16* __restrict__ y) {
+  const long long n8 = static_cast<long long>(B) * Tpad * (D >> 3);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % (D >> 3));
+    const long long bt = i / (D >> 3);
+    const int tp = static_cast<int>(bt % Tpad), b = static_cast<int>(bt / Tpad);
+    const int t = tp - pad_l;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (t >= 0 && t < T && (!vlen || t < vlen[b])) ld8(x, x_dtype, (static_cast<long long>(b) * T + t) * D + c * 8, v);
+    st8_bf16(y + i * 8, v);
+  }
+}
+
+// GLU over the channel halves of a channels-last row: y[r][c] = a[r][c] * sigmoid(a[r][C + c]).
+__global__ void glu_fwd_kernel(const void* __restrict__ x, int x_dtype, long long rows, int C,
+                               __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32) {
+  const long long n8 = rows * (C >> 3);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % (C >> 3));
+    const long long r = i / (C >> 3);
+    float a[8], g[8], o[8];
+    ld8(x, x_dtype, r * 2 * C + c * 8, a);
+    ld8(x, x_dtype, r * 2 * C + C + c * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = a[j] * sigmoid_f(g[j]);
+    if (y_bf16) st8_bf16(y_bf16 + r * C + c * 8, o);
+    if (y_f32) st8_f32(y_f32 + r * C + c * 8, o);
+  }
+}
+// dx[r][c] = dy * sig(g);  dx[r][C+c] = dy * a * sig(g) * (1 - sig(g))
+__global__ void glu_bwd_kernel(const void* __restrict__ x, int x_dtype, const void* __restrict__ dy, int dy_dtype,
+                               long long rows, int C, __nv_bfloat16* __restrict__ dx) {
+  const long long n8 = rows * (C >> 3);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % (C >> 3));
+    const long long r = i / (C >> 3);
+    float a[8], g[8], d[8], o1[8], o2[8];
+    ld8(x, x_dtype, r * 2 * C + c * 8, a);
+    ld8(x, x_dtype, r * 2 * C + C + c * 8, g);
+    ld8(dy, dy_dtype, r * C + c * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float s = sigmoid_f(g[j]);
+      o1[j] = d[j] * s;
+      o2[j] = d[j] * a[j] * s * (1.f - s);
+    }
+    st8_bf16(dx + r * 2 * C + c * 8, o1);
+    st8_bf16(dx + r * 2 * C + C + c * 8, o2);
+  }
+}
+
+static int grid_for(long long work_items, int per_block) {
+  long long g = (work_items + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(num_sms()) * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace mtasr
+
+using namespace mtasr;
+
+extern "C" int mtasr_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, const float* beta, float eps,
+                                   int64_t rows, int32_t D, int32_t post_gelu, void* y_bf16, float* y_f32, float* mean,
+                                   float* rstd, void* stream) {
+  MTASR_CHECK_ARG(x && gamma && beta && rows > 0 && (y_bf16 || y_f32), "layernorm_fwd: bad arguments");
+  MTASR_CHECK_ARG(D % 8 == 0 && D <= 32 * MAXV, "layernorm_fwd: D=%d must be a multiple of 8 and <= 1024", D);
+  layernorm_fwd_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, x_dtype, gamma, beta, eps, rows, D, post_gelu, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32, mean, rstd);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("layernorm_fwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
+                                   const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D,
+                                   float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, void* stream) {
+  MTASR_CHECK_ARG(dy && x && mean && rstd && gamma && rows > 0 && (dx_f32 || dx_bf16 || dgamma), "layernorm_bwd: bad arguments");
+  MTASR_CHECK_ARG(D % 8 == 0 && D <= 32 * MAXV, "layernorm_bwd: D=%d must be a multiple of 8 and <= 1024", D);
+  int grid = grid_for(rows, 8);
+  if (grid > 2 * num_sms()) grid = 2 * num_sms();
+  layernorm_bwd_kernel<<<grid, 256, 2 * D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres, rows, D, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16),
+      dgamma, dbeta);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("layernorm_bwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
+  MTASR_CHECK_ARG(x && y && n > 0, "cast_f32_bf16: bad arguments");
+  MTASR_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "cast: unaligned pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n8 = n / 8;
+  if (n8 > 0) {
+    cast_f32_bf16_kernel<<<grid_for(n8, 256), 256, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n8);
+    MTASR_COUNT_LAUNCH();
+  }
+  if (n8 * 8 < n) {
+    cast_tail_kernel<<<1, 32, 0, st>>>(x, reinterpret_cast<__nv_bfloat16*>(y), n8 * 8, n);
+    MTASR_COUNT_LAUNCH();
+  }
+  MTASR_CHECK_LAUNCH("cast_f32_bf16");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_colsum(const void* x, int32_t dtype, int64_t M, int32_t N, int64_t ld, float* out, void* stream) {
+  MTASR_CHECK_ARG(x && out && M > 0 && N > 0 && ld >= N, "colsum: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(out, 0, sizeof(float) * N, st) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "colsum: memset failed");
+  int gy = static_cast<int>((M + 255) / 256);
+  const int gx = (N + 31) / 32;
+  const int cap = (num_sms() * 8 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  colsum_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, dtype, M, N, ld, out);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("colsum");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_attn_softmax_fwd(const float* S, const float* gate, const float* table, const int32_t* klen,
+                                      int32_t B, int32_t H, int32_t T, int32_t Tp, float scale, void* P, void* stream) {
+  MTASR_CHECK_ARG(S && gate && table && P && B > 0 && H > 0 && T > 0 && Tp >= T, "attn_softmax_fwd: bad arguments");
+  const long long rows = static_cast<long long>(B) * H * T;
+  attn_softmax_fwd_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      S, gate, table, klen, B, H, T, Tp, scale, reinterpret_cast<__nv_bfloat16*>(P));
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("attn_softmax_fwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_attn_softmax_bwd(const void* P, const float* dP, const float* gate, const float* table, int32_t B,
+                                      int32_t H, int32_t T, int32_t Tp, float scale, void* dS, float* dgate,
+                                      float* dtable, void* stream) {
+  MTASR_CHECK_ARG(P && dP && gate && table && dS && dgate && dtable && B > 0 && H > 0 && T > 0 && Tp >= T, "attn_softmax_bwd: bad arguments");
+  const int rows_per_cta = 64;
+  const long long bq = static_cast<long long>(B) * T;
+  dim3 grid(static_cast<unsigned>((bq + rows_per_cta - 1) / rows_per_cta), H);
+  const size_t smem = sizeof(float) * (2 * T - 1);
+  MTASR_CHECK_ARG(smem <= 48 * 1024, "attn_softmax_bwd: T=%d too long for the smem table accumulator", T);
+  attn_softmax_bwd_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(P), dP, gate, table, B, H, T, Tp, scale, rows_per_cta,
+      reinterpret_cast<__nv_bfloat16*>(dS), dgate, dtable);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("attn_softmax_bwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_pad_cast(const void* x, int32_t x_dtype, int32_t B, int32_t T, int32_t D, int32_t pad_l,
+                              int32_t Tpad, const int32_t* vlen, void* y, void* stream) {
+  MTASR_CHECK_ARG(x && y && B > 0 && T > 0 && D % 8 == 0 && Tpad >= T + pad_l, "pad_cast: bad arguments");
+  const long long n8 = static_cast<long long>(B) * Tpad * (D >> 3);
+  pad_cast_kernel<<<grid_for(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, x_dtype, B, T, D, pad_l, Tpad, vlen, reinterpret_cast<__nv_bfloat16*>(y));
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("pad_cast");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_glu_fwd(const void* x, int32_t x_dtype, int64_t rows, int32_t C, void* y_bf16, float* y_f32,
+                             void* stream) {
+  MTASR_CHECK_ARG(x && (y_bf16 || y_f32) && rows > 0 && C % 8 == 0, "glu_fwd: bad arguments");
+  glu_fwd_kernel<<<grid_for(rows * (C >> 3), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, x_dtype, rows, C, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("glu_fwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_glu_bwd(const void* x, int32_t x_dtype, const void* dy, int32_t dy_dtype, int64_t rows, int32_t C,
+                             void* dx_bf16, void* stream) {
+  MTASR_CHECK_ARG(x && dy && dx_bf16 && rows > 0 && C % 8 == 0, "glu_bwd: bad arguments");
+  glu_bwd_kernel<<<grid_for(rows * (C >> 3), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, x_dtype, dy, dy_dtype, rows, C, reinterpret_cast<__nv_bfloat16*>(dx_bf16));
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("glu_bwd");
+  return MTASR_OK;
+}

@@ -1,0 +1,330 @@
+"""Tensor-level wrappers over the C ABI (include/mtasr.h).  torch is used for device memory and streams only.
+
+Every function enqueues hand-written sm_100a kernels on torch's current CUDA stream and returns torch tensors that
+own the output buffers.  Nothing here falls back to torch arithmetic: without a CUDA device or without libmtasr.so
+the calls raise.
+"""
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import ctypes as C
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, check
+
+BF16, F32 = 0, 1
+ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_BWD, ACT_RELU_BWD = 0, 1, 2, 3, 4
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return BF16
+    if t.dtype == torch.float32:
+        return F32
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor], offset: int = 0) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise _lib.MtasrError("mtasr kernels need CUDA tensors (there is no CPU fallback)")
+    return t.data_ptr() + offset * t.element_size()
+
+
+def launch_count() -> int:
+    return int(_lib.load().mtasr_launch_count())
+
+
+# ----------------------------------------------------------------------------------------------------------- GEMM
+@dataclass
+class Operand:
+    """One GEMM operand view: element strides into `t` (bf16).  major 0 = K-major, 1 = MN-major."""
+    t: torch.Tensor
+    ld: int
+    major: int = 0
+    sb0: int = 0
+    sb1: int = 0
+    offset: int = 0
+    inner: int = 0      # A only: channels per tap for implicit conv
+    phase: int = 1      # A only: conv stride
+    rows: int = 0
+
+
+@dataclass
+class Out:
+    t: torch.Tensor
+    ld: int
+    sb0: int = 0
+    sb1: int = 0
+    offset: int = 0
+
+
+def gemm(a: Operand, b: Operand, M: int, N: int, K: int, out: Optional[Out], *, batch: Tuple[int, int] = (1, 1),
+         bias: Optional[torch.Tensor] = None, bias_sb0: int = 0, act: int = ACT_NONE, residual: Optional[Out] = None,
+         aux: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False, mode: int = 0,
+         row_vec: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
+         lse_part: Optional[torch.Tensor] = None, block_n: int = 0) -> None:
+    """C = epilogue(alpha * A @ B^T) on the tcgen05 kernel (csrc/gemm.cu); see include/mtasr.h for the contract."""
+    lib = _lib.load()
+    if a.t.dtype != torch.bfloat16 or b.t.dtype != torch.bfloat16:
+        raise TypeError("gemm operands must be bf16")
+    d = GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.batch0, d.batch1 = batch
+    d.a_major, d.b_major = a.major, b.major
+    d.block_n = block_n
+    d.a = _p(a.t, a.offset)
+    d.a_ld, d.a_sb0, d.a_sb1 = a.ld, a.sb0, a.sb1
+    d.a_inner, d.a_phase, d.a_rows = a.inner, a.phase, a.rows
+    d.b = _p(b.t, b.offset)
+    d.b_ld, d.b_sb0, d.b_sb1, d.b_rows = b.ld, b.sb0, b.sb1, b.rows
+    if out is not None:
+        d.c = _p(out.t, out.offset)
+        d.c_dtype = _dt(out.t)
+        d.c_ld, d.c_sb0, d.c_sb1 = out.ld, out.sb0, out.sb1
+    if aux is not None:
+        if aux.dtype != torch.bfloat16:
+            raise TypeError("aux must be bf16")
+        d.aux = _p(aux)
+    if bias is not None:
+        if bias.dtype != torch.float32:
+            raise TypeError("bias must be fp32")
+        d.bias = _p(bias)
+        d.bias_sb0 = bias_sb0
+    if residual is not None:
+        d.residual = _p(residual.t, residual.offset)
+        d.res_dtype = _dt(residual.t)
+        d.r_ld, d.r_sb0, d.r_sb1 = residual.ld, residual.sb0, residual.sb1
+    d.act = act
+    d.alpha = alpha
+    d.accumulate = 1 if accumulate else 0
+    d.mode = mode
+    d.row_vec = _p(row_vec)
+    d.row_scale = _p(row_scale)
+    d.lse_part = _p(lse_part)
+    check(lib.mtasr_gemm_bf16(C.byref(d), _stream()), "mtasr_gemm_bf16")
+
+
+def gemm_n_tiles(N: int, block_n: int = 0) -> int:
+    return int(_lib.load().mtasr_gemm_n_tiles(N, block_n))
+
+
+def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
+               residual: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, want_aux: bool = False,
+               out: Optional[torch.Tensor] = None):
+    """y[M,N] = act(x[M,K] @ w[N,K]^T + bias) (+ residual).  Returns y (and the bf16 pre-activation if want_aux)."""
+    M, K = x.shape
+    N = w.shape[0]
+    y = out if out is not None else torch.empty(M, N, device=x.device, dtype=out_dtype)
+    aux = torch.empty(M, N, device=x.device, dtype=torch.bfloat16) if want_aux else None
+    gemm(Operand(x, x.stride(0)), Operand(w, w.stride(0)), M, N, K, Out(y, y.stride(0)), bias=bias, act=act,
+         residual=None if residual is None else Out(residual, residual.stride(0)), aux=aux)
+    return (y, aux) if want_aux else y
+
+
+def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, out_dtype=torch.bfloat16, act: int = ACT_NONE,
+                 act_src: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+                 accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx[M,K] = dy[M,N] @ w[N,K]; optional fused activation backward (act 3/4 with act_src) or residual add."""
+    M, N = dy.shape
+    K = w.shape[1]
+    dx = accumulate_into if accumulate_into is not None else torch.empty(M, K, device=dy.device, dtype=out_dtype)
+    res = None
+    if act in (ACT_GELU_BWD, ACT_RELU_BWD):
+        res = Out(act_src, act_src.stride(0))
+    elif residual is not None:
+        res = Out(residual, residual.stride(0))
+    gemm(Operand(dy, dy.stride(0)), Operand(w, w.stride(0), major=1), M, K, N, Out(dx, dx.stride(0)), act=act,
+         residual=res, accumulate=accumulate_into is not None)
+    return dx
+
+
+def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, *, accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dw[N,K] (fp32) = dy[M,N]^T @ x[M,K]  (both operands MN-major: no transposes are materialised)."""
+    M, N = dy.shape
+    K = x.shape[1]
+    dw = accumulate_into if accumulate_into is not None else torch.empty(N, K, device=dy.device, dtype=torch.float32)
+    gemm(Operand(dy, dy.stride(0), major=1), Operand(x, x.stride(0), major=1), N, K, M, Out(dw, dw.stride(0)),
+         accumulate=accumulate_into is not None)
+    return dw
+
+
+# ----------------------------------------------------------------------------------------------------------- rows
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, *, out_bf16: bool = True,
+                  out_f32: bool = False, post_gelu: bool = False, save_stats: bool = True):
+    D = x.shape[-1]
+    rows = x.numel() // D
+    x = x.contiguous()
+    yb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    yf = torch.empty(x.shape, device=x.device, dtype=torch.float32) if out_f32 else None
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
+    check(_lib.load().mtasr_layernorm_fwd(_p(x), _dt(x), _p(gamma), _p(beta), eps, rows, D, int(post_gelu), _p(yb), _p(yf),
+                                          _p(mean), _p(rstd), _stream()), "mtasr_layernorm_fwd")
+    return yb, yf, mean, rstd
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor, *,
+                  dres: Optional[torch.Tensor] = None, want_f32: bool = True, want_bf16: bool = False,
+                  want_param_grads: bool = True):
+    D = x.shape[-1]
+    rows = x.numel() // D
+    dy = dy.contiguous()
+    dxf = torch.empty(x.shape, device=x.device, dtype=torch.float32) if want_f32 else None
+    dxb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    dg = torch.zeros(D, device=x.device, dtype=torch.float32) if want_param_grads else None
+    db = torch.zeros(D, device=x.device, dtype=torch.float32) if want_param_grads else None
+    check(_lib.load().mtasr_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma), _p(dres), rows, D,
+                                          _p(dxf), _p(dxb), _p(dg), _p(db), _stream()), "mtasr_layernorm_bwd")
+    return dxf, dxb, dg, db
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype == torch.bfloat16:
+        return x
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    if x.numel():
+        check(_lib.load().mtasr_cast_f32_bf16(_p(x), _p(y), x.numel(), _stream()), "mtasr_cast_f32_bf16")
+    return y
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    M, N = x.shape
+    out = torch.empty(N, device=x.device, dtype=torch.float32)
+    check(_lib.load().mtasr_colsum(_p(x), _dt(x), M, N, x.stride(0), _p(out), _stream()), "mtasr_colsum")
+    return out
+
+
+def attn_softmax_fwd(S, gate, table, klen, B, H, T, Tp, scale):
+    P = torch.empty(B, H, T, Tp, device=S.device, dtype=torch.bfloat16)
+    check(_lib.load().mtasr_attn_softmax_fwd(_p(S), _p(gate), _p(table), _p(klen), B, H, T, Tp, scale, _p(P), _stream()),
+          "mtasr_attn_softmax_fwd")
+    return P
+
+
+def attn_softmax_bwd(P, dP, gate, table, B, H, T, Tp, scale):
+    dS = torch.empty(B, H, T, Tp, device=P.device, dtype=torch.bfloat16)
+    dgate = torch.empty(B, H, T, device=P.device, dtype=torch.float32)
+    dtable = torch.zeros(H, 2 * T - 1, device=P.device, dtype=torch.float32)
+    check(_lib.load().mtasr_attn_softmax_bwd(_p(P), _p(dP), _p(gate), _p(table), B, H, T, Tp, scale, _p(dS), _p(dgate),
+                                             _p(dtable), _stream()), "mtasr_attn_softmax_bwd")
+    return dS, dgate, dtable
+
+
+def pad_cast(x: torch.Tensor, pad_l: int, Tpad: int, vlen: Optional[torch.Tensor] = None) -> torch.Tensor:
+    B, T, D = x.shape
+    x = x.contiguous()
+    y = torch.empty(B, Tpad, D, device=x.device, dtype=torch.bfloat16)
+    check(_lib.load().mtasr_pad_cast(_p(x), _dt(x), B, T, D, pad_l, Tpad, _p(vlen), _p(y), _stream()), "mtasr_pad_cast")
+    return y
+
+
+def glu_fwd(x: torch.Tensor, *, out_f32: bool = False):
+    C2 = x.shape[-1]
+    Cc = C2 // 2
+    rows = x.numel() // C2
+    x = x.contiguous()
+    yb = torch.empty(*x.shape[:-1], Cc, device=x.device, dtype=torch.bfloat16)
+    yf = torch.empty(*x.shape[:-1], Cc, device=x.device, dtype=torch.float32) if out_f32 else None
+    check(_lib.load().mtasr_glu_fwd(_p(x), _dt(x), rows, Cc, _p(yb), _p(yf), _stream()), "mtasr_glu_fwd")
+    return yb, yf
+
+
+def glu_bwd(x: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    C2 = x.shape[-1]
+    rows = x.numel() // C2
+    dy = dy.contiguous()
+    dx = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    check(_lib.load().mtasr_glu_bwd(_p(x), _dt(x), _p(dy), _dt(dy), rows, C2 // 2, _p(dx), _stream()), "mtasr_glu_bwd")
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------------------- CTC
+def ctc_state_pad(max_label_len: int) -> int:
+    sp = int(_lib.load().mtasr_ctc_state_pad(max_label_len))
+    if sp < 0:
+        raise _lib.MtasrError(f"CTC label length {max_label_len} > 255 is not supported by the warp-per-utterance kernel")
+    return sp
+
+
+def ctc_alpha_fwd(glog, lse, ys, hlens, ylens, max_label_len):
+    B, T, Lp = glog.shape
+    sp = ctc_state_pad(max_label_len)
+    alpha = torch.empty(B, T, sp, device=glog.device, dtype=torch.float32)
+    coff = torch.empty(B, T, device=glog.device, dtype=torch.float64)
+    nll = torch.empty(B, device=glog.device, dtype=torch.float32)
+    nll_raw = torch.empty(B, device=glog.device, dtype=torch.float32)
+    ys_ld = ys.stride(0) if ys.numel() else 0
+    check(_lib.load().mtasr_ctc_alpha_fwd(_p(glog), _p(lse), _p(ys) if ys.numel() else None, _p(hlens), _p(ylens), B, T, Lp,
+                                          ys_ld, max_label_len, _p(alpha), _p(coff), _p(nll), _p(nll_raw), _stream()),
+          "mtasr_ctc_alpha_fwd")
+    return nll, nll_raw, alpha, coff
+
+
+def ctc_beta_bwd(glog, lse, ys, hlens, ylens, max_label_len, alpha, coff, nll_raw, gout):
+    B, T, Lp = glog.shape
+    dG = torch.empty(B, T, Lp, device=glog.device, dtype=torch.float32)
+    rowscale = torch.empty(B, T, device=glog.device, dtype=torch.float32)
+    ys_ld = ys.stride(0) if ys.numel() else 0
+    check(_lib.load().mtasr_ctc_beta_bwd(_p(glog), _p(lse), _p(ys) if ys.numel() else None, _p(hlens), _p(ylens), B, T, Lp,
+                                         ys_ld, max_label_len, _p(alpha), _p(coff), _p(nll_raw), _p(gout), _p(dG),
+                                         _p(rowscale), _stream()), "mtasr_ctc_beta_bwd")
+    return dG, rowscale
+
+
+def lse_finalize(part: torch.Tensor, rows: int, n_tiles: int, want_lse=True, want_argmax=False):
+    lse = torch.empty(rows, device=part.device, dtype=torch.float32) if want_lse else None
+    am = torch.empty(rows, device=part.device, dtype=torch.int64) if want_argmax else None
+    check(_lib.load().mtasr_lse_finalize(_p(part), rows, n_tiles, _p(lse), _p(am), _stream()), "mtasr_lse_finalize")
+    return lse, am
+
+
+def ctc_collapse(ids: torch.Tensor, blank_id: int, pad_id: int):
+    B, T = ids.shape
+    ids = ids.contiguous()
+    out = torch.empty(B, T, device=ids.device, dtype=torch.int64)
+    lens = torch.empty(B, device=ids.device, dtype=torch.int32)
+    check(_lib.load().mtasr_ctc_collapse(_p(ids), B, T, blank_id, pad_id, _p(out), _p(lens), _stream()), "mtasr_ctc_collapse")
+    return out, lens
+
+
+def ctc_gather_cols(dense, ys, ylens, Lp, blank):
+    B, T, V = dense.shape
+    out = torch.empty(B, T, Lp, device=dense.device, dtype=torch.float32)
+    ys_ld = ys.stride(0) if ys.numel() else 0
+    check(_lib.load().mtasr_ctc_gather_cols(_p(dense), _p(ys) if ys.numel() else None, _p(ylens), B, T, V, Lp, ys_ld, blank,
+                                            _p(out), _stream()), "mtasr_ctc_gather_cols")
+    return out
+
+
+def ctc_scatter_cols(src, ys, ylens, dense, blank):
+    B, T, Lp = src.shape
+    V = dense.shape[-1]
+    ys_ld = ys.stride(0) if ys.numel() else 0
+    check(_lib.load().mtasr_ctc_scatter_cols(_p(src), _p(ys) if ys.numel() else None, _p(ylens), B, T, V, Lp, ys_ld, blank,
+                                             _p(dense), _stream()), "mtasr_ctc_scatter_cols")
+
+
+def ctc_gather_rows(w_bf16, bias, ys, ylens, Lp, blank):
+    B = ylens.numel()
+    D = w_bf16.shape[1]
+    wg = torch.empty(B, Lp, D, device=w_bf16.device, dtype=torch.bfloat16)
+    bg = torch.empty(B, Lp, device=w_bf16.device, dtype=torch.float32)
+    ys_ld = ys.stride(0) if ys.numel() else 0
+    check(_lib.load().mtasr_ctc_gather_rows(_p(w_bf16), _p(bias), _p(ys) if ys.numel() else None, _p(ylens), B, Lp, D, ys_ld,
+                                            blank, _p(wg), _p(bg), _stream()), "mtasr_ctc_gather_rows")
+    return wg, bg
+
+
+def ctc_scatter_rows(dwg, dbg, ys, ylens, blank, dw, db):
+    B, Lp, D = dwg.shape
+    ys_ld = ys.stride(0) if ys.numel() else 0
+    check(_lib.load().mtasr_ctc_scatter_rows(_p(dwg), _p(dbg), _p(ys) if ys.numel() else None, _p(ylens), B, Lp, D, ys_ld,
+                                             blank, _p(dw), _p(db), _stream()), "mtasr_ctc_scatter_rows")

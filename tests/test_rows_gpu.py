@@ -1,0 +1,92 @@
+"""HBM-bound row kernels vs plain PyTorch fp32 references."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20)).item()
+
+
+@pytest.mark.parametrize("D", [512, 896, 1024, 128, 64])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_layernorm_fwd_bwd(cuda, D, dt):
+    from mtasr_b200 import kernels as Kn
+    torch.manual_seed(0)
+    rows = 777
+    x = (torch.randn(rows, D, device=cuda) * 2 + 0.5).to(dt)
+    gamma, beta = torch.randn(D, device=cuda), torch.randn(D, device=cuda)
+    yb, yf, mean, rstd = Kn.layernorm_fwd(x, gamma, beta, 1e-5, out_bf16=True, out_f32=True)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (D,), gr, br, 1e-5)
+    assert _rel(yf, ref) < 1e-5 and _rel(yb, ref) < 5e-3
+    dy = torch.randn(rows, D, device=cuda)
+    dres = torch.randn(rows, D, device=cuda)
+    dxf, dxb, dg, db = Kn.layernorm_bwd(dy, x, mean, rstd, gamma, dres=dres, want_bf16=True)
+    ref.backward(dy)
+    assert _rel(dxf, xr.grad + dres) < 1e-5 and _rel(dxb, xr.grad + dres) < 5e-3
+    assert _rel(dg, gr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
+    g2, _, _, _ = Kn.layernorm_fwd(x, gamma, beta, 1e-5, post_gelu=True)
+    assert _rel(g2, F.gelu(ref.detach())) < 5e-3
+
+
+def test_cast_colsum_pad_glu(cuda):
+    from mtasr_b200 import kernels as Kn
+    torch.manual_seed(1)
+    x = torch.randn(1003, device=cuda)
+    assert torch.equal(Kn.cast_bf16(x), x.to(torch.bfloat16))
+    m = torch.randn(999, 200, device=cuda)
+    assert _rel(Kn.colsum(m), m.sum(0)) < 1e-5
+    mb = m.to(torch.bfloat16)
+    assert _rel(Kn.colsum(mb), mb.float().sum(0)) < 1e-5
+    a = torch.randn(2, 50, 64, device=cuda)
+    vlen = torch.tensor([50, 31], device=cuda, dtype=torch.int32)
+    p = Kn.pad_cast(a, 8, 66, vlen)
+    ref = torch.zeros(2, 66, 64, device=cuda)
+    ref[0, 8:58] = a[0]; ref[1, 8:39] = a[1, :31]
+    assert torch.equal(p, ref.to(torch.bfloat16))
+    z = torch.randn(3, 40, 256, device=cuda)
+    yb, yf = Kn.glu_fwd(z, out_f32=True)
+    assert _rel(yf, F.glu(z, -1)) < 1e-6
+    zr = z.clone().requires_grad_(True)
+    dy = torch.randn(3, 40, 128, device=cuda)
+    F.glu(zr, -1).backward(dy)
+    assert _rel(Kn.glu_bwd(z, dy), zr.grad) < 5e-3
+
+
+@pytest.mark.parametrize("B,H,T", [(2, 3, 197), (1, 2, 64), (2, 2, 499)])
+def test_attn_softmax(cuda, B, H, T):
+    from mtasr_b200 import kernels as Kn
+    torch.manual_seed(2)
+    Tp = (T + 7) // 8 * 8
+    S = torch.randn(B, H, T, Tp, device=cuda) * 3
+    gate = torch.rand(B, H, T, device=cuda) * 2
+    table = torch.randn(H, 2 * T - 1, device=cuda)
+    klen = torch.tensor([T] + [max(1, T - 13)] * (B - 1), device=cuda, dtype=torch.int32)
+    scale = 0.125
+    P = Kn.attn_softmax_fwd(S, gate, table, klen, B, H, T, Tp, scale)
+    idx = (torch.arange(T, device=cuda)[None, :] - torch.arange(T, device=cuda)[:, None]) + T - 1      # [q,k]
+    Sr = S[..., :T].clone().requires_grad_(True)
+    gr = gate.clone().requires_grad_(True)
+    tr = table.clone().requires_grad_(True)
+    bias = gr[..., None] * tr[:, idx][None]
+    z = Sr * scale + bias
+    kmask = torch.arange(T, device=cuda)[None, :] >= klen[:, None]
+    z = z.masked_fill(kmask[:, None, None, :], float("-inf"))
+    ref = torch.softmax(z, -1)
+    assert _rel(P[..., :T], ref) < 5e-3
+    assert (P[..., T:] == 0).all()
+    dP = torch.randn(B, H, T, Tp, device=cuda)
+    Pf = P.float()[..., :T]
+    dS, dgate, dtable = Kn.attn_softmax_bwd(P, dP, gate, table, B, H, T, Tp, scale)
+    # reference backward evaluated at the SAME (bf16-rounded) probabilities
+    dot = (Pf * dP[..., :T]).sum(-1, keepdim=True)
+    dz = Pf * (dP[..., :T] - dot)
+    assert _rel(dS[..., :T], dz * scale) < 5e-3
+    assert _rel(dgate, (dz * table[:, idx][None]).sum(-1)) < 1e-4
+    dt_ref = torch.zeros_like(table)
+    dt_ref.index_add_(1, idx.reshape(-1), (dz * gate[..., None]).sum(0).reshape(H, -1))
+    assert _rel(dtable, dt_ref) < 1e-4
