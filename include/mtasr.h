@@ -107,15 +107,15 @@ int mtasr_gemm_n_tiles(int32_t N, int32_t block_n);
  */
 /* padded state count SP = 32*NS used to size alpha_ws (B*T*SP f32); -1 if max_label_len unsupported */
 int mtasr_ctc_state_pad(int32_t max_label_len);
-/* alpha recursion: nll_out (B) = per-utterance loss with infeasible rows zeroed, nll_raw (B) keeps +inf. */
+/* alpha recursion: nll_out (B) = per-utterance loss with infeasible rows zeroed, nll_raw (B) f64 keeps +inf. */
 int mtasr_ctc_alpha_fwd(const float* glog, const float* lse, const int64_t* ys, const int64_t* hlens,
                         const int64_t* ylens, int32_t B, int32_t T, int32_t Lp, int32_t ys_ld, int32_t max_label_len,
-                        float* alpha_ws, double* coff_ws, float* nll_out, float* nll_raw, void* stream);
+                        float* alpha_ws, double* coff_ws, float* nll_out, double* nll_raw, void* stream);
 /* beta recursion + gradient: dG (B,T,Lp) = gout[b] * d nll_b / d lp(t, column) (= -gout*occupancy),
  * rowscale (B,T) = gout[b] on valid frames of feasible utterances else 0 (scales the dense softmax term). */
 int mtasr_ctc_beta_bwd(const float* glog, const float* lse, const int64_t* ys, const int64_t* hlens,
                        const int64_t* ylens, int32_t B, int32_t T, int32_t Lp, int32_t ys_ld, int32_t max_label_len,
-                       const float* alpha_ws, const double* coff_ws, const float* nll_raw, const float* gout,
+                       const float* alpha_ws, const double* coff_ws, const double* nll_raw, const float* gout,
                        float* dG, float* rowscale, void* stream);
 /* Combine the mode-1 GEMM partials: lse (rows) f32 and/or argmax (rows) i64 (first maximal index, like
  * torch.argmax -- ref:models/ctc.py:190). */
@@ -165,6 +165,34 @@ int mtasr_pad_cast(const void* x, int32_t x_dtype, int32_t B, int32_t T, int32_t
 int mtasr_glu_fwd(const void* x, int32_t x_dtype, int64_t rows, int32_t C, void* y_bf16, float* y_f32, void* stream);
 int mtasr_glu_bwd(const void* x, int32_t x_dtype, const void* dy, int32_t dy_dtype, int64_t rows, int32_t C,
                   void* dx_bf16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Persistent LSTM recurrence (ref:models/separator.py:6-59; gate order i,f,g,o; h0 = c0 = 0).
+ * xg (B,T,4Hs) f32 = x_t W_ih^T + b for every step (one batched GEMM beforehand); whh (4Hs, ldw) bf16 is the
+ * recurrent half W[:, in:] with row stride ldw.  B <= 64, Hs % 16 == 0, Hs/8 <= #SMs (cooperative launch).
+ * Outputs: h (B,T,Hs) bf16 (+ optional f32), c (B,T,Hs) f32, gates (B,T,4Hs) f32 activations (saved for BPTT).
+ * `barrier` is a 4-byte device scratch word.  Backward: dgates (B,T,4Hs) bf16 = gradient wrt the gate
+ * pre-activations; dx / dW / db follow as GEMMs / column sums over it.
+ */
+int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw, int32_t B, int32_t T, int32_t Hs, void* h_bf16,
+                   float* h_f32, float* c_all, float* gates, uint32_t* barrier, void* stream);
+int mtasr_lstm_bwd(const float* dh_out, const float* gates, const float* c_all, const void* whh_bf16, int32_t ldw,
+                   int32_t B, int32_t T, int32_t Hs, void* dgates_bf16, uint32_t* barrier, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Feature-extractor layer 0 (hf:709-751): conv1d(1 -> C0, k, stride) on the waveform x (B,S) f32, weights (C0,1,k)
+ * f32.  mode 1 ("layer" norm, WavLM-Large): + LayerNorm over channels + GELU -> y_bf16 (B,L0,C0) channels-last.
+ * mode 0 ("group" norm, WavLM-Base+): raw conv (+bias) -> y_f32 (B,L0,C0); follow with mtasr_groupnorm_gelu, which
+ * normalises every (b, channel) over time (GroupNorm with C groups), applies the affine and GELU -> bf16.
+ */
+int mtasr_conv0_fwd(const float* x, const float* w, const float* bias, const float* gamma, const float* beta, float eps,
+                    int32_t B, int32_t S, int32_t C0, int32_t k, int32_t stride, int32_t mode, void* y_bf16, float* y_f32,
+                    void* stream);
+int mtasr_groupnorm_gelu(const float* x, const float* gamma, const float* beta, float eps, int32_t B, int32_t L, int32_t C,
+                         float* mean_ws, float* rstd_ws, void* y_bf16, void* stream);
+/* du = dy * act'(.) as bf16: act 3 = GELU from the saved pre-activation, act 4 = ReLU from the saved output. */
+int mtasr_act_bwd(const void* dy, int32_t dy_dtype, const void* src_bf16, int32_t act, int64_t n, void* du_bf16,
+                  void* stream);
 
 #ifdef __cplusplus
 }

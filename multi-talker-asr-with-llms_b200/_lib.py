@@ -68,6 +68,11 @@ SIGNATURES = {
     "mtasr_attn_softmax_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P, _P, _P, _P]),
     "mtasr_pad_cast": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "mtasr_glu_fwd": (C.c_int, [_P, _I32, _I64, _I32, _P, _P, _P]),
+    "mtasr_conv0_fwd": (C.c_int, [_P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "mtasr_groupnorm_gelu": (C.c_int, [_P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "mtasr_act_bwd": (C.c_int, [_P, _I32, _P, _I32, _I64, _P, _P]),
+    "mtasr_lstm_fwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "mtasr_lstm_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "mtasr_glu_bwd": (C.c_int, [_P, _I32, _P, _I32, _I64, _I32, _P, _P]),
 }
 

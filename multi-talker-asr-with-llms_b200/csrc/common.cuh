@@ -67,7 +67,7 @@ __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __ex
 __device__ __forceinline__ float logaddexp_f(float a, float b) {
   const float m = fmaxf(a, b);
   if (m == -INFINITY) return -INFINITY;
-  return m + log1pf(__expf(fminf(a, b) - m));
+  return m + log1pf(expf(fminf(a, b) - m));
 }
 
 // Block-wide sum for blockDim.x <= 1024 (result broadcast to all threads).

@@ -20,7 +20,7 @@ static constexpr float NEG_INF = -INFINITY;
 __device__ __forceinline__ float lse3(float a, float b, float c) {
   const float m = fmaxf(a, fmaxf(b, c));
   if (m == NEG_INF) return NEG_INF;
-  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
 }
 
 // ------------------------------------------------------------------------------------------------ alpha
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128)
 ctc_alpha_kernel(const float* __restrict__ glog, const float* __restrict__ lse, const long long* __restrict__ ys,
                  const long long* __restrict__ hlens, const long long* __restrict__ ylens, int B, int T, int Lp,
                  int ys_ld, float* __restrict__ alpha_ws, double* __restrict__ coff_ws, float* __restrict__ nll_out,
-                 float* __restrict__ nll_raw) {
+                 double* __restrict__ nll_raw) {
   constexpr int SP = 32 * NS;
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -51,9 +51,9 @@ ctc_alpha_kernel(const float* __restrict__ glog, const float* __restrict__ lse, 
   }
   if (Tb == 0) {
     if (lane == 0) {
-      const float v = L == 0 ? 0.f : INFINITY;
+      const double v = L == 0 ? 0.0 : static_cast<double>(INFINITY);
       nll_raw[b] = v;
-      nll_out[b] = isinf(v) ? 0.f : v;
+      nll_out[b] = isinf(v) ? 0.f : static_cast<float>(v);
     }
     return;
   }
@@ -133,9 +133,9 @@ ctc_alpha_kernel(const float* __restrict__ glog, const float* __restrict__ lse, 
   e2 = warp_max(e2);
   if (lane == 0) {
     const float tail = logaddexp_f(e1, e2);
-    const float v = tail == NEG_INF ? INFINITY : static_cast<float>(-(coff + static_cast<double>(tail)));
-    nll_raw[b] = v;
-    nll_out[b] = isinf(v) ? 0.f : v;  // zero_infinity=True (ref:models/ctc.py:31,44-46)
+    const double v = tail == NEG_INF ? static_cast<double>(INFINITY) : -(coff + static_cast<double>(tail));
+    nll_raw[b] = v;  // kept in double: |nll| ~ 1e3 would cost 1e-4 absolute in fp32 and that error multiplies every occupancy
+    nll_out[b] = isinf(v) ? 0.f : static_cast<float>(v);  // zero_infinity=True (ref:models/ctc.py:31,44-46)
   }
 }
 
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(128)
 ctc_beta_grad_kernel(const float* __restrict__ glog, const float* __restrict__ lse, const long long* __restrict__ ys,
                      const long long* __restrict__ hlens, const long long* __restrict__ ylens, int B, int T, int Lp,
                      int ys_ld, const float* __restrict__ alpha_ws, const double* __restrict__ coff_ws,
-                     const float* __restrict__ nll_raw, const float* __restrict__ gout, float* __restrict__ dG,
+                     const double* __restrict__ nll_raw, const float* __restrict__ gout, float* __restrict__ dG,
                      float* __restrict__ rowscale) {
   constexpr int SP = 32 * NS;
   const int lane = threadIdx.x & 31;
@@ -158,7 +158,7 @@ ctc_beta_grad_kernel(const float* __restrict__ glog, const float* __restrict__ l
   const int L = static_cast<int>(ylens[b]);
   const int S = 2 * L + 1;
   const long long* y = ys + static_cast<long long>(b) * ys_ld;
-  const float nll = nll_raw[b];
+  const double nll = nll_raw[b];
   const bool feasible = !isinf(nll) && Tb > 0;
   const float go = gout[b];
   float* rs = rowscale + static_cast<long long>(b) * T;
@@ -232,7 +232,7 @@ ctc_beta_grad_kernel(const float* __restrict__ glog, const float* __restrict__ l
     for (int j = 0; j < NS; ++j) bt[j] -= m;
     boff += static_cast<double>(m);
     // occupancy: exp(alpha + beta - lp + nll) with the three O(|nll|) offsets combined in double
-    const float shift = static_cast<float>(cw[t] + boff + static_cast<double>(nll));
+    const float shift = static_cast<float>(cw[t] + boff + nll);
     const float* ar = aw + static_cast<long long>(t) * SP + lane * NS;
     float blank_occ = 0.f;
     float* dgr = dg + static_cast<long long>(t) * Lp;
@@ -240,7 +240,7 @@ ctc_beta_grad_kernel(const float* __restrict__ glog, const float* __restrict__ l
     for (int j = 0; j < NS; ++j) {
       if (ok[j]) {
         const float e = ar[j] + bt[j] - lp[j] + shift;
-        const float occ = (ar[j] == NEG_INF || bt[j] == NEG_INF) ? 0.f : __expf(e);
+        const float occ = (ar[j] == NEG_INF || bt[j] == NEG_INF) ? 0.f : expf(e);
         if (col[j] == 0) blank_occ += occ;
         else dgr[col[j]] = -go * occ;
       }
@@ -415,7 +415,7 @@ extern "C" int mtasr_ctc_state_pad(int32_t max_label_len) {
 extern "C" int mtasr_ctc_alpha_fwd(const float* glog, const float* lse, const int64_t* ys, const int64_t* hlens,
                                    const int64_t* ylens, int32_t B, int32_t T, int32_t Lp, int32_t ys_ld,
                                    int32_t max_label_len, float* alpha_ws, double* coff_ws, float* nll_out,
-                                   float* nll_raw, void* stream) {
+                                   double* nll_raw, void* stream) {
   MTASR_CHECK_ARG(glog && lse && hlens && ylens && alpha_ws && coff_ws && nll_out && nll_raw, "ctc_alpha_fwd: null pointer");
   MTASR_CHECK_ARG(ys || max_label_len == 0, "ctc_alpha_fwd: null labels");
   MTASR_CHECK_ARG(B > 0 && T > 0 && Lp >= max_label_len + 1, "ctc_alpha_fwd: bad sizes B=%d T=%d Lp=%d Lmax=%d", B, T, Lp, max_label_len);
@@ -441,7 +441,7 @@ extern "C" int mtasr_ctc_alpha_fwd(const float* glog, const float* lse, const in
 extern "C" int mtasr_ctc_beta_bwd(const float* glog, const float* lse, const int64_t* ys, const int64_t* hlens,
                                   const int64_t* ylens, int32_t B, int32_t T, int32_t Lp, int32_t ys_ld,
                                   int32_t max_label_len, const float* alpha_ws, const double* coff_ws,
-                                  const float* nll_raw, const float* gout, float* dG, float* rowscale, void* stream) {
+                                  const double* nll_raw, const float* gout, float* dG, float* rowscale, void* stream) {
   MTASR_CHECK_ARG(glog && lse && hlens && ylens && alpha_ws && coff_ws && nll_raw && gout && dG && rowscale, "ctc_beta_bwd: null pointer");
   MTASR_CHECK_ARG(B > 0 && T > 0 && Lp >= max_label_len + 1, "ctc_beta_bwd: bad sizes");
   const int ns = pick_ns(2 * max_label_len + 1);

@@ -346,6 +346,20 @@ __global__ void glu_bwd_kernel(const void* __restrict__ x, int x_dtype, const vo
   }
 }
 
+// du = dy * act'(src): act 3 = GELU'(pre-activation), act 4 = ReLU (src = activation output).
+__global__ void act_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const __nv_bfloat16* __restrict__ src, int act,
+                               long long n8, __nv_bfloat16* __restrict__ du) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float d[8], u[8], o[8];
+    ld8(dy, dy_dtype, i * 8, d);
+    ld8(src, MTASR_DT_BF16, i * 8, u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = act == 3 ? d[j] * gelu_grad_f(u[j]) : (u[j] > 0.f ? d[j] : 0.f);
+    st8_bf16(du + i * 8, o);
+  }
+}
+
 static int grid_for(long long work_items, int per_block) {
   long long g = (work_items + per_block - 1) / per_block;
   const long long cap = static_cast<long long>(num_sms()) * 8;
@@ -473,5 +487,15 @@ extern "C" int mtasr_glu_bwd(const void* x, int32_t x_dtype, const void* dy, int
       x, x_dtype, dy, dy_dtype, rows, C, reinterpret_cast<__nv_bfloat16*>(dx_bf16));
   MTASR_COUNT_LAUNCH();
   MTASR_CHECK_LAUNCH("glu_bwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_act_bwd(const void* dy, int32_t dy_dtype, const void* src_bf16, int32_t act, int64_t n, void* du_bf16,
+                             void* stream) {
+  MTASR_CHECK_ARG(dy && src_bf16 && du_bf16 && n > 0 && n % 8 == 0 && (act == 3 || act == 4), "act_bwd: bad arguments");
+  act_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dy, dy_dtype, reinterpret_cast<const __nv_bfloat16*>(src_bf16), act, n / 8, reinterpret_cast<__nv_bfloat16*>(du_bf16));
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("act_bwd");
   return MTASR_OK;
 }

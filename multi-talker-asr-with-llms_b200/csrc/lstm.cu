@@ -1,0 +1,342 @@
+// Persistent LSTM recurrence for the separator (ref:models/separator.py:6-59: CustomLSTMCell / StackedCustomLSTM).
+//
+// The reference runs a Python `for t in range(T)` over ~10 tiny kernels per layer.  Here the
+// input half x_t W_ih^T + b of every step is ONE batched tcgen05 GEMM (csrc/gemm.cu) done beforehand, and the
+// sequential half runs in a single cooperative kernel per layer:
+//   * grid = Hs/8 CTAs; CTA j owns hidden units [8j, 8j+8) = 32 gate columns (i,f,g,o) and keeps that slice of
+//     W_hh (32 x Hs bf16) resident in shared memory for all T steps;
+//   * per step: h_{t-1} (B x Hs bf16) is pulled from L2 into smem, the 8 warps do the (B x Hs)(Hs x 32) product
+//     with mma.sync m16n8k16 (latency-bound GEMV-like step: not a tcgen05 shape), gates/cell update in fp32
+//     registers, h_t is published and a grid-wide arrive/spin barrier (one atomic per CTA) orders the steps.
+// Backward (BPTT) mirrors it: CTA j owns dh_{t-1}[:, 8j:8j+8], streams dgates_t (B x 4Hs bf16) through smem in
+// four Hs-wide chunks against its resident W_hh^T slice, split-K over the 8 warps with an smem reduction.
+// dW / dx / db are batched GEMMs / column sums over the saved dgates afterwards.
+#include "common.cuh"
+
+namespace mtasr {
+
+static constexpr int LU = 8;           // hidden units per CTA
+static constexpr int LTHREADS = 256;   // 8 warps
+static constexpr int LPAD = 8;         // bf16 row padding (16 B) -> conflict-free ldmatrix
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// Grid barrier: every CTA adds 1 after publishing step data; waiters spin until the count reaches `target`.
+__device__ __forceinline__ void grid_arrive(unsigned int* bar) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(bar, 1u);
+}
+__device__ __forceinline__ void grid_wait(unsigned int* bar, unsigned int target) {
+  if (threadIdx.x == 0) {
+    unsigned int v;
+    long long t0 = clock64();
+    unsigned int spins = 0;
+    while (true) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (v >= target) break;
+      if ((++spins & 0xfff) == 0 && clock64() - t0 > 4000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ uint4 ldcg16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+struct LstmFwdP {
+  const float* xg;            // (B,T,4Hs)
+  const __nv_bfloat16* whh;   // (4Hs, ldw): whh[col*ldw + k]
+  __nv_bfloat16* h_bf16;      // (B,T,Hs)
+  float* h_f32;               // (B,T,Hs) optional
+  float* c_all;               // (B,T,Hs)
+  float* gates;               // (B,T,4Hs) activations i,f,g,o
+  unsigned int* bar;
+  int B, T, Hs, ldw, Bp;
+};
+
+__global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_kernel(const LstmFwdP p) {
+  extern __shared__ __align__(16) uint8_t lsm[];
+  const int Hs = p.Hs, B = p.B, T = p.T, Bp = p.Bp;
+  const int rs = Hs + LPAD;  // smem row stride (elements)
+  __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(lsm);   // [32][rs]
+  __nv_bfloat16* Hsm = Ws + 32 * rs;                           // [Bp][rs]
+  float* G = reinterpret_cast<float*>(Hsm + Bp * rs);          // [Bp][33]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int u0 = blockIdx.x * LU;
+
+  // resident W_hh slice: local column lc = gate*8 + u  <-  global column gate*Hs + u0 + u
+  for (int i = tid; i < 32 * (Hs / 8); i += LTHREADS) {
+    const int lc = i / (Hs / 8), kc = i % (Hs / 8);
+    const int gcol = (lc >> 3) * Hs + u0 + (lc & 7);
+    *reinterpret_cast<uint4*>(Ws + lc * rs + kc * 8) =
+        *reinterpret_cast<const uint4*>(p.whh + static_cast<long long>(gcol) * p.ldw + kc * 8);
+  }
+  for (int i = tid; i < Bp * rs; i += LTHREADS) Hsm[i] = f2bf(0.f);
+  for (int i = tid; i < Bp * 33; i += LTHREADS) G[i] = 0.f;
+  __syncthreads();
+
+  const int npair = B * LU;
+  float creg[2] = {0.f, 0.f};  // cell state of the (b, unit) pairs this thread owns (B <= 64)
+  const int m_tiles = Bp / 16;
+
+  for (int t = 0; t < T; ++t) {
+    float xv[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int pr = tid + i * LTHREADS;
+      if (pr < npair) {
+        const int b = pr >> 3, u = pr & 7;
+        const float* xr = p.xg + (static_cast<long long>(b) * T + t) * 4 * Hs + u0 + u;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) xv[i][g] = xr[g * Hs];
+      }
+    }
+    if (t > 0) {
+      grid_wait(p.bar, gridDim.x * static_cast<unsigned>(t));
+      for (int i = tid; i < B * (Hs / 8); i += LTHREADS) {
+        const int b = i / (Hs / 8), kc = i % (Hs / 8);
+        *reinterpret_cast<uint4*>(Hsm + b * rs + kc * 8) =
+            ldcg16(p.h_bf16 + (static_cast<long long>(b) * T + (t - 1)) * Hs + kc * 8);
+      }
+      __syncthreads();
+      for (int tile = warp; tile < m_tiles * 4; tile += 8) {
+        const int mt = tile >> 2, nt = tile & 3;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t a_base = smem_addr(Hsm + (mt * 16 + (lane & 15)) * rs + (lane >> 4) * 8);
+        const uint32_t b_base = smem_addr(Ws + (nt * 8 + (lane & 7)) * rs + ((lane >> 3) & 1) * 8);
+        for (int k0 = 0; k0 < Hs; k0 += 16) {
+          uint32_t a0, a1, a2, a3, b0, b1;
+          ldsm_x4(a_base + k0 * 2, a0, a1, a2, a3);
+          ldsm_x2(b_base + k0 * 2, b0, b1);
+          mma16816(acc, a0, a1, a2, a3, b0, b1);
+        }
+        const int r = mt * 16 + (lane >> 2), c = nt * 8 + (lane & 3) * 2;
+        G[r * 33 + c] = acc[0];
+        G[r * 33 + c + 1] = acc[1];
+        G[(r + 8) * 33 + c] = acc[2];
+        G[(r + 8) * 33 + c + 1] = acc[3];
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int pr = tid + i * LTHREADS;
+      if (pr < npair) {
+        const int b = pr >> 3, u = pr & 7;
+        const float ai = xv[i][0] + G[b * 33 + u];
+        const float af = xv[i][1] + G[b * 33 + 8 + u];
+        const float ag = xv[i][2] + G[b * 33 + 16 + u];
+        const float ao = xv[i][3] + G[b * 33 + 24 + u];
+        const float ig = 1.f / (1.f + expf(-ai)), fg = 1.f / (1.f + expf(-af));
+        const float gg = tanhf(ag), og = 1.f / (1.f + expf(-ao));
+        const float c = fg * creg[i] + ig * gg;
+        creg[i] = c;
+        const float h = og * tanhf(c);
+        const long long o = (static_cast<long long>(b) * T + t) * Hs + u0 + u;
+        p.h_bf16[o] = f2bf(h);
+        if (p.h_f32) p.h_f32[o] = h;
+        p.c_all[o] = c;
+        float* gr = p.gates + (static_cast<long long>(b) * T + t) * 4 * Hs + u0 + u;
+        gr[0] = ig; gr[Hs] = fg; gr[2 * Hs] = gg; gr[3 * Hs] = og;
+      }
+    }
+    if (t + 1 < T) grid_arrive(p.bar);
+  }
+}
+
+struct LstmBwdP {
+  const float* dh_out;        // (B,T,Hs)
+  const float* gates;         // (B,T,4Hs)
+  const float* c_all;         // (B,T,Hs)
+  const __nv_bfloat16* whh;   // (4Hs, ldw)
+  __nv_bfloat16* dgates;      // (B,T,4Hs) out, pre-activation gradients
+  unsigned int* bar;
+  int B, T, Hs, ldw, Bp;
+};
+
+__global__ void __launch_bounds__(LTHREADS, 1) lstm_bwd_kernel(const LstmBwdP p) {
+  extern __shared__ __align__(16) uint8_t lsm[];
+  const int Hs = p.Hs, B = p.B, T = p.T, Bp = p.Bp;
+  const int K4 = 4 * Hs;
+  const int wrs = K4 + LPAD;  // W^T slice row stride
+  const int ars = Hs + LPAD;  // A chunk row stride
+  __nv_bfloat16* Wt = reinterpret_cast<__nv_bfloat16*>(lsm);  // [8][wrs]: Wt[u][col] = whh[col][u0+u]
+  __nv_bfloat16* Asm = Wt + LU * wrs;                         // [Bp][ars]
+  float* R = reinterpret_cast<float*>(Asm + Bp * ars);        // [8 warps][Bp][8] partials
+  float* Dh = R + 8 * Bp * 8;                                 // [Bp][8] reduced dh_rec
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int u0 = blockIdx.x * LU;
+
+  for (int i = tid; i < LU * K4; i += LTHREADS) {
+    const int u = i % LU, col = i / LU;
+    Wt[u * wrs + col] = p.whh[static_cast<long long>(col) * p.ldw + u0 + u];
+  }
+  for (int i = tid; i < Bp * ars; i += LTHREADS) Asm[i] = f2bf(0.f);
+  for (int i = tid; i < Bp * 8; i += LTHREADS) Dh[i] = 0.f;
+  __syncthreads();
+
+  const int npair = B * LU;
+  float dc_carry[2] = {0.f, 0.f};
+  const int m_tiles = Bp / 16;
+  unsigned int step = 0;
+
+  for (int t = T - 1; t >= 0; --t) {
+    if (t < T - 1) {
+      ++step;
+      grid_wait(p.bar, gridDim.x * step);
+      float acc[4][4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[m][j] = 0.f;
+      for (int g = 0; g < 4; ++g) {
+        __syncthreads();  // previous chunk fully consumed
+        for (int i = tid; i < B * (Hs / 8); i += LTHREADS) {
+          const int b = i / (Hs / 8), kc = i % (Hs / 8);
+          *reinterpret_cast<uint4*>(Asm + b * ars + kc * 8) =
+              ldcg16(p.dgates + (static_cast<long long>(b) * T + (t + 1)) * K4 + g * Hs + kc * 8);
+        }
+        __syncthreads();
+        // split-K over warps: 16-wide k-steps dealt round-robin
+        for (int ks = warp; ks < Hs / 16; ks += 8) {
+          const int k0 = ks * 16;
+          uint32_t b0, b1;
+          ldsm_x2(smem_addr(Wt + (lane & 7) * wrs + g * Hs + k0 + ((lane >> 3) & 1) * 8), b0, b1);
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) {
+            if (mt < m_tiles) {
+              uint32_t a0, a1, a2, a3;
+              ldsm_x4(smem_addr(Asm + (mt * 16 + (lane & 15)) * ars + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+              mma16816(acc[mt], a0, a1, a2, a3, b0, b1);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        if (mt < m_tiles) {
+          const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
+          float* Rw = R + warp * Bp * 8;
+          Rw[r * 8 + c] = acc[mt][0];
+          Rw[r * 8 + c + 1] = acc[mt][1];
+          Rw[(r + 8) * 8 + c] = acc[mt][2];
+          Rw[(r + 8) * 8 + c + 1] = acc[mt][3];
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < Bp * 8; i += LTHREADS) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += R[w * Bp * 8 + i];
+        Dh[i] = s;
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int pr = tid + i * LTHREADS;
+      if (pr < npair) {
+        const int b = pr >> 3, u = pr & 7;
+        const long long o = (static_cast<long long>(b) * T + t) * Hs + u0 + u;
+        const float* gr = p.gates + (static_cast<long long>(b) * T + t) * K4 + u0 + u;
+        const float ig = gr[0], fg = gr[Hs], gg = gr[2 * Hs], og = gr[3 * Hs];
+        const float c = p.c_all[o];
+        const float cprev = t > 0 ? p.c_all[o - Hs] : 0.f;
+        const float dh = p.dh_out[o] + (t < T - 1 ? Dh[b * 8 + u] : 0.f);
+        const float tc = tanhf(c);
+        const float dc = dh * og * (1.f - tc * tc) + dc_carry[i];
+        dc_carry[i] = dc * fg;
+        const float dai = dc * gg * ig * (1.f - ig);
+        const float daf = dc * cprev * fg * (1.f - fg);
+        const float dag = dc * ig * (1.f - gg * gg);
+        const float dao = dh * tc * og * (1.f - og);
+        __nv_bfloat16* dg = p.dgates + (static_cast<long long>(b) * T + t) * K4 + u0 + u;
+        dg[0] = f2bf(dai); dg[Hs] = f2bf(daf); dg[2 * Hs] = f2bf(dag); dg[3 * Hs] = f2bf(dao);
+      }
+    }
+    if (t > 0) grid_arrive(p.bar);
+  }
+}
+
+static size_t lstm_fwd_smem(int Hs, int Bp) {
+  return static_cast<size_t>(32 + Bp) * (Hs + LPAD) * 2 + static_cast<size_t>(Bp) * 33 * 4;
+}
+static size_t lstm_bwd_smem(int Hs, int Bp) {
+  return static_cast<size_t>(LU) * (4 * Hs + LPAD) * 2 + static_cast<size_t>(Bp) * (Hs + LPAD) * 2 +
+         static_cast<size_t>(9) * Bp * 8 * 4;
+}
+
+static int lstm_check(int B, int T, int Hs, int ldw, const char* who) {
+  if (B <= 0 || B > 64) return set_error(MTASR_ERR_UNSUPPORTED, "%s: batch %d not in [1,64] (chunk the batch)", who, B);
+  if (T <= 0 || Hs <= 0 || Hs % 16 != 0)
+    return set_error(MTASR_ERR_UNSUPPORTED, "%s: need T > 0 and Hs %% 16 == 0 (Hs=%d)", who, Hs);
+  if (Hs / LU > num_sms())
+    return set_error(MTASR_ERR_UNSUPPORTED, "%s: Hs=%d needs %d co-resident CTAs > %d SMs", who, Hs, Hs / LU, num_sms());
+  if (ldw % 8 != 0) return set_error(MTASR_ERR_INVALID_ARG, "%s: ldw must be a multiple of 8", who);
+  return 0;
+}
+
+}  // namespace mtasr
+
+using namespace mtasr;
+
+extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw, int32_t B, int32_t T, int32_t Hs,
+                              void* h_bf16, float* h_f32, float* c_all, float* gates, uint32_t* barrier, void* stream) {
+  MTASR_CHECK_ARG(xg && whh_bf16 && h_bf16 && c_all && gates && barrier, "lstm_fwd: null pointer");
+  if (int rc = lstm_check(B, T, Hs, ldw, "lstm_fwd")) return rc;
+  LstmFwdP p;
+  p.xg = xg; p.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16); p.h_bf16 = reinterpret_cast<__nv_bfloat16*>(h_bf16);
+  p.h_f32 = h_f32; p.c_all = c_all; p.gates = gates; p.bar = barrier;
+  p.B = B; p.T = T; p.Hs = Hs; p.ldw = ldw; p.Bp = (B + 15) / 16 * 16;
+  const size_t smem = lstm_fwd_smem(Hs, p.Bp);
+  if (smem > 227 * 1024) return set_error(MTASR_ERR_UNSUPPORTED, "lstm_fwd: Hs=%d B=%d needs %zu B smem", Hs, B, smem);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+    return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: cannot set smem attribute");
+  if (cudaMemsetAsync(barrier, 0, sizeof(uint32_t), st) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: memset failed");
+  void* args[] = {&p};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_fwd_kernel), dim3(Hs / LU), dim3(LTHREADS), args, smem, st);
+  MTASR_COUNT_LAUNCH();
+  if (e != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: cooperative launch failed: %s", cudaGetErrorString(e));
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_lstm_bwd(const float* dh_out, const float* gates, const float* c_all, const void* whh_bf16, int32_t ldw,
+                              int32_t B, int32_t T, int32_t Hs, void* dgates_bf16, uint32_t* barrier, void* stream) {
+  MTASR_CHECK_ARG(dh_out && gates && c_all && whh_bf16 && dgates_bf16 && barrier, "lstm_bwd: null pointer");
+  if (int rc = lstm_check(B, T, Hs, ldw, "lstm_bwd")) return rc;
+  LstmBwdP p;
+  p.dh_out = dh_out; p.gates = gates; p.c_all = c_all; p.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16);
+  p.dgates = reinterpret_cast<__nv_bfloat16*>(dgates_bf16); p.bar = barrier;
+  p.B = B; p.T = T; p.Hs = Hs; p.ldw = ldw; p.Bp = (B + 15) / 16 * 16;
+  const size_t smem = lstm_bwd_smem(Hs, p.Bp);
+  if (smem > 227 * 1024) return set_error(MTASR_ERR_UNSUPPORTED, "lstm_bwd: Hs=%d B=%d needs %zu B smem", Hs, B, smem);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+    return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: cannot set smem attribute");
+  if (cudaMemsetAsync(barrier, 0, sizeof(uint32_t), st) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: memset failed");
+  void* args[] = {&p};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_bwd_kernel), dim3(Hs / LU), dim3(LTHREADS), args, smem, st);
+  MTASR_COUNT_LAUNCH();
+  if (e != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: cooperative launch failed: %s", cudaGetErrorString(e));
+  return MTASR_OK;
+}

@@ -37,6 +37,16 @@ def _p(t: Optional[torch.Tensor], offset: int = 0) -> Optional[int]:
     return t.data_ptr() + offset * t.element_size()
 
 
+def empty_act(shape, dtype, device) -> torch.Tensor:
+    """Activation buffer with a little slack after the last element: implicit-conv TMA views may address (never
+    use) up to one stride-row past the end of the last utterance."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    flat = torch.empty(n + 8192, device=device, dtype=dtype)
+    return flat[:n].view(*shape)
+
+
 def launch_count() -> int:
     return int(_lib.load().mtasr_launch_count())
 
@@ -161,7 +171,7 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     D = x.shape[-1]
     rows = x.numel() // D
     x = x.contiguous()
-    yb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if out_bf16 else None
+    yb = empty_act(x.shape, torch.bfloat16, x.device) if out_bf16 else None
     yf = torch.empty(x.shape, device=x.device, dtype=torch.float32) if out_f32 else None
     mean = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
     rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if save_stats else None
@@ -221,7 +231,7 @@ def attn_softmax_bwd(P, dP, gate, table, B, H, T, Tp, scale):
 def pad_cast(x: torch.Tensor, pad_l: int, Tpad: int, vlen: Optional[torch.Tensor] = None) -> torch.Tensor:
     B, T, D = x.shape
     x = x.contiguous()
-    y = torch.empty(B, Tpad, D, device=x.device, dtype=torch.bfloat16)
+    y = empty_act((B, Tpad, D), torch.bfloat16, x.device)
     check(_lib.load().mtasr_pad_cast(_p(x), _dt(x), B, T, D, pad_l, Tpad, _p(vlen), _p(y), _stream()), "mtasr_pad_cast")
     return y
 
@@ -231,7 +241,7 @@ def glu_fwd(x: torch.Tensor, *, out_f32: bool = False):
     Cc = C2 // 2
     rows = x.numel() // C2
     x = x.contiguous()
-    yb = torch.empty(*x.shape[:-1], Cc, device=x.device, dtype=torch.bfloat16)
+    yb = empty_act(tuple(x.shape[:-1]) + (Cc,), torch.bfloat16, x.device)
     yf = torch.empty(*x.shape[:-1], Cc, device=x.device, dtype=torch.float32) if out_f32 else None
     check(_lib.load().mtasr_glu_fwd(_p(x), _dt(x), rows, Cc, _p(yb), _p(yf), _stream()), "mtasr_glu_fwd")
     return yb, yf
@@ -260,7 +270,7 @@ def ctc_alpha_fwd(glog, lse, ys, hlens, ylens, max_label_len):
     alpha = torch.empty(B, T, sp, device=glog.device, dtype=torch.float32)
     coff = torch.empty(B, T, device=glog.device, dtype=torch.float64)
     nll = torch.empty(B, device=glog.device, dtype=torch.float32)
-    nll_raw = torch.empty(B, device=glog.device, dtype=torch.float32)
+    nll_raw = torch.empty(B, device=glog.device, dtype=torch.float64)
     ys_ld = ys.stride(0) if ys.numel() else 0
     check(_lib.load().mtasr_ctc_alpha_fwd(_p(glog), _p(lse), _p(ys) if ys.numel() else None, _p(hlens), _p(ylens), B, T, Lp,
                                           ys_ld, max_label_len, _p(alpha), _p(coff), _p(nll), _p(nll_raw), _stream()),
@@ -328,3 +338,63 @@ def ctc_scatter_rows(dwg, dbg, ys, ylens, blank, dw, db):
     ys_ld = ys.stride(0) if ys.numel() else 0
     check(_lib.load().mtasr_ctc_scatter_rows(_p(dwg), _p(dbg), _p(ys) if ys.numel() else None, _p(ylens), B, Lp, D, ys_ld,
                                              blank, _p(dw), _p(db), _stream()), "mtasr_ctc_scatter_rows")
+
+
+# ----------------------------------------------------------------------------------------------------------- misc
+def act_bwd(dy: torch.Tensor, src_bf16: torch.Tensor, act: int) -> torch.Tensor:
+    dy = dy.contiguous()
+    du = torch.empty(dy.shape, device=dy.device, dtype=torch.bfloat16)
+    check(_lib.load().mtasr_act_bwd(_p(dy), _dt(dy), _p(src_bf16), act, dy.numel(), _p(du), _stream()), "mtasr_act_bwd")
+    return du
+
+
+def conv0_fwd(x: torch.Tensor, w: torch.Tensor, bias, gamma, beta, eps: float, k: int, stride: int, layer_norm: bool):
+    """First feature-extractor conv (+LayerNorm+GELU when layer_norm) -> (B, L0, C0); bf16 if fused else raw fp32."""
+    B, S = x.shape
+    C0 = w.shape[0]
+    L0 = (S - k) // stride + 1
+    x = x.contiguous()
+    if layer_norm:
+        y = empty_act((B, L0, C0), torch.bfloat16, x.device)
+        check(_lib.load().mtasr_conv0_fwd(_p(x), _p(w), _p(bias), _p(gamma), _p(beta), eps, B, S, C0, k, stride, 1, _p(y), None,
+                                          _stream()), "mtasr_conv0_fwd")
+    else:
+        y = torch.empty(B, L0, C0, device=x.device, dtype=torch.float32)
+        check(_lib.load().mtasr_conv0_fwd(_p(x), _p(w), _p(bias), None, None, eps, B, S, C0, k, stride, 0, None, _p(y),
+                                          _stream()), "mtasr_conv0_fwd")
+    return y
+
+
+def groupnorm_gelu(x: torch.Tensor, gamma, beta, eps: float) -> torch.Tensor:
+    B, L, Cc = x.shape
+    mean = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
+    y = empty_act((B, L, Cc), torch.bfloat16, x.device)
+    check(_lib.load().mtasr_groupnorm_gelu(_p(x), _p(gamma), _p(beta), eps, B, L, Cc, _p(mean), _p(rstd), _p(y), _stream()),
+          "mtasr_groupnorm_gelu")
+    return y
+
+
+def lstm_fwd(xg: torch.Tensor, whh: torch.Tensor, ldw: int, want_h_f32: bool = False):
+    """xg (B,T,4Hs) f32; whh bf16 view of W[:, in:] (row stride ldw).  Returns h_bf16, h_f32|None, c, gates."""
+    B, T, H4 = xg.shape
+    Hs = H4 // 4
+    dev = xg.device
+    h = torch.empty(B, T, Hs, device=dev, dtype=torch.bfloat16)
+    hf = torch.empty(B, T, Hs, device=dev, dtype=torch.float32) if want_h_f32 else None
+    c = torch.empty(B, T, Hs, device=dev, dtype=torch.float32)
+    gates = torch.empty(B, T, H4, device=dev, dtype=torch.float32)
+    bar = torch.zeros(1, device=dev, dtype=torch.int32)
+    check(_lib.load().mtasr_lstm_fwd(_p(xg), _p(whh), ldw, B, T, Hs, _p(h), _p(hf), _p(c), _p(gates), _p(bar), _stream()),
+          "mtasr_lstm_fwd")
+    return h, hf, c, gates
+
+
+def lstm_bwd(dh: torch.Tensor, gates: torch.Tensor, c: torch.Tensor, whh: torch.Tensor, ldw: int) -> torch.Tensor:
+    B, T, Hs = dh.shape
+    dh = dh.contiguous()
+    dgates = torch.empty(B, T, 4 * Hs, device=dh.device, dtype=torch.bfloat16)
+    bar = torch.zeros(1, device=dh.device, dtype=torch.int32)
+    check(_lib.load().mtasr_lstm_bwd(_p(dh), _p(gates), _p(c), _p(whh), ldw, B, T, Hs, _p(dgates), _p(bar), _stream()),
+          "mtasr_lstm_bwd")
+    return dgates

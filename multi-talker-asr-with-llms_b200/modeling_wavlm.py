@@ -1,0 +1,341 @@
+"""Drop-in `WavLMModel` for ref:models/modeling_wavlm.py (same constructor, forward signature, 6-field output and
+state_dict names) whose arithmetic runs on the hand-written sm_100a kernels of this package.
+
+Parameter containers are the third-party `transformers.models.wavlm` classes the reference itself instantiates
+(ref:models/modeling_wavlm.py:36-43, 322-334) -- that keeps checkpoint keys, `_init_weights`, `freeze_feature_encoder`
+and `gradient_checkpointing` attributes identical -- but their `forward`s are never called: every contraction goes
+through `ops`/`kernels` (tcgen05 GEMM, fused row kernels).
+
+Deliberate, documented differences:
+  * compute is bf16 operands / fp32 accumulation with an fp32 residual stream, whatever the autocast state;
+  * `output_attentions=True` raises (attention probabilities exist only tile-wise per head);
+  * the feature encoder has no backward: it is frozen in every reference run (ref:run.sh:231); asking for its
+    gradients raises instead of silently falling back;
+  * dropout / LayerDrop inside the encoder are not applied (parity and throughput runs use p=0; ref RNG streams
+    cannot be reproduced anyway).
+"""
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+from transformers.models.wavlm.configuration_wavlm import WavLMConfig
+from transformers.models.wavlm.modeling_wavlm import (
+    WavLMAdapterLayer,
+    WavLMEncoder,
+    WavLMEncoderStableLayerNorm,
+    WavLMFeatureEncoder,
+    WavLMFeatureProjection,
+    WavLMPreTrainedModel,
+    _compute_mask_indices,
+)
+from transformers.utils import ModelOutput
+
+from . import kernels as K
+from . import ops
+
+BF, F32 = torch.bfloat16, torch.float32
+
+
+@dataclass
+class WavLMBaseModelOutput(ModelOutput):
+    """Same fields, same order as ref:models/modeling_wavlm.py:71-99 (callers index [0..3] positionally)."""
+    last_hidden_state: torch.FloatTensor = None
+    encoder_hidden_state: torch.FloatTensor = None
+    wavlm_down_hidden_states: torch.FloatTensor = None
+    extract_features: torch.FloatTensor = None
+    hidden_states: Optional[Tuple[torch.FloatTensor]] = None
+    attentions: Optional[Tuple[torch.FloatTensor]] = None
+
+
+class WavLMAdapter(nn.Module):
+    """Parameter container with the reference's names (ref:models/modeling_wavlm.py:223-254); forward is B200-native."""
+
+    def __init__(self, config):
+        super().__init__()
+        if config.output_hidden_size != config.hidden_size:
+            self.proj = nn.Linear(config.hidden_size, config.output_hidden_size)
+            self.proj_layer_norm = nn.LayerNorm(config.output_hidden_size)
+        else:
+            self.proj = self.proj_layer_norm = None
+        self.layers = nn.ModuleList(WavLMAdapterLayer(config) for _ in range(config.num_adapter_layers))
+        self.layerdrop = config.layerdrop
+        self.stride = config.adapter_stride
+        self.kernel = config.adapter_kernel_size
+
+    def forward(self, hidden_states):
+        return AdapterFn.apply(hidden_states, self, *[p for p in self.parameters()])
+
+
+class AdapterFn(torch.autograd.Function):
+    """3 x [conv1d(D -> 2D, k=3, s=2, p=1) as implicit GEMM -> GLU]; returns (x8, x4) like the reference's adapter
+    (tap after layer index 1).  Backward is not implemented yet (the CTC-only loss never reaches the adapter)."""
+
+    @staticmethod
+    def forward(ctx, x, mod, *params):
+        h = x
+        if mod.proj is not None:
+            h = K.linear_fwd(K.cast_bf16(h.contiguous().view(-1, h.shape[-1])), ops.bf16_of(mod.proj.weight),
+                             mod.proj.bias.detach().float(), out_dtype=F32).view(*x.shape[:-1], -1)
+            h = K.layernorm_fwd(h, mod.proj_layer_norm.weight.detach(), mod.proj_layer_norm.bias.detach(),
+                                mod.proj_layer_norm.eps, out_bf16=False, out_f32=True)[1]
+        tap = None
+        for i, layer in enumerate(mod.layers):
+            conv = layer.conv
+            B, T, D = h.shape
+            k, s, pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+            Tpad = T + 2 * pad
+            Tpad += (-Tpad) % s
+            xp = K.pad_cast(h, pad, Tpad)
+            Lout = (T + 2 * pad - k) // s + 1
+            C2 = conv.weight.shape[0]
+            wk = ops.bf16_of(conv.weight).permute(0, 2, 1).contiguous().view(C2, k * D)
+            y = K.empty_act((B, Lout, C2), BF, h.device)
+            K.gemm(K.Operand(xp, s * D, sb1=Tpad * D, inner=D, phase=s, rows=Tpad // s), K.Operand(wk, k * D), Lout, C2, k * D,
+                   K.Out(y, C2, sb1=Lout * C2), batch=(1, B), bias=None if conv.bias is None else conv.bias.detach().float())
+            hb, hf = K.glu_fwd(y, out_f32=True)
+            h = hf
+            if i == 1:
+                tap = hf
+        return h, tap
+
+    @staticmethod
+    def backward(ctx, *grads):
+        raise NotImplementedError(
+            "mtasr_b200: the adapter backward (hf:803-807 conv+GLU) is not implemented yet; the CTC loss does not depend on "
+            "it.  Training losses that consume `last_hidden_state` are outside this round's scope (SURVEY 8f).")
+
+
+def relpos_bucket(rel: torch.Tensor, num_buckets: int, max_distance: int) -> torch.Tensor:
+    """T5-style bucket of hf:253-271 for relative positions rel = k - q (int64 tensor)."""
+    nb = num_buckets // 2
+    out = (rel > 0).to(torch.long) * nb
+    a = rel.abs()
+    max_exact = nb // 2
+    large = torch.log(a.float() / max_exact) / math.log(max_distance / max_exact) * (nb - max_exact)
+    large = (max_exact + large).to(torch.long).clamp(max=nb - 1)
+    return out + torch.where(a < max_exact, a, large)
+
+
+class WavLMModel(WavLMPreTrainedModel):
+    def __init__(self, config: WavLMConfig):
+        super().__init__(config)
+        self.config = config
+        self.feature_extractor = WavLMFeatureEncoder(config)
+        self.feature_projection = WavLMFeatureProjection(config)
+        if config.mask_time_prob > 0.0 or config.mask_feature_prob > 0.0:
+            self.masked_spec_embed = nn.Parameter(torch.Tensor(config.hidden_size).uniform_())
+        if config.do_stable_layer_norm:
+            self.encoder = WavLMEncoderStableLayerNorm(config)
+        else:
+            self.encoder = WavLMEncoder(config)
+        self.adapter = WavLMAdapter(config) if config.add_adapter else None
+        self.post_init()
+
+    # ------------------------------------------------------------------ reference API (ref:models/modeling_wavlm.py)
+    def freeze_feature_extractor(self):
+        self.freeze_feature_encoder()
+
+    def freeze_feature_encoder(self):
+        self.feature_extractor._freeze_parameters()
+
+    def _conv_lengths(self, n: torch.Tensor) -> torch.Tensor:
+        for k, s in zip(self.config.conv_kernel, self.config.conv_stride):
+            n = torch.div(n - k, s, rounding_mode="floor") + 1
+        return n
+
+    @staticmethod
+    def _prefix_mask(lengths: torch.Tensor, T: int) -> torch.Tensor:
+        return torch.arange(T, device=lengths.device)[None, :] < lengths.to(torch.long)[:, None]
+
+    def _get_feature_vector_attention_mask_x0(self, feature_vector_length: int, attention_mask, add_adapter=None):
+        """ref:models/modeling_wavlm.py:508-533 -- frame-rate (no adapter) prefix mask."""
+        n = self._conv_lengths(attention_mask.cumsum(dim=-1)[:, -1])
+        return self._prefix_mask(n, feature_vector_length)
+
+    def _get_feat_extract_output_lengths_x4(self, input_lengths, add_adapter: Optional[bool] = None):
+        """ref:models/modeling_wavlm.py:536-557 -- conv stack + (num_adapter_layers - 1) stride-2 steps."""
+        add_adapter = self.config.add_adapter if add_adapter is None else add_adapter
+        n = self._conv_lengths(input_lengths)
+        if add_adapter:
+            for _ in range(self.config.num_adapter_layers - 1):
+                n = torch.div(n - 1, self.config.adapter_stride, rounding_mode="floor") + 1
+        return n
+
+    def _get_feature_vector_attention_mask_x4(self, feature_vector_length: int, attention_mask, add_adapter=None):
+        n = self._get_feat_extract_output_lengths_x4(attention_mask.cumsum(dim=-1)[:, -1], add_adapter=add_adapter)
+        return self._prefix_mask(n, feature_vector_length)
+
+    def get_downsampled_feature_mask(self, feature_vector_length: int, attention_mask, extra_total_stride: int = 4):
+        """ref:models/modeling_wavlm.py:467-506."""
+        n = self._conv_lengths(attention_mask.cumsum(dim=-1)[:, -1])
+        if extra_total_stride > 1:
+            n = torch.div(n, extra_total_stride, rounding_mode="floor")
+        lengths = n.to(torch.long).clamp_min(0).clamp_max(feature_vector_length)
+        return self._prefix_mask(lengths, feature_vector_length), lengths
+
+    def _mask_hidden_states(self, hidden_states, mask_time_indices=None, attention_mask=None):
+        """SpecAugment (ref:models/modeling_wavlm.py:358-402): host-side numpy RNG + boolean scatter, kept in Python."""
+        if not getattr(self.config, "apply_spec_augment", True):
+            return hidden_states
+        B, T, D = hidden_states.size()
+        if mask_time_indices is not None:
+            hidden_states = hidden_states.clone()
+            hidden_states[mask_time_indices] = self.masked_spec_embed.to(hidden_states.dtype)
+        elif self.config.mask_time_prob > 0 and self.training:
+            m = _compute_mask_indices((B, T), mask_prob=self.config.mask_time_prob, mask_length=self.config.mask_time_length,
+                                      attention_mask=attention_mask, min_masks=self.config.mask_time_min_masks)
+            m = torch.tensor(m, device=hidden_states.device, dtype=torch.bool)
+            hidden_states = hidden_states.clone()
+            hidden_states[m] = self.masked_spec_embed.to(hidden_states.dtype)
+        if self.config.mask_feature_prob > 0 and self.training:
+            m = _compute_mask_indices((B, D), mask_prob=self.config.mask_feature_prob, mask_length=self.config.mask_feature_length,
+                                      min_masks=self.config.mask_feature_min_masks)
+            m = torch.tensor(m, device=hidden_states.device, dtype=torch.bool)[:, None].expand(-1, T, -1)
+            hidden_states = hidden_states.masked_fill(m, 0)
+        return hidden_states
+
+    # ------------------------------------------------------------------ B200-native stages
+    def _feature_extractor_fwd(self, x: torch.Tensor) -> torch.Tensor:
+        """hf:754-789: 7 conv layers -> (B, T, C) channels-last bf16.  Layer 0 direct conv (+LN/GN+GELU); layers 1-6
+        implicit GEMM over a strided channels-last view (no im2col buffer) + fused LN+GELU row kernel."""
+        cfg = self.config
+        if any(p.requires_grad for p in self.feature_extractor.parameters()) and torch.is_grad_enabled():
+            raise NotImplementedError(
+                "mtasr_b200: the conv feature encoder has no backward kernels; call freeze_feature_encoder() as every "
+                "reference run does (ref:run.sh:231, ref:src/arguments.py:134-136)")
+        layer_norm = cfg.feat_extract_norm == "layer"
+        with torch.no_grad():
+            l0 = self.feature_extractor.conv_layers[0]
+            w0 = l0.conv.weight.detach().float().contiguous()
+            b0 = None if l0.conv.bias is None else l0.conv.bias.detach().float()
+            if layer_norm:
+                y = K.conv0_fwd(x.float(), w0, b0, l0.layer_norm.weight.detach().float(), l0.layer_norm.bias.detach().float(),
+                                l0.layer_norm.eps, cfg.conv_kernel[0], cfg.conv_stride[0], True)
+            else:
+                raw = K.conv0_fwd(x.float(), w0, b0, None, None, 0.0, cfg.conv_kernel[0], cfg.conv_stride[0], False)
+                y = K.groupnorm_gelu(raw, l0.layer_norm.weight.detach().float(), l0.layer_norm.bias.detach().float(), l0.layer_norm.eps)
+            for i in range(1, len(self.feature_extractor.conv_layers)):
+                lyr = self.feature_extractor.conv_layers[i]
+                B, L, C = y.shape
+                k, s = cfg.conv_kernel[i], cfg.conv_stride[i]
+                Cout = lyr.conv.weight.shape[0]
+                wk = ops.bf16_of(lyr.conv.weight).permute(0, 2, 1).contiguous().view(Cout, k * C)
+                bias = None if lyr.conv.bias is None else lyr.conv.bias.detach().float()
+                Lout = (L - k) // s + 1
+                a = K.Operand(y, s * C, sb1=L * C, inner=C, phase=s, rows=(L + s - 1) // s)
+                if layer_norm:
+                    pre = torch.empty(B, Lout, Cout, device=y.device, dtype=F32)
+                    K.gemm(a, K.Operand(wk, k * C), Lout, Cout, k * C, K.Out(pre, Cout, sb1=Lout * Cout), batch=(1, B), bias=bias)
+                    y = K.layernorm_fwd(pre, lyr.layer_norm.weight.detach().float(), lyr.layer_norm.bias.detach().float(),
+                                        lyr.layer_norm.eps, post_gelu=True, save_stats=False)[0]
+                else:
+                    out = K.empty_act((B, Lout, Cout), BF, y.device)
+                    K.gemm(a, K.Operand(wk, k * C), Lout, Cout, k * C, K.Out(out, Cout, sb1=Lout * Cout), batch=(1, B), bias=bias,
+                           act=K.ACT_GELU)
+                    y = out
+        return y
+
+    def _relpos_table(self, T: int, device) -> torch.Tensor:
+        """hf:243-271: bias[h,q,k] = rel_attn_embed[bucket(k-q), h] is Toeplitz -> keep only table (H, 2T-1)."""
+        attn0 = self.encoder.layers[0].attention
+        rel = torch.arange(-(T - 1), T, device=device, dtype=torch.long)
+        bucket = relpos_bucket(rel, attn0.num_buckets, attn0.max_distance)
+        return attn0.rel_attn_embed.weight[bucket].t().contiguous()
+
+    @staticmethod
+    def _gate(h: torch.Tensor, attn) -> torch.Tensor:
+        """gru_rel_pos gate of hf:167-176 -> (B,H,T) fp32.  64->8 projection per head; tiny, kept as torch glue so
+        autograd delivers gradients to gru_rel_pos_linear / gru_rel_pos_const and back into the layer input."""
+        B, T, D = h.shape
+        H = attn.num_heads
+        proj = F.linear(h.view(B, T, H, D // H).float(), attn.gru_rel_pos_linear.weight.float(), attn.gru_rel_pos_linear.bias.float())
+        ab = torch.sigmoid(proj.view(B, T, H, 2, 4).sum(-1))
+        gate = ab[..., 0] * (ab[..., 1] * attn.gru_rel_pos_const.view(1, 1, H).float() - 1.0) + 2.0
+        return gate.permute(0, 2, 1).contiguous()
+
+    def _encoder_layer(self, x, layer, table, klen):
+        at, ff = layer.attention, layer.feed_forward
+        H = at.num_heads
+        eps = layer.layer_norm.eps
+        if self.config.do_stable_layer_norm:   # hf:355-366
+            h1 = ops.layer_norm(x, layer.layer_norm.weight, layer.layer_norm.bias, eps, BF)
+            x = ops.AttentionFn.apply(h1, x, at.q_proj.weight, at.q_proj.bias, at.k_proj.weight, at.k_proj.bias, at.v_proj.weight,
+                                      at.v_proj.bias, at.out_proj.weight, at.out_proj.bias, self._gate(h1, at), table, klen, H)
+            h2 = ops.layer_norm(x, layer.final_layer_norm.weight, layer.final_layer_norm.bias, eps, BF)
+            x = ops.FFNFn.apply(h2, x, ff.intermediate_dense.weight, ff.intermediate_dense.bias, ff.output_dense.weight,
+                                ff.output_dense.bias)
+        else:                                  # hf:314-329
+            y = ops.AttentionFn.apply(x, x, at.q_proj.weight, at.q_proj.bias, at.k_proj.weight, at.k_proj.bias, at.v_proj.weight,
+                                      at.v_proj.bias, at.out_proj.weight, at.out_proj.bias, self._gate(x, at), table, klen, H)
+            y = ops.layer_norm(y, layer.layer_norm.weight, layer.layer_norm.bias, eps, F32)
+            z = ops.FFNFn.apply(y, y, ff.intermediate_dense.weight, ff.intermediate_dense.bias, ff.output_dense.weight,
+                                ff.output_dense.bias)
+            x = ops.layer_norm(z, layer.final_layer_norm.weight, layer.final_layer_norm.bias, eps, F32)
+        return x
+
+    def _encoder_fwd(self, hidden: torch.Tensor, fmask: Optional[torch.Tensor], output_hidden_states: bool):
+        """hf:376-447 / hf:450-522."""
+        enc = self.encoder
+        B, T, D = hidden.shape
+        klen = None
+        if fmask is not None:
+            hidden = hidden * fmask.unsqueeze(-1).to(hidden.dtype)       # hf:476-479 zero padded frames
+            klen = fmask.sum(1).to(torch.int32).contiguous()
+        conv = enc.pos_conv_embed.conv
+        hidden = ops.PosConvFn.apply(hidden.contiguous(), conv.weight, conv.bias, conv.groups, None)
+        if not self.config.do_stable_layer_norm:
+            hidden = ops.layer_norm(hidden, enc.layer_norm.weight, enc.layer_norm.bias, enc.layer_norm.eps, F32)
+        table = self._relpos_table(T, hidden.device)
+        all_h = () if output_hidden_states else None
+        for layer in enc.layers:
+            if output_hidden_states:
+                all_h = all_h + (hidden,)
+            hidden = self._encoder_layer(hidden, layer, table, klen)
+        if self.config.do_stable_layer_norm:
+            hidden = ops.layer_norm(hidden, enc.layer_norm.weight, enc.layer_norm.bias, enc.layer_norm.eps, F32)
+        if output_hidden_states:
+            all_h = all_h + (hidden,)
+        return hidden, all_h
+
+    def forward(
+        self,
+        input_values: Optional[torch.Tensor],
+        attention_mask: Optional[torch.Tensor] = None,
+        mask_time_indices: Optional[torch.FloatTensor] = None,
+        output_attentions: Optional[bool] = None,
+        output_hidden_states: Optional[bool] = None,
+        return_dict: Optional[bool] = None,
+    ) -> Union[Tuple, WavLMBaseModelOutput]:
+        output_attentions = output_attentions if output_attentions is not None else self.config.output_attentions
+        output_hidden_states = output_hidden_states if output_hidden_states is not None else self.config.output_hidden_states
+        return_dict = return_dict if return_dict is not None else getattr(self.config, "return_dict", True)
+        if output_attentions:
+            raise NotImplementedError("mtasr_b200: output_attentions=True is not supported (probabilities are never materialised "
+                                      "per layer outside the kernels)")
+        if not input_values.is_cuda:
+            raise K._lib.MtasrError("mtasr_b200.WavLMModel runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self.adapter is None:
+            raise ValueError("WavLMModel requires config.add_adapter=True (as the reference does, ref:models/modeling_wavlm.py:452-461)")
+
+        feats = self._feature_extractor_fwd(input_values)                    # (B,T,C) bf16
+        B, T, C = feats.shape
+        fmask = None
+        if attention_mask is not None:
+            fmask = self._get_feature_vector_attention_mask(T, attention_mask, add_adapter=False)
+        fp = self.feature_projection
+        normed_b = ops.layer_norm(feats, fp.layer_norm.weight, fp.layer_norm.bias, fp.layer_norm.eps, BF)
+        with torch.no_grad():   # `extract_features` output (returned, never on the loss path): fp32 copy of the same LN
+            normed_f = K.layernorm_fwd(feats, fp.layer_norm.weight.detach().float(), fp.layer_norm.bias.detach().float(),
+                                       fp.layer_norm.eps, out_bf16=False, out_f32=True, save_stats=False)[1]
+        hidden = ops.linear(normed_b, fp.projection.weight, fp.projection.bias, out_dtype=F32)
+        hidden = self._mask_hidden_states(hidden, mask_time_indices=mask_time_indices, attention_mask=fmask)
+        enc_out, all_h = self._encoder_fwd(hidden, fmask, output_hidden_states)
+        last, down = self.adapter(enc_out)
+        if not return_dict:
+            return (last, normed_f) + ((all_h,) if all_h is not None else ())
+        return WavLMBaseModelOutput(last_hidden_state=last, encoder_hidden_state=enc_out, wavlm_down_hidden_states=down,
+                                    extract_features=normed_f, hidden_states=all_h, attentions=None)

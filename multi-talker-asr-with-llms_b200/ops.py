@@ -1,0 +1,436 @@
+"""torch.autograd.Functions over the C-ABI kernels.
+
+Every Function keeps its saved tensors untouched in backward (safe under retain_graph=True: the reference's PCGrad
+trainer back-propagates K+1 times per step, ref:src/trainer_seq2seq.py:1071-1141), holds no hidden global state
+(safe under torch.utils.checkpoint) and honours ctx.needs_input_grad (frozen sub-modules,
+ref:utils/unfreeze_utils.py:39-96).  Parameters stay ordinary fp32 nn.Parameters; bf16 operand copies are made
+on the fly and cached per parameter version.
+"""
+import weakref
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+
+from . import kernels as K
+
+BF = torch.bfloat16
+F32 = torch.float32
+
+_bf16_cache = {}
+
+
+def bf16_of(p: torch.Tensor) -> torch.Tensor:
+    """bf16 copy of a (parameter) tensor, cached on (identity, version) so frozen weights are converted once."""
+    if p.dtype == BF:
+        return p
+    key = id(p)
+    hit = _bf16_cache.get(key)
+    if hit is not None:
+        ref, ver, ptr, val = hit
+        if ref() is p and ver == p._version and ptr == p.data_ptr():
+            return val
+    val = K.cast_bf16(p.detach())
+    try:
+        _bf16_cache[key] = (weakref.ref(p, lambda _r, k=key: _bf16_cache.pop(k, None)), p._version, p.data_ptr(), val)
+    except TypeError:
+        pass
+    return val
+
+
+def _flat2d(x: torch.Tensor) -> torch.Tensor:
+    return x.contiguous().view(-1, x.shape[-1])
+
+
+# ------------------------------------------------------------------------------------------------------ LayerNorm
+class LayerNormFn(Function):
+    """hf:100-105, hf:314-366, hf:513, ref:models/separator.py:158-165 -- LayerNorm over the last dim."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, out_dtype):
+        want_bf = out_dtype == BF
+        yb, yf, mean, rstd = K.layernorm_fwd(x, gamma.detach().float(), beta.detach().float(), eps, out_bf16=want_bf, out_f32=not want_bf)
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        return yb if want_bf else yf
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        need_x, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        x_f32 = x.dtype == F32
+        dxf, dxb, dg, db = K.layernorm_bwd(dy, x, mean, rstd, gamma.detach().float(), want_f32=need_x and x_f32,
+                                           want_bf16=need_x and not x_f32, want_param_grads=need_p)
+        dx = (dxf if x_f32 else dxb) if need_x else None
+        return dx, dg, db, None, None
+
+
+def layer_norm(x, gamma, beta, eps, out_dtype=BF):
+    return LayerNormFn.apply(x, gamma, beta, eps, out_dtype)
+
+
+# ------------------------------------------------------------------------------------------------------ Linear
+class LinearFn(Function):
+    """y = act(x W^T + b) (+ residual) on the tcgen05 GEMM; backward = dgrad + wgrad GEMMs + bias column sum."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, residual, out_dtype):
+        shp = x.shape
+        xb = K.cast_bf16(_flat2d(x))
+        wb = bf16_of(w)
+        res2 = None if residual is None else _flat2d(residual)
+        want_aux = act != K.ACT_NONE
+        out = K.linear_fwd(xb, wb, None if b is None else b.detach().float(), act=act, residual=res2, out_dtype=out_dtype,
+                           want_aux=want_aux)
+        y, aux = out if want_aux else (out, None)
+        ctx.act = act
+        ctx.x_dtype = x.dtype
+        ctx.has_res = residual is not None
+        ctx.has_bias = b is not None
+        ctx.save_for_backward(xb, wb, aux)
+        return y.view(*shp[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        xb, wb, aux = ctx.saved_tensors
+        dy2 = _flat2d(dy)
+        du = K.act_bwd(dy2, aux, K.ACT_GELU_BWD if ctx.act == K.ACT_GELU else K.ACT_RELU_BWD) if ctx.act != K.ACT_NONE \
+            else K.cast_bf16(dy2)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = K.linear_dgrad(du, wb, out_dtype=ctx.x_dtype).view(*dy.shape[:-1], wb.shape[1])
+        if ctx.needs_input_grad[1]:
+            dw = K.linear_wgrad(du, xb)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = K.colsum(du)
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[4]) else None
+        return dx, dw, db, None, dres, None
+
+
+def linear(x, w, b=None, act=K.ACT_NONE, residual=None, out_dtype=BF):
+    return LinearFn.apply(x, w, b, act, residual, out_dtype)
+
+
+# ------------------------------------------------------------------------------------------------------ FFN
+class FFNFn(Function):
+    """res + W2 GELU(W1 h + b1) + b2  (hf:274-295 with the residual add of hf:366/329 fused into the 2nd epilogue).
+    The GELU backward is fused into the W2-dgrad epilogue (act 3)."""
+
+    @staticmethod
+    def forward(ctx, h, res, w1, b1, w2, b2):
+        shp = h.shape
+        hb = K.cast_bf16(_flat2d(h))
+        w1b, w2b = bf16_of(w1), bf16_of(w2)
+        a, u = K.linear_fwd(hb, w1b, b1.detach().float(), act=K.ACT_GELU, want_aux=True)
+        y = K.linear_fwd(a, w2b, b2.detach().float(), residual=_flat2d(res), out_dtype=F32)
+        ctx.h_dtype = h.dtype
+        ctx.save_for_backward(hb, u, a, w1b, w2b)
+        return y.view(shp[:-1] + (w2.shape[0],))
+
+    @staticmethod
+    def backward(ctx, dy):
+        hb, u, a, w1b, w2b = ctx.saved_tensors
+        dyb = K.cast_bf16(_flat2d(dy))
+        du = K.linear_dgrad(dyb, w2b, act=K.ACT_GELU_BWD, act_src=u)
+        dh = dw1 = db1 = dw2 = db2 = None
+        if ctx.needs_input_grad[0]:
+            dh = K.linear_dgrad(du, w1b, out_dtype=ctx.h_dtype).view(dy.shape[:-1] + (w1b.shape[1],))
+        if ctx.needs_input_grad[2]:
+            dw1 = K.linear_wgrad(du, hb)
+        if ctx.needs_input_grad[3]:
+            db1 = K.colsum(du)
+        if ctx.needs_input_grad[4]:
+            dw2 = K.linear_wgrad(dyb, a)
+        if ctx.needs_input_grad[5]:
+            db2 = K.colsum(dyb)
+        return dh, (dy if ctx.needs_input_grad[1] else None), dw1, db1, dw2, db2
+
+
+# ------------------------------------------------------------------------------------------------------ attention
+class AttentionFn(Function):
+    """res + out_proj(softmax(Q K^T / sqrt(d) + gate * relpos + key mask) V)   (hf:147-241, torch:6244-6695).
+
+    h (B,T,D) is the attention input (bf16), gate (B,H,T) fp32 the gru_rel_pos gate (hf:167-176), table (H, 2T-1) the
+    Toeplitz relative-position bias (hf:243-271) so bias[h,q,k] = table[h, k-q+T-1]; klen (B,) int32 valid key
+    lengths or None.  QK^T and PV are batched tcgen05 GEMMs over (head, utterance); the gated bias, mask and softmax
+    run in one row kernel that never materialises the (B*H,T,T) fp32 bias of the reference."""
+
+    @staticmethod
+    def forward(ctx, h, res, wq, bq, wk, bk, wv, bv, wo, bo, gate, table, klen, H):
+        B, T, D = h.shape
+        d = D // H
+        hb = K.cast_bf16(_flat2d(h))
+        wqkv = torch.cat([bf16_of(wq), bf16_of(wk), bf16_of(wv)], 0)
+        bqkv = torch.cat([bq.detach().float(), bk.detach().float(), bv.detach().float()], 0)
+        wob = bf16_of(wo)
+        qkv = K.linear_fwd(hb, wqkv, bqkv)                                   # (B*T, 3D) bf16: [q | k | v], head-major
+        Tp = (T + 7) // 8 * 8
+        S = torch.empty(B, H, T, Tp, device=h.device, dtype=F32)
+        K.gemm(K.Operand(qkv, 3 * D, sb0=d, sb1=T * 3 * D, rows=T), K.Operand(qkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=D, rows=T),
+               T, T, d, K.Out(S, Tp, sb0=T * Tp, sb1=H * T * Tp), batch=(H, B))
+        scale = float(d) ** -0.5
+        gate = gate.detach().contiguous().float()
+        table = table.detach().contiguous().float()
+        P = K.attn_softmax_fwd(S, gate, table, klen, B, H, T, Tp, scale)
+        del S
+        O = torch.empty(B * T, D, device=h.device, dtype=BF)
+        K.gemm(K.Operand(P, Tp, sb0=T * Tp, sb1=H * T * Tp), K.Operand(qkv, 3 * D, major=1, sb0=d, sb1=T * 3 * D, offset=2 * D, rows=T),
+               T, d, T, K.Out(O, D, sb0=d, sb1=T * D), batch=(H, B))
+        y = K.linear_fwd(O, wob, bo.detach().float(), residual=_flat2d(res), out_dtype=F32)
+        ctx.dims = (B, T, D, H, Tp, scale)
+        ctx.h_dtype = h.dtype
+        ctx.save_for_backward(hb, qkv, P, O, wqkv, wob, gate, table)
+        return y.view(B, T, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        hb, qkv, P, O, wqkv, wob, gate, table = ctx.saved_tensors
+        B, T, D, H, Tp, scale = ctx.dims
+        d = D // H
+        need = ctx.needs_input_grad
+        dyb = K.cast_bf16(_flat2d(dy))
+        dO = K.linear_dgrad(dyb, wob)                                         # (B*T, D) bf16
+        dwo = K.linear_wgrad(dyb, O) if need[8] else None
+        dbo = K.colsum(dyb) if need[9] else None
+        dP = torch.empty(B, H, T, Tp, device=dy.device, dtype=F32)
+        K.gemm(K.Operand(dO, D, sb0=d, sb1=T * D, rows=T), K.Operand(qkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=2 * D, rows=T),
+               T, T, d, K.Out(dP, Tp, sb0=T * Tp, sb1=H * T * Tp), batch=(H, B))
+        dqkv = torch.empty(B * T, 3 * D, device=dy.device, dtype=BF)
+        # dV = P^T dO
+        K.gemm(K.Operand(P, Tp, major=1, sb0=T * Tp, sb1=H * T * Tp, rows=T), K.Operand(dO, D, major=1, sb0=d, sb1=T * D, rows=T),
+               T, d, T, K.Out(dqkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=2 * D), batch=(H, B))
+        dS, dgate, dtable = K.attn_softmax_bwd(P, dP, gate, table, B, H, T, Tp, scale)
+        del dP
+        # dQ = dS K ; dK = dS^T Q   (dS already carries the 1/sqrt(d) factor)
+        K.gemm(K.Operand(dS, Tp, sb0=T * Tp, sb1=H * T * Tp), K.Operand(qkv, 3 * D, major=1, sb0=d, sb1=T * 3 * D, offset=D, rows=T),
+               T, d, T, K.Out(dqkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=0), batch=(H, B))
+        K.gemm(K.Operand(dS, Tp, major=1, sb0=T * Tp, sb1=H * T * Tp, rows=T), K.Operand(qkv, 3 * D, major=1, sb0=d, sb1=T * 3 * D, offset=0, rows=T),
+               T, d, T, K.Out(dqkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=D), batch=(H, B))
+        dh = K.linear_dgrad(dqkv, wqkv, out_dtype=ctx.h_dtype).view(B, T, D) if need[0] else None
+        dwq = dwk = dwv = dbq = dbk = dbv = None
+        if need[2] or need[4] or need[6]:
+            dwqkv = K.linear_wgrad(dqkv, hb)
+            dwq, dwk, dwv = dwqkv[:D], dwqkv[D:2 * D], dwqkv[2 * D:]
+        if need[3] or need[5] or need[7]:
+            dbqkv = K.colsum(dqkv)
+            dbq, dbk, dbv = dbqkv[:D], dbqkv[D:2 * D], dbqkv[2 * D:]
+        return (dh, dy if need[1] else None, dwq, dbq, dwk, dbk, dwv, dbv, dwo, dbo,
+                dgate if need[10] else None, dtable if need[11] else None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------------ pos conv
+def _posconv_weight_layout(w: torch.Tensor, G: int) -> torch.Tensor:
+    """torch grouped-conv weight (D, D/G, k) -> (g, out, tap, c) bf16, K-major for the implicit GEMM."""
+    D, cg, k = w.shape
+    return w.detach().view(G, D // G, cg, k).permute(0, 1, 3, 2).contiguous().to(BF)
+
+
+class PosConvFn(Function):
+    """x + GELU(grouped_conv1d(x, w, bias, k, pad=k//2)[:T])   (hf:48-90 + hf:403/481; `w` is the already
+    weight-normalised kernel g*v/||v||, computed by torch so autograd carries the gradient to original0/original1).
+    One implicit-GEMM launch over (group, utterance): A = taps x 64-channel slices of the zero-padded input."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, G, vlen):
+        B, T, D = x.shape
+        cg = D // G
+        k = w.shape[2]
+        pad = k // 2
+        Tpad = T + k
+        xp = K.pad_cast(x, pad, Tpad, vlen)                                  # (B, Tpad, D) bf16; rows >= vlen zeroed
+        wk = _posconv_weight_layout(w, G)
+        u = torch.empty(B, T, D, device=x.device, dtype=BF)
+        y = torch.empty(B, T, D, device=x.device, dtype=F32)
+        xres = x if vlen is None else (x * (torch.arange(T, device=x.device)[None, :] < vlen[:, None]).unsqueeze(-1))
+        xres = xres.contiguous()
+        K.gemm(K.Operand(xp, D, sb0=cg, sb1=Tpad * D, inner=cg, phase=1, rows=Tpad), K.Operand(wk, k * cg, sb0=cg * k * cg),
+               T, cg, k * cg, K.Out(y, D, sb0=cg, sb1=T * D), batch=(G, B), bias=bias.detach().float(), bias_sb0=cg,
+               act=K.ACT_GELU, aux=u, residual=K.Out(xres, D, sb0=cg, sb1=T * D))
+        ctx.dims = (B, T, D, G, k)
+        ctx.save_for_backward(xp, u, w, vlen)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xp, u, w, vlen = ctx.saved_tensors
+        B, T, D, G, k = ctx.dims
+        cg = D // G
+        pad = k // 2
+        Tpad = T + k
+        du = K.act_bwd(dy.contiguous().view(B * T, D), u.view(B * T, D), K.ACT_GELU_BWD).view(B, T, D)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dx[t'] = sum_{o,tap} du[t' - tap + pad, o] w[o,c,tap]: conv of du (left pad k-1-pad) with flipped taps
+            dup = K.pad_cast(du, k - 1 - pad, Tpad)
+            wf = w.detach().view(G, cg, cg, k).flip(3).permute(0, 2, 3, 1).contiguous().to(BF)   # (g, c_in, tap', o)
+            dxc = torch.empty(B, T, D, device=dy.device, dtype=F32)
+            K.gemm(K.Operand(dup, D, sb0=cg, sb1=Tpad * D, inner=cg, phase=1, rows=Tpad), K.Operand(wf, k * cg, sb0=cg * k * cg),
+                   T, cg, k * cg, K.Out(dxc, D, sb0=cg, sb1=T * D), batch=(G, B), residual=K.Out(dy.contiguous(), D, sb0=cg, sb1=T * D))
+            if vlen is not None:
+                dxc = dxc * (torch.arange(T, device=dy.device)[None, :] < vlen[:, None]).unsqueeze(-1)
+            dx = dxc
+        if ctx.needs_input_grad[1]:
+            # dW[g,o,tap,c] = sum_{b,t} du[b,t,g*cg+o] xp[b,t+tap,g*cg+c]; rows flattened over (b, padded t)
+            du2 = K.pad_cast(du, 0, Tpad)                                      # zero rows kill cross-utterance terms
+            xpe = torch.zeros(B * Tpad + k, D, device=dy.device, dtype=BF)
+            xpe[: B * Tpad] = xp.view(B * Tpad, D)
+            dwk = torch.empty(G, cg, k, cg, device=dy.device, dtype=F32)       # (g, o, tap, c)
+            for g in range(G):                                                 # batch dims are (tap) only: 16 launches
+                K.gemm(K.Operand(du2, D, major=1, offset=g * cg, rows=B * Tpad),
+                       K.Operand(xpe, D, major=1, sb0=D, offset=g * cg, rows=B * Tpad), cg, cg, B * Tpad,
+                       K.Out(dwk, k * cg, sb0=cg, offset=g * cg * k * cg), batch=(k, 1))
+            dw = dwk.permute(0, 1, 3, 2).reshape(D, cg, k)
+        if ctx.needs_input_grad[2]:
+            db = K.colsum(du.view(B * T, D))
+        return dx, dw, db, None, None
+
+
+# ------------------------------------------------------------------------------------------------------ LSTM
+class LSTMLayerFn(Function):
+    """One layer of ref:models/separator.py:27-59 (CustomLSTMCell: gates = W [x_t, h_t] + b, order i,f,g,o).
+    x (B,T,In) -> h (B,T,Hs) fp32.  Input half as one batched GEMM, recurrent half in the persistent kernel."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        B, T, In = x.shape
+        Hs = W.shape[0] // 4
+        xb = K.cast_bf16(_flat2d(x))
+        Wb = bf16_of(W)                                                        # (4Hs, In+Hs)
+        ld = Wb.stride(0)
+        xg = torch.empty(B * T, 4 * Hs, device=x.device, dtype=F32)
+        K.gemm(K.Operand(xb, In), K.Operand(Wb, ld), B * T, 4 * Hs, In, K.Out(xg, 4 * Hs), bias=b.detach().float())
+        whh = Wb[:, In:]
+        outs = []
+        for b0 in range(0, B, 64):
+            outs.append(K.lstm_fwd(xg.view(B, T, 4 * Hs)[b0:b0 + 64].contiguous() if B > 64 else xg.view(B, T, 4 * Hs), whh, ld,
+                                   want_h_f32=True))
+        if len(outs) == 1:
+            hb, hf, c, gates = outs[0]
+        else:
+            hb, hf, c, gates = (torch.cat([o[i] for o in outs], 0) for i in range(4))
+        ctx.dims = (B, T, In, Hs)
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(xb, Wb, hb, c, gates)
+        return hf
+
+    @staticmethod
+    def backward(ctx, dh):
+        xb, Wb, hb, c, gates = ctx.saved_tensors
+        B, T, In, Hs = ctx.dims
+        ld = Wb.stride(0)
+        whh = Wb[:, In:]
+        dh = dh.contiguous().float()
+        parts = []
+        for b0 in range(0, B, 64):
+            sl = slice(b0, b0 + 64)
+            parts.append(K.lstm_bwd(dh[sl].contiguous(), gates[sl].contiguous(), c[sl].contiguous(), whh, ld))
+        dg = parts[0] if len(parts) == 1 else torch.cat(parts, 0)              # (B,T,4Hs) bf16
+        dg2 = dg.view(B * T, 4 * Hs)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(B * T, In, device=dh.device, dtype=ctx.x_dtype)
+            K.gemm(K.Operand(dg2, 4 * Hs), K.Operand(Wb, ld, major=1), B * T, In, 4 * Hs, K.Out(dx, In))
+            dx = dx.view(B, T, In)
+        if ctx.needs_input_grad[1]:
+            dW = torch.empty(4 * Hs, In + Hs, device=dh.device, dtype=F32)
+            # input half: dgates^T x
+            K.gemm(K.Operand(dg2, 4 * Hs, major=1), K.Operand(xb, In, major=1), 4 * Hs, In, B * T, K.Out(dW, In + Hs))
+            # recurrent half: sum_t dgates_t^T h_{t-1}  (per utterance: rows shifted by one step; accumulate over b)
+            for bi in range(B):
+                K.gemm(K.Operand(dg, 4 * Hs, major=1, offset=(bi * T + 1) * 4 * Hs, rows=T - 1),
+                       K.Operand(hb, Hs, major=1, offset=bi * T * Hs, rows=T - 1), 4 * Hs, Hs, T - 1,
+                       K.Out(dW, In + Hs, offset=In), accumulate=bi > 0) if T > 1 else None
+            if T == 1:
+                dW[:, In:] = 0
+        if ctx.needs_input_grad[2]:
+            db = K.colsum(dg2)
+        return dx, dW, db
+
+
+# ------------------------------------------------------------------------------------------------------ CTC head
+class CTCHeadFn(Function):
+    """Per-utterance CTC negative log-likelihood of one head, fused with its vocabulary projection.
+
+    Replaces ctc_lo -> log_softmax -> torch.nn.CTCLoss(reduction='none', zero_infinity=True, blank=V-1)
+    (ref:models/ctc.py:129-160, 51-65).  The (B,T,V) logits / log-probs are never written: the vocab GEMM's epilogue
+    produces per-tile (max, sum-exp) partials -> row LSE, the <= L+1 lattice columns of every utterance come from a
+    small gathered GEMM, the alpha/beta recursions run one warp per utterance.  Backward regenerates softmax tiles
+    (GEMM mode 2, scaled per row by the upstream gradient) for the dense term and adds the sparse occupancy term."""
+
+    @staticmethod
+    def forward(ctx, hs, w, bias, hlens, ys, ylens, blank):
+        B, T, D = hs.shape
+        V = w.shape[0]
+        hb = K.cast_bf16(_flat2d(hs))
+        wb = bf16_of(w)
+        bf = bias.detach().float()
+        nt = K.gemm_n_tiles(V)
+        part = torch.empty(B * T, nt, 4, device=hs.device, dtype=F32)
+        K.gemm(K.Operand(hb, D), K.Operand(wb, D), B * T, V, D, None, bias=bf, mode=1, lse_part=part)
+        lse, _ = K.lse_finalize(part, B * T, nt)
+        del part
+        Lmax = int(ys.shape[1]) if ys.numel() else 0
+        Lp = (Lmax + 1 + 63) // 64 * 64
+        ys = ys.contiguous()
+        hlens = hlens.to(torch.int64).contiguous()
+        ylens = ylens.to(torch.int64).contiguous()
+        wg, bg = K.ctc_gather_rows(wb, bf, ys, ylens, Lp, blank)
+        glog = torch.empty(B, T, Lp, device=hs.device, dtype=F32)
+        K.gemm(K.Operand(hb, D, sb0=T * D), K.Operand(wg, D, sb0=Lp * D), T, Lp, D, K.Out(glog, Lp, sb0=T * Lp), batch=(B, 1),
+               bias=bg, bias_sb0=Lp)
+        lse = lse.view(B, T)
+        nll, nll_raw, alpha, coff = K.ctc_alpha_fwd(glog, lse, ys, hlens, ylens, Lmax)
+        ctx.dims = (B, T, D, V, Lp, Lmax, blank)
+        ctx.hs_dtype = hs.dtype
+        ctx.save_for_backward(hb, wb, bf, wg, glog, lse, alpha, coff, nll_raw, hlens, ys, ylens)
+        return nll
+
+    @staticmethod
+    def backward(ctx, gout):
+        hb, wb, bf, wg, glog, lse, alpha, coff, nll_raw, hlens, ys, ylens = ctx.saved_tensors
+        B, T, D, V, Lp, Lmax, blank = ctx.dims
+        dev = gout.device
+        dG, rowscale = K.ctc_beta_bwd(glog, lse, ys, hlens, ylens, Lmax, alpha, coff, nll_raw, gout.contiguous().float())
+        dGb = K.cast_bf16(dG)
+        Vp = (V + 7) // 8 * 8
+        P = torch.empty(B * T, Vp, device=dev, dtype=BF)                       # softmax * upstream, regenerated
+        K.gemm(K.Operand(hb, D), K.Operand(wb, D), B * T, V, D, K.Out(P, Vp), bias=bf, mode=2, row_vec=lse.view(-1),
+               row_scale=rowscale.view(-1))
+        dh = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dhf = torch.empty(B * T, D, device=dev, dtype=F32)
+            K.gemm(K.Operand(P, Vp), K.Operand(wb, D, major=1), B * T, D, V, K.Out(dhf, D))
+            K.gemm(K.Operand(dGb, Lp, sb0=T * Lp), K.Operand(wg, D, major=1, sb0=Lp * D), T, D, Lp, K.Out(dhf, D, sb0=T * D),
+                   batch=(B, 1), accumulate=True)
+            dh = dhf.view(B, T, D).to(ctx.hs_dtype)
+        need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        if need_w or need_b:
+            dw = torch.empty(V, D, device=dev, dtype=F32)
+            K.gemm(K.Operand(P, Vp, major=1), K.Operand(hb, D, major=1), V, D, B * T, K.Out(dw, D))
+            dwg = torch.empty(B, Lp, D, device=dev, dtype=F32)
+            K.gemm(K.Operand(dGb, Lp, major=1, sb0=T * Lp, rows=T), K.Operand(hb, D, major=1, sb0=T * D, rows=T), Lp, D, T,
+                   K.Out(dwg, D, sb0=Lp * D), batch=(B, 1))
+            db = K.colsum(P)[:V].contiguous()
+            K.ctc_scatter_rows(dwg, dG.sum(1).contiguous(), ys, ylens, blank, dw, db)
+            if not need_w:
+                dw = None
+            if not need_b:
+                db = None
+        return dh, dw, db, None, None, None, None
+
+
+def ctc_head_argmax(hs: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """argmax_v (hs W^T + b) without writing the logits (ref:models/ctc.py:182-190): GEMM mode 1 + finalize."""
+    B, T, D = hs.shape
+    V = w.shape[0]
+    hb = K.cast_bf16(_flat2d(hs))
+    wb = bf16_of(w)
+    nt = K.gemm_n_tiles(V)
+    part = torch.empty(B * T, nt, 4, device=hs.device, dtype=F32)
+    K.gemm(K.Operand(hb, D), K.Operand(wb, D), B * T, V, D, None, bias=bias.detach().float(), mode=1, lse_part=part)
+    _, am = K.lse_finalize(part, B * T, nt, want_lse=False, want_argmax=True)
+    return am.view(B, T)
+
+
+def ctc_head_logits(hs: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """Dense (B,T,V) fp32 logits for the API-compat methods CTC.logits/.softmax/.log_softmax (not on the hot path)."""
+    return LinearFn.apply(hs, w, bias, K.ACT_NONE, None, F32)

@@ -150,6 +150,8 @@ def gen_ctc():
         (grad,) = torch.autograd.grad((nll * w.to(dt)).sum(), lg)
         assert np.abs(n64 - nll.detach().numpy()).max() < tol_n, dt
         assert np.abs(g64 * w.numpy()[:, None, None] - grad.numpy()).max() < tol_g, dt
+        if dt == torch.float64:
+            nll_f64, grad_f64 = nll.detach(), grad
     # brute force on a tiny case
     lp_small = ctc_ref.log_softmax(np.random.RandomState(0).randn(5, 4))
     for y in ([0], [1, 1], [0, 2], []):
@@ -157,7 +159,8 @@ def gen_ctc():
         b = ctc_ref.ctc_brute_force(lp_small, y, 3)
         assert abs(a - b) < 1e-10, (y, a, b)
     print("[ctc] numpy oracle == torch.nn.CTCLoss == brute force")
-    npz("ctc_small.npz", logits=logits, hlens=hlens, ys=ys, ylens=ylens, nll=nll, upstream=w, grad=grad, blank=V - 1)
+    npz("ctc_small.npz", logits=logits, hlens=hlens, ys=ys, ylens=ylens, nll=nll_f64, upstream=w, grad=grad_f64, blank=V - 1,
+        nll_f32=nll, grad_f32=grad)
 
 
 def gen_host():

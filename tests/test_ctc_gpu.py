@@ -28,7 +28,7 @@ def test_ctc_golden(cuda, golden_dir):
     t = lambda k, dt=None: torch.from_numpy(g[k]).to(cuda) if dt is None else torch.from_numpy(g[k]).to(cuda).to(dt)
     nll, dl = _ctc_dense(Kn, t("logits"), t("hlens"), t("ys"), t("ylens"), int(g["blank"]), t("upstream"))
     ref_nll, ref_grad = t("nll"), t("grad")
-    assert torch.allclose(nll, ref_nll, rtol=1e-5, atol=1e-5), (nll, ref_nll)
+    assert torch.allclose(nll.double(), ref_nll.double(), rtol=1e-5, atol=1e-5), (nll, ref_nll)
     rel = ((dl - ref_grad).norm() / ref_grad.norm()).item()
     assert rel < 1e-5, rel
     assert nll[5].item() == 0.0 and dl[5].abs().max().item() == 0.0      # infeasible row: zero_infinity
