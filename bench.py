@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark: WavLM-Large encoder + separator + serialized-CTC forward+backward throughput in audio-seconds/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              (N > 1: launched under torch.distributed.run)
+    python bench.py --impl reference ...                             (the reference algorithm on the host CPU cores)
+
+Workload = BASELINE.json configs[1] ("cfg2"): WavLM-Large (24 layers, D=1024) + Separator(896) + 2 CTC heads with the
+Llama-3 vocabulary (V=128259) on synthetic LibriMix-shaped 2-speaker 10 s 16 kHz mixtures, batch 32 per GPU, bf16
+operands / fp32 accumulation, feature encoder frozen (as in every reference run).  One step = one forward + backward of
+the serialized-CTC loss through the repo's public modules (every gradient of encoder, separator and CTC heads is
+produced; for N > 1 the NCCL gradient all-reduce is inside the step).  Prints ONE JSON line (see README / DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "encoder+serialized-CTC fwd+bwd audio-sec/s"
+UNIT = "audio-s/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--speakers", type=int, default=2)
+    ap.add_argument("--layers", type=int, default=0, help="debug only: override the number of encoder layers")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-run", action="store_true", help="ncu helper: 1 warm-up + 1 step, no e2e/roofline/cpu legs")
+    return ap.parse_args()
+
+
+def synth_batch(B, S, n_spk, vocab, seed):
+    """LibriMix-shaped synthetic batch: sum of low-passed noise 'speakers' with random gains, per-utterance
+    zero-mean / unit-variance (what Wav2Vec2FeatureExtractor(do_normalize=True) yields), fixed length; per-speaker targets
+    of U(2,6) tokens per second with ids U[0, vocab-3), pad = vocab-2, blank = vocab-1, one forced repeat."""
+    g = torch.Generator().manual_seed(seed)
+    wav = torch.zeros(B, S)
+    k = 0.85
+    w = (k ** torch.arange(64, dtype=torch.float32)).flip(0)[None, None] * (1 - k)
+    for _ in range(n_spk):
+        n = torch.randn(B, S, generator=g)
+        lp = torch.nn.functional.conv1d(torch.nn.functional.pad(n[:, None], (63, 0)), w)[:, 0]
+        wav += lp * (0.5 + 0.5 * torch.rand(B, 1, generator=g))
+    wav = (wav - wav.mean(1, keepdim=True)) / torch.sqrt(wav.var(1, keepdim=True, unbiased=False) + 1e-7)
+    mask = torch.ones(B, S, dtype=torch.int32)
+    sec = S / 16000.0
+    lo, hi = max(1, int(2 * sec)), max(2, int(6 * sec))
+    pad_id = vocab - 2
+    labels, lens = [], []
+    for _ in range(n_spk):
+        L = torch.randint(lo, hi + 1, (B,), generator=g)
+        y = torch.full((B, int(L.max())), pad_id, dtype=torch.long)
+        for b in range(B):
+            y[b, : L[b]] = torch.randint(0, vocab - 3, (int(L[b]),), generator=g)
+            if L[b] >= 3:
+                y[b, 2] = y[b, 1]
+        labels.append(y)
+        lens.append(L)
+    return wav, mask, labels, lens
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed regions run."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(s for s, p in zip(sm, pw) if p >= 0.5 * max(pw)) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+
+
+# --------------------------------------------------------------------------------------------------- reference arm
+def run_cpu_reference(args, steps, warmup, budget_s):
+    """The reference algorithm on the host cores: the oracle's restatement of the reference modules (torch CPU fp32, the
+    same library kernels the reference itself runs), Large encoder + separator + N CTC heads + serialized-CTC loss,
+    fwd+bwd with the feature encoder frozen, on a bounded sample (few utterances per step) of the cfg2 workload."""
+    from oracle.model_ref import RefCTC, RefSeparator, RefWavLMModel, ref_hybrid_ctc
+    from mtasr_b200.configs import V_LLAMA3_CTC, wavlm_config
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    cfg = wavlm_config("large", **({"num_hidden_layers": args.layers} if args.layers else {}))
+    S = int(args.seconds * 16000)
+    enc = RefWavLMModel(cfg).eval()
+    for p in enc.feature_extractor.parameters():
+        p.requires_grad_(False)
+    for p in enc.adapter.parameters():
+        p.requires_grad_(False)
+    sep = RefSeparator(cfg.hidden_size, 896, args.speakers).eval()
+    heads = torch.nn.ModuleList(RefCTC(V_LLAMA3_CTC, cfg.hidden_size) for _ in range(args.speakers))
+    params = [p for m in (enc, sep, heads) for p in m.parameters() if p.requires_grad]
+
+    def step(Bc, seed):
+        wav, mask, labels, lens = synth_batch(Bc, S, args.speakers, V_LLAMA3_CTC, seed)
+        t0 = time.perf_counter()
+        _, h, _, _ = enc(wav, mask.long())
+        sp = sep(h)
+        fm = enc.frame_mask_x0(h.shape[1], mask.long())
+        loss, _ = ref_hybrid_ctc(heads, sp, fm, labels, lens)
+        torch.autograd.grad(loss, params, allow_unused=True)
+        return time.perf_counter() - t0
+
+    t1 = step(1, 100)                                   # warm-up / calibration on one utterance
+    n_steps = max(1, steps) + max(0, warmup - 1)
+    Bc = 1
+    for cand in (4, 2):
+        if t1 * cand * n_steps <= budget_s:
+            Bc = cand
+            break
+    for i in range(max(0, warmup - 1)):
+        step(Bc, 200 + i)
+    ts = [step(Bc, 300 + i) for i in range(max(1, steps))]
+    dt = sum(ts) / len(ts)
+    return dict(value=Bc * args.seconds / dt, ms_per_step=dt * 1e3, cores=cores, batch=Bc, steps=len(ts),
+                sample=f"{Bc} utterance(s) x {args.seconds:g} s per step of the cfg2 workload (WavLM-Large, {args.speakers} heads, "
+                       f"V={V_LLAMA3_CTC}), {len(ts)} timed step(s), torch CPU fp32, {cores} threads")
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = run_cpu_reference(args, args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, r["batch"], 1),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch, world):
+    return {"workload": "cfg2: WavLM-Large + Separator(896) + serialized CTC (2mix), 10 s 16 kHz, fwd+bwd, feature encoder frozen"
+            if not args.layers else f"DEBUG {args.layers}-layer encoder",
+            "encoder": "wavlm-large-shaped (24L, D=1024, H=16, F=4096), random init", "speakers": args.speakers,
+            "seconds": args.seconds, "batch_per_gpu": batch, "global_batch": batch * world, "vocab": 128259,
+            "separator_hidden": 896, "parallelism": f"dp{world}", "spec_augment": "off", "dropout": 0.0,
+            "l2": "working set per step (>1 GB of weights, >20 GB of activations) exceeds the 126 MB L2; no explicit flush"}
+
+
+# --------------------------------------------------------------------------------------------------------- our arm
+def main_ours(args):
+    import torch.distributed as dist
+    from mtasr_b200 import kernels as K
+    from mtasr_b200.configs import V_LLAMA3_CTC, algorithmic_flops, wavlm_config
+    from mtasr_b200.pipeline import SerializedCTCPath
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(1234)
+    cfg = wavlm_config("large", **({"num_hidden_layers": args.layers} if args.layers else {}))
+    S = int(args.seconds * 16000)
+    B = args.batch
+    model = SerializedCTCPath(cfg, talker_numbers=args.speakers, separator_hidden=896, vocab_size=V_LLAMA3_CTC - 1).to(dev)
+    model.encoder.freeze_feature_encoder()
+    for p in model.encoder.adapter.parameters():       # the serialized-CTC loss does not depend on the adapter branch
+        p.requires_grad_(False)
+    model.eval()      # dropout 0 / SpecAugment off (RNG streams of the reference are not reproducible); gradients still flow
+    n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                        bucket_cap_mb=100, broadcast_buffers=False)
+
+    wav, mask, labels, lens = synth_batch(B, S, args.speakers, V_LLAMA3_CTC, seed=1234 + rank)
+    host = [wav.pin_memory(), mask.pin_memory()] + [y.pin_memory() for y in labels] + [l.pin_memory() for l in lens]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+    ns = args.speakers
+
+    def to_dev():
+        d = [t.to(dev, non_blocking=True) for t in host]
+        return d[0], d[1], d[2:2 + ns], d[2 + ns:2 + 2 * ns]
+
+    def step(w, m, ys, yl):
+        for p in model.parameters():
+            p.grad = None
+        loss = net(w, attention_mask=m, label_spks=ys, label_spks_lengths=yl)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    dw, dm, dys, dyl = to_dev()
+    if args.profile_run:
+        step(dw, dm, dys, dyl)
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push("timed_step")
+        step(dw, dm, dys, dyl)
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        return
+    for _ in range(max(3, args.warmup)):
+        loss = step(dw, dm, dys, dyl)
+    torch.cuda.synchronize()
+    loss0 = loss.item()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = K.launch_count()
+    ms = timed(lambda: step(dw, dm, dys, dyl), args.steps)
+    launches = K.launch_count() - l0
+
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            w, m, ys, yl = to_dev()
+            return step(w, m, ys, yl).item()           # device->host read of the step's loss
+        e2e_step()
+        ms_e2e = timed(e2e_step, args.steps)
+        e2e = {"value": world * B * args.seconds * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps}
+    clocks = sampler.stop() if sampler else None
+
+    # roofline of the dominant kernel (gemm_bf16_kernel): per-launch CUDA events on its stream over one more step
+    K.profile_begin()
+    step(dw, dm, dys, dyl)
+    torch.cuda.synchronize()
+    gemm_ms, exec_flops, gemm_launches = K.profile_end()
+    fl = algorithmic_flops(cfg, S, args.speakers, 896, V_LLAMA3_CTC)
+    alg_step = fl["total"] * B
+    peak, peak_src = peaks()
+    ms_step = ms / args.steps
+    roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05/TMEM/TMA)", "achieved": alg_step / (gemm_ms / 1e3) / 1e12,
+            "peak": peak, "unit": "TFLOP/s", "frac": alg_step / (gemm_ms / 1e3) / 1e12 / peak, "traffic": None,
+            "peak_source": peak_src, "launches_per_step": gemm_launches, "kernel_ms_per_step": gemm_ms,
+            "kernel_share_of_step": gemm_ms / ms_step, "algorithmic_tflop_per_step": alg_step / 1e12,
+            "executed_tflop_per_step": exec_flops / 1e12,
+            "step_achieved_tflops": alg_step / (ms_step / 1e3) / 1e12, "step_frac": alg_step / (ms_step / 1e3) / 1e12 / peak}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del net, model
+        torch.cuda.empty_cache()
+        r = run_cpu_reference(args, steps=2, warmup=1, budget_s=25.0)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": world * B * args.seconds * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(args, B, world), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+                "gpu_launches": int(launches), "clocks": clocks, "loss": loss0, "trainable_params": n_train,
+                "gflop_per_audio_s": fl["total"] / args.seconds / 1e9}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

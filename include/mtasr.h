@@ -37,6 +37,12 @@ const char* mtasr_last_error_string(void);
 /* Number of kernels this library has enqueued since load (process-wide; used by bench.py `gpu_launches`). */
 int64_t mtasr_launch_count(void);
 
+/* Per-launch timing of the tcgen05 GEMM kernel (bench.py `roofline`): between begin and end every
+ * mtasr_gemm_bf16 launch is bracketed by CUDA events on its own stream; end synchronises and returns the summed
+ * kernel milliseconds, the executed flops (2*M*N*K*batches, recompute included) and the launch count. */
+int mtasr_profile_begin(void);
+int mtasr_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Dense contraction on tcgen05 tensor cores (TMA-fed, TMEM accumulators, fp32 accumulate, bf16 operands).
  *   C[b][m][n] = epilogue( alpha * sum_k A[b][m][k] * B[b][n][k] )

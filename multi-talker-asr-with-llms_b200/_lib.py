@@ -49,6 +49,8 @@ SIGNATURES = {
     "mtasr_version": (C.c_int, []),
     "mtasr_last_error_string": (C.c_char_p, []),
     "mtasr_launch_count": (_I64, []),
+    "mtasr_profile_begin": (C.c_int, []),
+    "mtasr_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "mtasr_gemm_bf16": (C.c_int, [C.POINTER(GemmDesc), _P]),
     "mtasr_gemm_n_tiles": (C.c_int, [_I32, _I32]),
     "mtasr_ctc_state_pad": (C.c_int, [_I32]),

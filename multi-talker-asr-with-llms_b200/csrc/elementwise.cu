@@ -265,9 +265,18 @@ attn_softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __rest
     const float* dprow = dP + row * Tp;
     __nv_bfloat16* dsrow = dS + row * Tp;
     const float g = gate[row];
-    float dot = 0.f;
-    for (int k = lane; k < T; k += 32) dot += bf2f(prow[k]) * dprow[k];
+    // P was rounded to bf16, so its row no longer sums to 1 exactly: normalising the row dot by sum(P) keeps
+    // sum_k dZ[k] == 0 (the exact softmax backward of slightly perturbed logits) instead of leaking a rounding bias
+    // into the heavily cancelling dgate / dtable reductions.
+    float dot = 0.f, psum = 0.f;
+    for (int k = lane; k < T; k += 32) {
+      const float pk = bf2f(prow[k]);
+      dot += pk * dprow[k];
+      psum += pk;
+    }
     dot = warp_sum(dot);
+    psum = warp_sum(psum);
+    dot = psum > 0.f ? dot / psum : 0.f;
     float dg = 0.f;
     const float* trow = trow_h + (T - 1 - q);
     float* arow = acc + (T - 1 - q);

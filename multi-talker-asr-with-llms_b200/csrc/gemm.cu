@@ -15,6 +15,7 @@
 // an implicit-im2col addressing (tap, phase, row) so conv1d over a channels-last tensor is the same kernel.
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -415,6 +416,16 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64
 
 std::atomic<long long> g_launches{0};
 
+// Optional per-launch timing of the GEMM kernel (bench.py roofline): CUDA events recorded on the launching stream
+// around every gemm_bf16_kernel launch while profiling is on.
+struct ProfRec {
+  cudaEvent_t e0, e1;
+  double flops;
+};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
 }  // namespace mtasr
 
 using namespace mtasr;
@@ -515,8 +526,57 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
     return set_error(MTASR_ERR_LAUNCH, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
 
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, static_cast<cudaStream_t>(stream)>>>(ma, mb, p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ProfRec rec{};
+  bool prof = false;
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    prof = g_prof_on;
+  }
+  if (prof) {
+    cudaEventCreate(&rec.e0);
+    cudaEventCreate(&rec.e1);
+    rec.flops = 2.0 * d->M * static_cast<double>(d->N) * d->K * d->batch0 * d->batch1;
+    cudaEventRecord(rec.e0, st);
+  }
+  gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ma, mb, p);
   g_launches.fetch_add(1);
+  if (prof) {
+    cudaEventRecord(rec.e1, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(rec);
+  }
   MTASR_CHECK_LAUNCH("gemm_bf16");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  g_prof_on = true;
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = false;
+  double ms = 0.0, fl = 0.0;
+  for (auto& r : g_prof) {
+    if (cudaEventSynchronize(r.e1) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "profile_end: event sync failed");
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    ms += t;
+    fl += r.flops;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_flops) *gemm_flops = fl;
+  if (gemm_launches) *gemm_launches = static_cast<int64_t>(g_prof.size());
+  g_prof.clear();
   return MTASR_OK;
 }

@@ -1,0 +1,88 @@
+"""Data-parallel gradient reduction for the path: the path shards by utterance, one process per GPU, and
+the only collective is the gradient all-reduce (mean) of the trainable encoder / separator / CTC-head parameters --
+what the reference gets from DDP inside `accelerator.backward` (ref:src/trainer_seq2seq.py:1134).
+
+`GradBucketReducer` keeps every trainable parameter's `.grad` as a view into a few large flat fp32 buckets laid out in
+reverse registration order (~ the order backward produces them: CTC heads, separator, encoder layers 23..0).  A
+post-accumulate-grad hook counts arrivals per bucket and launches the bucket's asynchronous all-reduce (NCCL over
+NVLink/NVSwitch on the GPU box, gloo in the CPU tests) as soon as its last gradient has landed, so the wire time hides
+under the rest of the backward pass.  `finish()` flushes buckets that never filled (unused parameters), waits and
+turns the sums into means.
+"""
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class GradBucketReducer:
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 256 << 20, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        order = list(reversed(self.params))
+        self.buckets: List[dict] = []
+        cur, cur_bytes = [], 0
+        for p in order:
+            nbytes = p.numel() * 4
+            if cur and cur_bytes + nbytes > bucket_bytes:
+                self._close(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self._close(cur)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._works: List = []
+
+    def _close(self, plist):
+        dev = plist[0].device
+        n = sum(p.numel() for p in plist)
+        flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        b = dict(flat=flat, params=plist, pending=len(plist), launched=False)
+        off = 0
+        for p in plist:
+            p._mtasr_bucket = len(self.buckets)
+            p._mtasr_view = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.buckets.append(b)
+
+    def zero_grad(self):
+        """Point every .grad at its bucket view and zero the buckets (call before each backward)."""
+        self._works = []
+        for b in self.buckets:
+            b["flat"].zero_()
+            b["pending"] = len(b["params"])
+            b["launched"] = False
+            for p in b["params"]:
+                p.grad = p._mtasr_view
+
+    def _launch(self, b):
+        b["launched"] = True
+        if self.world > 1:
+            self._works.append(dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _on_grad(self, p):
+        b = self.buckets[p._mtasr_bucket]
+        if p.grad is not p._mtasr_view:               # autograd replaced the tensor (first accumulation): copy in
+            p._mtasr_view.copy_(p.grad)
+            p.grad = p._mtasr_view
+        b["pending"] -= 1
+        if b["pending"] == 0 and not b["launched"]:
+            self._launch(b)
+
+    def finish(self):
+        """Flush never-filled buckets, wait for the collectives and average."""
+        for b in self.buckets:
+            if not b["launched"]:
+                self._launch(b)
+        for w in self._works:
+            w.wait()
+        if self.world > 1:
+            for b in self.buckets:
+                b["flat"].div_(self.world)
+        self._works = []
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()

@@ -51,6 +51,17 @@ def launch_count() -> int:
     return int(_lib.load().mtasr_launch_count())
 
 
+def profile_begin() -> None:
+    check(_lib.load().mtasr_profile_begin(), "mtasr_profile_begin")
+
+
+def profile_end():
+    """-> (summed GEMM-kernel ms, executed flops, launches) since profile_begin()."""
+    ms, fl, n = C.c_double(), C.c_double(), C.c_int64()
+    check(_lib.load().mtasr_profile_end(C.byref(ms), C.byref(fl), C.byref(n)), "mtasr_profile_end")
+    return ms.value, fl.value, n.value
+
+
 # ----------------------------------------------------------------------------------------------------------- GEMM
 @dataclass
 class Operand:

@@ -218,33 +218,44 @@ class AttentionFn(Function):
 
 
 # ------------------------------------------------------------------------------------------------------ pos conv
-def _posconv_weight_layout(w: torch.Tensor, G: int) -> torch.Tensor:
-    """torch grouped-conv weight (D, D/G, k) -> (g, out, tap, c) bf16, K-major for the implicit GEMM."""
-    D, cg, k = w.shape
-    return w.detach().view(G, D // G, cg, k).permute(0, 1, 3, 2).contiguous().to(BF)
+def _group_pad(x_bf16: torch.Tensor, G: int, cgp: int) -> torch.Tensor:
+    """(B,T,G*cg) -> (B,T,G*cgp) with every group's channels zero-padded to cgp (pure data movement; only needed when
+    the group width is not a multiple of the 64-element TMA/UMMA K atom, e.g. WavLM-Base+: 768/16 = 48)."""
+    B, T, D = x_bf16.shape
+    cg = D // G
+    if cgp == cg:
+        return x_bf16
+    out = K.empty_act((B, T, G * cgp), BF, x_bf16.device)
+    o4 = out.view(B, T, G, cgp)
+    o4[..., :cg] = x_bf16.view(B, T, G, cg)
+    o4[..., cg:] = 0
+    return out
 
 
 class PosConvFn(Function):
     """x + GELU(grouped_conv1d(x, w, bias, k, pad=k//2)[:T])   (hf:48-90 + hf:403/481; `w` is the already
     weight-normalised kernel g*v/||v||, computed by torch so autograd carries the gradient to original0/original1).
-    One implicit-GEMM launch over (group, utterance): A = taps x 64-channel slices of the zero-padded input."""
+    One implicit-GEMM launch over (group, utterance): A = taps x per-group channel slices of the zero-padded input."""
 
     @staticmethod
     def forward(ctx, x, w, bias, G, vlen):
         B, T, D = x.shape
         cg = D // G
+        cgp = (cg + 63) // 64 * 64
         k = w.shape[2]
         pad = k // 2
         Tpad = T + k
         xp = K.pad_cast(x, pad, Tpad, vlen)                                  # (B, Tpad, D) bf16; rows >= vlen zeroed
-        wk = _posconv_weight_layout(w, G)
+        xg = _group_pad(xp, G, cgp)
+        wk = torch.zeros(G, cg, k, cgp, device=x.device, dtype=BF)           # (g, out, tap, c) K-major
+        wk[..., :cg] = w.detach().view(G, cg, cg, k).permute(0, 1, 3, 2)
         u = torch.empty(B, T, D, device=x.device, dtype=BF)
         y = torch.empty(B, T, D, device=x.device, dtype=F32)
         xres = x if vlen is None else (x * (torch.arange(T, device=x.device)[None, :] < vlen[:, None]).unsqueeze(-1))
         xres = xres.contiguous()
-        K.gemm(K.Operand(xp, D, sb0=cg, sb1=Tpad * D, inner=cg, phase=1, rows=Tpad), K.Operand(wk, k * cg, sb0=cg * k * cg),
-               T, cg, k * cg, K.Out(y, D, sb0=cg, sb1=T * D), batch=(G, B), bias=bias.detach().float(), bias_sb0=cg,
-               act=K.ACT_GELU, aux=u, residual=K.Out(xres, D, sb0=cg, sb1=T * D))
+        K.gemm(K.Operand(xg, G * cgp, sb0=cgp, sb1=Tpad * G * cgp, inner=cgp, phase=1, rows=Tpad),
+               K.Operand(wk, k * cgp, sb0=cg * k * cgp), T, cg, k * cgp, K.Out(y, D, sb0=cg, sb1=T * D), batch=(G, B),
+               bias=bias.detach().float(), bias_sb0=cg, act=K.ACT_GELU, aux=u, residual=K.Out(xres, D, sb0=cg, sb1=T * D))
         ctx.dims = (B, T, D, G, k)
         ctx.save_for_backward(xp, u, w, vlen)
         return y
@@ -254,17 +265,20 @@ class PosConvFn(Function):
         xp, u, w, vlen = ctx.saved_tensors
         B, T, D, G, k = ctx.dims
         cg = D // G
+        cgp = (cg + 63) // 64 * 64
         pad = k // 2
         Tpad = T + k
         du = K.act_bwd(dy.contiguous().view(B * T, D), u.view(B * T, D), K.ACT_GELU_BWD).view(B, T, D)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # dx[t'] = sum_{o,tap} du[t' - tap + pad, o] w[o,c,tap]: conv of du (left pad k-1-pad) with flipped taps
-            dup = K.pad_cast(du, k - 1 - pad, Tpad)
-            wf = w.detach().view(G, cg, cg, k).flip(3).permute(0, 2, 3, 1).contiguous().to(BF)   # (g, c_in, tap', o)
+            dup = _group_pad(K.pad_cast(du, k - 1 - pad, Tpad), G, cgp)
+            wf = torch.zeros(G, cg, k, cgp, device=dy.device, dtype=BF)        # (g, c_in, tap', o)
+            wf[..., :cg] = w.detach().view(G, cg, cg, k).flip(3).permute(0, 2, 3, 1)
             dxc = torch.empty(B, T, D, device=dy.device, dtype=F32)
-            K.gemm(K.Operand(dup, D, sb0=cg, sb1=Tpad * D, inner=cg, phase=1, rows=Tpad), K.Operand(wf, k * cg, sb0=cg * k * cg),
-                   T, cg, k * cg, K.Out(dxc, D, sb0=cg, sb1=T * D), batch=(G, B), residual=K.Out(dy.contiguous(), D, sb0=cg, sb1=T * D))
+            K.gemm(K.Operand(dup, G * cgp, sb0=cgp, sb1=Tpad * G * cgp, inner=cgp, phase=1, rows=Tpad),
+                   K.Operand(wf, k * cgp, sb0=cg * k * cgp), T, cg, k * cgp, K.Out(dxc, D, sb0=cg, sb1=T * D), batch=(G, B),
+                   residual=K.Out(dy.contiguous(), D, sb0=cg, sb1=T * D))
             if vlen is not None:
                 dxc = dxc * (torch.arange(T, device=dy.device)[None, :] < vlen[:, None]).unsqueeze(-1)
             dx = dxc
@@ -274,7 +288,7 @@ class PosConvFn(Function):
             xpe = torch.zeros(B * Tpad + k, D, device=dy.device, dtype=BF)
             xpe[: B * Tpad] = xp.view(B * Tpad, D)
             dwk = torch.empty(G, cg, k, cg, device=dy.device, dtype=F32)       # (g, o, tap, c)
-            for g in range(G):                                                 # batch dims are (tap) only: 16 launches
+            for g in range(G):                                                 # batch dims are (tap) only: G launches
                 K.gemm(K.Operand(du2, D, major=1, offset=g * cg, rows=B * Tpad),
                        K.Operand(xpe, D, major=1, sb0=D, offset=g * cg, rows=B * Tpad), cg, cg, B * Tpad,
                        K.Out(dwk, k * cg, sb0=cg, offset=g * cg * k * cg), batch=(k, 1))

@@ -69,7 +69,7 @@ class RefWavLMModel(WavLMPreTrainedModel):
         n = attention_mask.cumsum(dim=-1)[:, -1]
         for k, s in zip(self.config.conv_kernel, self.config.conv_stride):
             n = torch.div(n - k, s, rounding_mode="floor") + 1
-        return torch.arange(T)[None, :] < n[:, None]
+        return torch.arange(T, device=n.device)[None, :] < n[:, None]
 
     def forward(self, input_values, attention_mask=None, mask_time_indices=None):
         feats = self.feature_extractor(input_values).transpose(1, 2)

@@ -65,10 +65,60 @@ def perturb_(enc, seed=0):
     with torch.no_grad():
         for lyr in enc.encoder.layers:
             a = lyr.attention
-            a.gru_rel_pos_const.copy_(torch.rand(a.gru_rel_pos_const.shape, generator=g) + 0.5)
-            a.gru_rel_pos_linear.bias.copy_(torch.randn(a.gru_rel_pos_linear.bias.shape, generator=g) * 0.5)
+            a.gru_rel_pos_const.copy_((torch.rand(a.gru_rel_pos_const.shape, generator=g) + 0.5).to(a.gru_rel_pos_const.device))
+            b = a.gru_rel_pos_linear.bias
+            b.copy_((torch.randn(b.shape, generator=g) * 0.5).to(b.device))
         w = enc.encoder.layers[0].attention.rel_attn_embed.weight
-        w.copy_(torch.randn(w.shape, generator=g) * 0.5)
+        w.copy_((torch.randn(w.shape, generator=g) * 0.5).to(w.device))
         for n, p in enc.named_parameters():
             if "layer_norm" in n:
-                p.add_(0.1 * torch.randn(p.shape, generator=g))
+                p.add_((0.1 * torch.randn(p.shape, generator=g)).to(p.device))
+
+
+def oracle_run(o_enc, o_sep, o_heads, wav, mask, labels, lens, autocast=False, want_grads=True):
+    """Oracle forward (+ backward) of the serialized-CTC loss.  autocast=True gives the yardstick "what the reference
+    itself loses in bf16" (torch.autocast on encoder + separator; the CTC block stays fp32 like
+    ref:models/losses.py:265-268)."""
+    from oracle.model_ref import ref_hybrid_ctc
+    prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            last, enc, down, feats = o_enc(wav, mask)
+            seps = o_sep(enc)
+        fm = o_enc.frame_mask_x0(enc.shape[1], mask)
+        loss, _ = ref_hybrid_ctc(o_heads, [s.float() for s in seps], fm, labels, lens)
+        grads = None
+        if want_grads:
+            named = named_params(o_enc, o_sep, o_heads)
+            names = [k for k, v in named.items() if v.requires_grad]
+            gs = torch.autograd.grad(loss, [named[k] for k in names], allow_unused=True)
+            grads = {k: v for k, v in zip(names, gs) if v is not None}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    return dict(last=last.float(), enc=enc.float(), down=down.float(), feats=feats.float(), seps=[s.float() for s in seps],
+                loss=loss, fm=fm, grads=grads)
+
+
+def named_params(enc, sep, heads):
+    return {**{"encoder." + k: v for k, v in enc.named_parameters()},
+            **{"separator." + k: v for k, v in sep.named_parameters()},
+            **{"serialized_ctc." + k: v for k, v in heads.named_parameters()}}
+
+
+def grad_errors(got, ref):
+    """global relative L2 error over all parameters in `ref`, and per-parameter errors."""
+    num = den = 0.0
+    per = {}
+    for k, r in ref.items():
+        gv = got.get(k)
+        r = r.float()
+        if gv is None:
+            gv = torch.zeros_like(r)
+        gv = gv.float().to(r.device)
+        num += (gv - r).pow(2).sum().item()
+        den += r.pow(2).sum().item()
+        if r.norm().item() > 1e-8:
+            per[k] = ((gv - r).norm() / r.norm()).item()
+    return (num / max(den, 1e-30)) ** 0.5, per
