@@ -82,8 +82,8 @@ def test_attn_softmax(cuda, B, H, T):
     dP = torch.randn(B, H, T, Tp, device=cuda)
     Pf = P.float()[..., :T]
     dS, dgate, dtable = Kn.attn_softmax_bwd(P, dP, gate, table, B, H, T, Tp, scale)
-    # reference backward evaluated at the SAME (bf16-rounded) probabilities
-    dot = (Pf * dP[..., :T]).sum(-1, keepdim=True)
+    # reference backward evaluated at the SAME (bf16-rounded) probabilities, row dot normalised by sum(P) like the kernel
+    dot = (Pf * dP[..., :T]).sum(-1, keepdim=True) / Pf.sum(-1, keepdim=True)
     dz = Pf * (dP[..., :T] - dot)
     assert _rel(dS[..., :T], dz * scale) < 5e-3
     assert _rel(dgate, (dz * table[:, idx][None]).sum(-1)) < 1e-4
