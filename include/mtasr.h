@@ -156,6 +156,15 @@ int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t
 int mtasr_cast_f32_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
 /* out[n] = sum_m x[m][n] (bias gradients) */
 int mtasr_colsum(const void* x, int32_t dtype, int64_t M, int32_t N, int64_t ld, float* out, void* stream);
+/* gru_rel_pos gate of hf:167-176 for every (b, t, head), head_dim 64: wab (128) = [sum of weight rows 0..3 | rows 4..7]
+ * of gru_rel_pos_linear, bab (2) the matching bias sums, cst (H) = gru_rel_pos_const; x (B,T,H*64) f32|bf16 is the
+ * attention input.  gate (B,H,T) f32 = sigmoid(a) * (sigmoid(b) * cst[h] - 1) + 2.  Backward: dx (B,T,H*64) f32 written,
+ * dwab / dbab / dcst ACCUMULATED (zero them first). */
+int mtasr_relpos_gate_fwd(const void* x, int32_t x_dtype, const float* wab, const float* bab, const float* cst, int32_t B,
+                          int32_t T, int32_t H, float* gate, void* stream);
+int mtasr_relpos_gate_bwd(const void* x, int32_t x_dtype, const float* wab, const float* bab, const float* cst,
+                          const float* dgate, int32_t B, int32_t T, int32_t H, float* dx, float* dwab, float* dbab, float* dcst,
+                          void* stream);
 /* softmax(S*scale + gate[b,h,q]*table[h,k-q+T-1]) over keys k < klen[b] (hf:167-180 + hf:206-228 fused);
  * S (B,H,T,Tp) f32, gate (B,H,T) f32, table (H,2T-1) f32, klen (B) i32 or NULL, P (B,H,T,Tp) bf16. */
 int mtasr_attn_softmax_fwd(const float* S, const float* gate, const float* table, const int32_t* klen, int32_t B,

@@ -61,6 +61,41 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+// Raw SFU approximations (single MUFU, no range fix-up branches: the fix-ups of exp2f()/__frcp_rn() put a
+// BSSY/BSYNC region around every element and serialise the otherwise independent per-element chains).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Epilogue-speed GELU: erf by the Abramowitz-Stegun 7.1.26 rational form (|abs err| < 1.5e-7 plus ~1e-7 from the
+// approximate SFU ops, i.e. at fp32 rounding level of the GELU output) with one MUFU.RCP + one MUFU.EX2.
+__device__ __forceinline__ float erf_fast_pos(float ax, float e /* = exp(-ax*ax) */) {
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  return fmaf(-poly * t, e, 1.0f);
+}
+__device__ __forceinline__ float gelu_fast_f(float x) {
+  const float ax = fabsf(x);
+  const float z = ax * 0.70710678118654752f;
+  const float e = ex2_approx(z * z * -1.4426950408889634f);
+  return 0.5f * fmaf(ax, erf_fast_pos(z, e), x);             // 0.5 x (1 + sign(x) erf|z|)
+}
+__device__ __forceinline__ float gelu_grad_fast_f(float x) {
+  const float ax = fabsf(x);
+  const float z = ax * 0.70710678118654752f;
+  const float e = ex2_approx(z * z * -1.4426950408889634f);      // exp(-x^2/2)
+  const float er = copysignf(erf_fast_pos(z, e), x);
+  return fmaf(x * 0.39894228040143268f, e, fmaf(0.5f, er, 0.5f));
+}
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 // log(exp(a)+exp(b)) that tolerates -inf on either side.

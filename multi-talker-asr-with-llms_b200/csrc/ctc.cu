@@ -263,6 +263,7 @@ __global__ void lse_finalize_kernel(const float4* __restrict__ part, int rows, i
   for (int i = lane; i < n_tiles; i += 32) {
     const float4 v = p[i];
     const int vi = __float_as_int(v.z);
+    if (v.x == NEG_INF) continue;   // empty partial (an epilogue warp that owned no column of this tile)
     if (v.x > m) {
       s = s * __expf(m - v.x) + v.y;
       m = v.x;

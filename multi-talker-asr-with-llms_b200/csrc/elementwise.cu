@@ -183,7 +183,49 @@ __global__ void cast_tail_kernel(const float* __restrict__ x, __nv_bfloat16* __r
   if (i < n) y[i] = f2bf(x[i]);
 }
 
-// out[n] (+)= sum_m x[m][n]; CTA = 32 columns x 8 row-lanes... each thread owns one column, strides rows.
+// out[n] += sum_m x[m][n]  (bias gradients).  Vector path (N % 8 == 0, 16-byte aligned rows): each thread owns 8
+// consecutive columns (one 128-bit load per row for bf16, two for fp32), 8 row-lanes per CTA, 4 rows in flight per
+// thread; CTA partials are combined in smem and added with one atomic per column.
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const void* __restrict__ x, int dtype, long long M, int N, long long ld, float* __restrict__ out) {
+  __shared__ float red[8][32][9];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cx) * 8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < N) {
+    const long long step = static_cast<long long>(gridDim.y) * 8;
+    long long m = static_cast<long long>(blockIdx.y) * 8 + ry;
+    for (; m + 3 * step < M; m += 4 * step) {
+      float a[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ld8(x, dtype, (m + u * step) * ld + col, a[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += a[u][j];
+    }
+    for (; m < M; m += step) {
+      float a[8];
+      ld8(x, dtype, m * ld + col, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += a[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ry][cx][j] = s[j];
+  __syncthreads();
+  // 256 threads -> 256 columns of this CTA
+  const int c = threadIdx.x;
+  const int gcol = blockIdx.x * 256 + c;
+  if (gcol < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][c >> 3][c & 7];
+    atomicAdd(out + gcol, t);
+  }
+}
+
+// scalar fallback for odd N / unaligned rows
 __global__ void __launch_bounds__(256)
 colsum_kernel(const void* __restrict__ x, int dtype, long long M, int N, long long ld, float* __restrict__ out) {
   __shared__ float red[8][33];
@@ -204,6 +246,97 @@ colsum_kernel(const void* __restrict__ x, int dtype, long long M, int N, long lo
     for (int i = 0; i < 8; ++i) t += red[i][cx];
     atomicAdd(out + col, t);
   }
+}
+
+// ------------------------------------------------------------------------------------------------ rel-pos gate
+// gru_rel_pos gate of hf:167-176 for every (b, t, head): with x_h the 64-wide head slice of the layer input,
+//   [a, b] = view(Linear_{64->8}(x_h), 2, 4).sum(-1) = [wa . x_h + ba, wb . x_h + bb]   (wa/wb = sums of 4 weight rows)
+//   gate = sigmoid(a) * (sigmoid(b) * const_h - 1) + 2
+// One warp per (b, t) row; lane l holds elements l and l+32 of each head slice.  wab = [wa | wb] (128 floats),
+// bab = [ba, bb].  Output gate (B,H,T) fp32.
+__global__ void __launch_bounds__(256)
+relpos_gate_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ wab, const float* __restrict__ bab,
+                       const float* __restrict__ cst, int B, int T, int H, float* __restrict__ gate) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  const float wa0 = wab[lane], wa1 = wab[lane + 32], wb0 = wab[64 + lane], wb1 = wab[96 + lane];
+  const float ba = bab[0], bb = bab[1];
+  const long long rows = static_cast<long long>(B) * T;
+  const int D = H * 64;
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
+    for (int h = 0; h < H; ++h) {
+      float x0, x1;
+      if (x_dtype == MTASR_DT_BF16) {
+        const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x) + row * D + h * 64;
+        x0 = bf2f(xp[lane]); x1 = bf2f(xp[lane + 32]);
+      } else {
+        const float* xp = reinterpret_cast<const float*>(x) + row * D + h * 64;
+        x0 = xp[lane]; x1 = xp[lane + 32];
+      }
+      const float a = warp_sum(wa0 * x0 + wa1 * x1) + ba;
+      const float bv = warp_sum(wb0 * x0 + wb1 * x1) + bb;
+      if (lane == 0) {
+        const float ga = 1.f / (1.f + expf(-a)), gb = 1.f / (1.f + expf(-bv));
+        gate[(static_cast<long long>(b) * H + h) * T + t] = ga * (gb * cst[h] - 1.f) + 2.f;
+      }
+    }
+  }
+}
+
+// Backward: dx (B,T,D) fp32 = da*wa + db*wb per head slice; dwab (128), dbab (2), dcst (H) accumulated with atomics
+// (zero them first).
+__global__ void __launch_bounds__(256)
+relpos_gate_bwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ wab, const float* __restrict__ bab,
+                       const float* __restrict__ cst, const float* __restrict__ dgate, int B, int T, int H,
+                       float* __restrict__ dx, float* __restrict__ dwab, float* __restrict__ dbab, float* __restrict__ dcst) {
+  __shared__ float red[8][132];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  const float wa0 = wab[lane], wa1 = wab[lane + 32], wb0 = wab[64 + lane], wb1 = wab[96 + lane];
+  const float ba = bab[0], bb = bab[1];
+  const long long rows = static_cast<long long>(B) * T;
+  const int D = H * 64;
+  float dwa0 = 0.f, dwa1 = 0.f, dwb0 = 0.f, dwb1 = 0.f, dba = 0.f, dbb = 0.f;
+  float dc = 0.f;   // lane h (< H) accumulates dcst[h]
+  for (long long row = warp0; row < rows; row += nwarps) {
+    const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
+    for (int h = 0; h < H; ++h) {
+      float x0, x1;
+      if (x_dtype == MTASR_DT_BF16) {
+        const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x) + row * D + h * 64;
+        x0 = bf2f(xp[lane]); x1 = bf2f(xp[lane + 32]);
+      } else {
+        const float* xp = reinterpret_cast<const float*>(x) + row * D + h * 64;
+        x0 = xp[lane]; x1 = xp[lane + 32];
+      }
+      const float a = warp_sum(wa0 * x0 + wa1 * x1) + ba;
+      const float bv = warp_sum(wb0 * x0 + wb1 * x1) + bb;
+      const float ga = 1.f / (1.f + expf(-a)), gb = 1.f / (1.f + expf(-bv));
+      const float c = cst[h];
+      const float dg = dgate[(static_cast<long long>(b) * H + h) * T + t];
+      const float da = dg * (gb * c - 1.f) * ga * (1.f - ga);
+      const float db = dg * ga * c * gb * (1.f - gb);
+      if (lane == (h & 31)) dc += dg * ga * gb;
+      float* dxp = dx + row * D + h * 64;
+      dxp[lane] = da * wa0 + db * wb0;
+      dxp[lane + 32] = da * wa1 + db * wb1;
+      dwa0 += da * x0; dwa1 += da * x1; dwb0 += db * x0; dwb1 += db * x1;
+      dba += da; dbb += db;   // identical on every lane
+    }
+  }
+  red[warp][lane] = dwa0; red[warp][lane + 32] = dwa1; red[warp][64 + lane] = dwb0; red[warp][96 + lane] = dwb1;
+  if (lane == 0) { red[warp][128] = dba; red[warp][129] = dbb; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 130; i += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w][i];
+    if (i < 128) atomicAdd(dwab + i, s);
+    else atomicAdd(dbab + (i - 128), s);
+  }
+  if (lane < H && dc != 0.f) atomicAdd(dcst + lane, dc);
 }
 
 // ------------------------------------------------------------------------------------------------ attention softmax
@@ -429,14 +562,41 @@ extern "C" int mtasr_colsum(const void* x, int32_t dtype, int64_t M, int32_t N, 
   MTASR_CHECK_ARG(x && out && M > 0 && N > 0 && ld >= N, "colsum: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (cudaMemsetAsync(out, 0, sizeof(float) * N, st) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "colsum: memset failed");
-  int gy = static_cast<int>((M + 255) / 256);
-  const int gx = (N + 31) / 32;
-  const int cap = (num_sms() * 8 + gx - 1) / gx;
+  const int esz = dtype == MTASR_DT_BF16 ? 2 : 4;
+  const bool vec = N % 8 == 0 && (ld * esz) % 16 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0;
+  const int gx = vec ? (N + 255) / 256 : (N + 31) / 32;
+  int gy = static_cast<int>((M + 63) / 64);
+  const int cap = (num_sms() * 4 + gx - 1) / gx;
   if (gy > cap) gy = cap;
   if (gy < 1) gy = 1;
-  colsum_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, dtype, M, N, ld, out);
+  if (vec) colsum_vec_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, dtype, M, N, ld, out);
+  else colsum_kernel<<<dim3(gx, gy), 256, 0, st>>>(x, dtype, M, N, ld, out);
   MTASR_COUNT_LAUNCH();
   MTASR_CHECK_LAUNCH("colsum");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_relpos_gate_fwd(const void* x, int32_t x_dtype, const float* wab, const float* bab, const float* cst,
+                                     int32_t B, int32_t T, int32_t H, float* gate, void* stream) {
+  MTASR_CHECK_ARG(x && wab && bab && cst && gate && B > 0 && T > 0 && H > 0 && H <= 32, "relpos_gate_fwd: bad arguments");
+  relpos_gate_fwd_kernel<<<grid_for(static_cast<long long>(B) * T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, x_dtype, wab, bab, cst, B, T, H, gate);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("relpos_gate_fwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_relpos_gate_bwd(const void* x, int32_t x_dtype, const float* wab, const float* bab, const float* cst,
+                                     const float* dgate, int32_t B, int32_t T, int32_t H, float* dx, float* dwab, float* dbab,
+                                     float* dcst, void* stream) {
+  MTASR_CHECK_ARG(x && wab && bab && cst && dgate && dx && dwab && dbab && dcst && B > 0 && T > 0 && H > 0 && H <= 32,
+                  "relpos_gate_bwd: bad arguments");
+  long long g = (static_cast<long long>(B) * T + 63) / 64;
+  if (g > num_sms() * 2) g = num_sms() * 2;
+  relpos_gate_bwd_kernel<<<static_cast<unsigned>(g), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, x_dtype, wab, bab, cst, dgate, B, T, H, dx, dwab, dbab, dcst);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("relpos_gate_bwd");
   return MTASR_OK;
 }
 

@@ -14,6 +14,8 @@
 // (dY W) and weight-gradient (dY^T X) contractions all run here without a transpose pass.  K-major A also takes
 // an implicit-im2col addressing (tap, phase, row) so conv1d over a channels-last tensor is the same kernel.
 #include <atomic>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -24,12 +26,15 @@ namespace mtasr {
 
 static constexpr int BM = 128;
 static constexpr int BK = 64;
-static constexpr int STAGES = 4;
-static constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-static constexpr int B_STAGE_BYTES = 256 * BK * 2;  // 32 KB (block_n <= 256)
-static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-static constexpr int GEMM_THREADS = 256;
-static constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static constexpr int A_STAGE_BYTES = BM * BK * 2;    // 16 KB; the B stage is block_n * BK * 2 bytes
+static constexpr int CTRL_WARPS = 4;                 // TMA producer, MMA issuer, TMEM allocator, spare
+static constexpr int EPI_WARPS = 8;                  // 2 warps per TMEM lane quadrant, alternating column groups
+static constexpr int GEMM_THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
+static constexpr int STG_BYTES = 4096;               // one 32-row x 128-byte swizzled staging box per warp and tensor
+static constexpr int MAX_STAGES = 8;
+static constexpr int BAR_BYTES = 512;                // mbarriers + TMEM slot
+static constexpr int BIAS_BYTES = EPI_WARPS * 64 * 4; // per-warp bias slot of one column group
+static constexpr int SMEM_LIMIT = 232448;            // 227 KB of dynamic shared memory per CTA on sm_100
 static constexpr int TMEM_COLS = 512;
 
 struct GemmKP {
@@ -38,6 +43,12 @@ struct GemmKP {
   int a_inner, a_phase;
   int a_use0, a_use1, b_use0, b_use1;  // 0 => operand broadcast over that batch dim (coordinate forced to 0)
   int m_tiles, n_tiles, num_tiles, num_kb;
+  int splits, kb_per_split;            // split-K (fp32 TMA reduce-add into a pre-zeroed C) for launches with few tiles
+  int stages, stage_bytes;             // smem ring geometry (host-chosen to fit the staging buffers)
+  int tma_epi;                         // 1: outputs leave through swizzled smem staging + TMA tiled stores
+  int gw;                              // column-group width of the epilogue: 32 or 64
+  int stg_aux, stg_res;                // staging buffer index of aux / residual (0 = C), -1 if absent
+  int n_stg;
   void* c;
   int c_dtype;
   long long c_ld, c_sb0, c_sb1;
@@ -110,8 +121,46 @@ __device__ __forceinline__ void store8(void* base, int dtype, long long idx, int
   }
 }
 
+// SWIZZLE_128B address transform of a tiled TMA box in shared memory (buffer 1024-byte aligned):
+// the 16-byte chunk index (address bits 4..6) is XORed with address bits 7..9.
+__device__ __forceinline__ uint32_t swz(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }
+
+// Boxes whose rows are 128 bytes (64 bf16 / 32 fp32 columns) use SWIZZLE_128B; the narrow 64-byte rows (bf16 tensors in
+// a 32-column group, i.e. a bf16 tensor next to an fp32 one) are plain row-major (SWIZZLE_NONE).
+__device__ __forceinline__ void stg_store8(uint8_t* buf, int dtype, int row, int gw, int c8, const float (&v)[8]) {
+  if (dtype == MTASR_DT_BF16) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    const uint32_t off = static_cast<uint32_t>(row * gw * 2 + c8 * 16);
+    *reinterpret_cast<uint4*>(buf + (gw == 64 ? swz(off) : off)) = u;
+  } else {
+    const uint32_t off = static_cast<uint32_t>(row * gw * 4 + c8 * 32);
+    *reinterpret_cast<float4*>(buf + swz(off)) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(buf + swz(off + 16)) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+__device__ __forceinline__ void stg_load8(const uint8_t* buf, int dtype, int row, int gw, int c8, float (&o)[8]) {
+  if (dtype == MTASR_DT_BF16) {
+    const uint32_t boff = static_cast<uint32_t>(row * gw * 2 + c8 * 16);
+    const uint4 u = *reinterpret_cast<const uint4*>(buf + (gw == 64 ? swz(boff) : boff));
+    float2 t;
+    t = unpack_bf16x2(u.x); o[0] = t.x; o[1] = t.y;
+    t = unpack_bf16x2(u.y); o[2] = t.x; o[3] = t.y;
+    t = unpack_bf16x2(u.z); o[4] = t.x; o[5] = t.y;
+    t = unpack_bf16x2(u.w); o[6] = t.x; o[7] = t.y;
+  } else {
+    const uint32_t off = static_cast<uint32_t>(row * gw * 4 + c8 * 32);
+    const float4 u0 = *reinterpret_cast<const float4*>(buf + swz(off));
+    const float4 u1 = *reinterpret_cast<const float4*>(buf + swz(off + 16));
+    o[0] = u0.x; o[1] = u0.y; o[2] = u0.z; o[3] = u0.w;
+    o[4] = u1.x; o[5] = u1.y; o[6] = u1.z; o[7] = u1.w;
+  }
+}
+
 struct TileCoord {
-  int m_tile, n_tile, b0, b1;
+  int m_tile, n_tile, b0, b1, kb0, kb1;
 };
 __device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, int tile) {
   TileCoord t;
@@ -119,21 +168,215 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, int tile) {
   int rest = tile / p.m_tiles;
   t.n_tile = rest % p.n_tiles;
   int batch = rest / p.n_tiles;
-  t.b0 = batch % p.batch0;
-  t.b1 = batch / p.batch0;
+  if (p.splits > 1) {   // un-batched launch: the outermost index is the K split
+    t.b0 = t.b1 = 0;
+    t.kb0 = batch * p.kb_per_split;
+    t.kb1 = min(p.num_kb, t.kb0 + p.kb_per_split);
+  } else {
+    t.b0 = batch % p.batch0;
+    t.b1 = batch / p.batch0;
+    t.kb0 = 0;
+    t.kb1 = p.num_kb;
+  }
   return t;
 }
 
+// ---- epilogue configuration, compile-time for the hot combinations (smaller, branch-free code: the fully generic
+// kernel is ~17k SASS instructions and stalls on instruction fetch), run-time for everything else ----------------------
+//   CFG = mode | act << 2 | aux << 5 | res << 6 | generic << 7
+static constexpr int CFG_GENERIC = 128;
+constexpr int make_cfg(int mode, int act, bool aux, bool res) { return mode | (act << 2) | (aux ? 32 : 0) | (res ? 64 : 0); }
+
+template <int CFG>
+struct Epi {
+  static constexpr bool GEN = (CFG & CFG_GENERIC) != 0;
+  __device__ __forceinline__ static int mode(const GemmKP& p) { return GEN ? p.mode : (CFG & 3); }
+  __device__ __forceinline__ static int act(const GemmKP& p) { return GEN ? p.act : ((CFG >> 2) & 7); }
+  __device__ __forceinline__ static bool aux(const GemmKP& p) { return GEN ? (p.aux != nullptr) : ((CFG & 32) != 0); }
+  __device__ __forceinline__ static bool res(const GemmKP& p) { return GEN ? (p.residual != nullptr) : ((CFG & 64) != 0); }
+  __device__ __forceinline__ static bool tma(const GemmKP& p) { return GEN ? (p.tma_epi != 0) : true; }
+  __device__ __forceinline__ static bool res_tma(const GemmKP& p) { return GEN ? (p.tma_epi && p.stg_res >= 0) : ((CFG & 64) != 0); }
+};
+
+// One column group (GW = 32 or 64 accumulator columns) of one tile, for the 32 rows (TMEM lanes) of this warp.
+template <int GW, int CFG>
+__device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMap* tmap_c, const CUtensorMap* tmap_aux,
+                                               const CUtensorMap* tmap_r, uint8_t* stg, float* bias_s, uint64_t* res_bar,
+                                               uint32_t& res_phase, uint32_t taddr, const TileCoord& t, int q, int lane,
+                                               int g, const float* bias, float rvec, float rscale, bool row_ok,
+                                               long long c_off, long long r_off, float& run_max, float& run_sum,
+                                               int& run_idx) {
+  using E = Epi<CFG>;
+  const int mode = E::mode(p), act = E::act(p);
+  const bool has_aux = E::aux(p), has_res = E::res(p), tma = E::tma(p), res_tma = E::res_tma(p);
+  const int col0 = t.n_tile * p.block_n + g * GW;
+  const int row0 = t.m_tile * BM + q * 32;
+  uint8_t* stg_c = stg;
+  uint8_t* stg_aux = stg + (p.stg_aux > 0 ? p.stg_aux : 0) * STG_BYTES;
+  uint8_t* stg_r = stg + (p.stg_res > 0 ? p.stg_res : 0) * STG_BYTES;
+  if (tma && mode != 1) {
+    // the previous group's bulk stores must have finished READING the staging buffers before they are rewritten
+    if (lane == 0) bulk_wait_read<0>();
+    if (res_tma) fence_proxy_async();   // this warp's generic reads of the residual box precede its async overwrite
+  }
+  __syncwarp();
+  if (res_tma && lane == 0) {
+    mbar_arrive_expect_tx(res_bar, GW * 32 * (p.res_dtype == MTASR_DT_BF16 ? 2 : 4));
+    tma_load_4d(stg_r, tmap_r, res_bar, col0, row0, t.b0, t.b1);
+  }
+  uint32_t r[GW];
+#pragma unroll
+  for (int j = 0; j < GW / 32; ++j) tmem_ld32(taddr + g * GW + j * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[j * 32]));
+  // bias of this group's columns: one coalesced load per 32 columns into the warp's smem slot, overlapped with the
+  // TMEM load; read back below as broadcast LDS.128 (no global-load latency inside the per-element loop)
+  if (bias) {
+#pragma unroll
+    for (int j = 0; j < GW / 32; ++j) {
+      const int col = col0 + j * 32 + lane;
+      bias_s[j * 32 + lane] = col < p.N ? __ldg(bias + col) : 0.f;
+    }
+  }
+  tmem_ld_wait();
+  __syncwarp();
+  if (res_tma) {
+    mbar_wait(res_bar, res_phase);
+    res_phase ^= 1;
+  }
+  const bool scale = p.alpha != 1.f;
+
+  if (mode == 1) {
+    // running (max, sum exp, first argmax) over this warp's columns of the row
+#pragma unroll
+    for (int c8 = 0; c8 < GW / 8; ++c8) {
+      const int col = col0 + c8 * 8;
+      if (col >= p.N) break;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[c8 * 8 + j]);
+      if (scale) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+      }
+      if (bias) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c8 * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c8 * 8 + 4);
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      float cm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (col + j >= p.N) v[j] = -INFINITY;
+        cm = fmaxf(cm, v[j]);
+      }
+      if (cm > run_max) {
+        run_sum *= __expf(run_max - cm);
+#pragma unroll
+        for (int j = 7; j >= 0; --j)
+          if (v[j] == cm) run_idx = col + j;
+        run_max = cm;
+      }
+      const float nm = -run_max * 1.4426950408889634f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) run_sum += ex2_approx(fmaf(v[j], 1.4426950408889634f, nm));
+    }
+    return;
+  }
+
+  const float nrv = -rvec * 1.4426950408889634f;
+#pragma unroll
+  for (int c8 = 0; c8 < GW / 8; ++c8) {
+    const int col = col0 + c8 * 8;
+    if (col >= p.N) break;   // warp-uniform
+    const int nv = min(8, p.N - col);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[c8 * 8 + j]);
+    if (scale) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+    }
+    if (bias) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias_s + c8 * 8);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias_s + c8 * 8 + 4);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (mode == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ex2_approx(fmaf(v[j], 1.4426950408889634f, nrv)) * rscale;
+    } else {
+      if (has_aux) {
+        if (tma) stg_store8(stg_aux, MTASR_DT_BF16, lane, GW, c8, v);
+        else if (row_ok) store8(p.aux, MTASR_DT_BF16, c_off + col, nv, v);
+      }
+      if (act == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = gelu_fast_f(v[j]);
+      } else if (act == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (has_res) {
+        float rr[8];
+        if (res_tma) stg_load8(stg_r, p.res_dtype, lane, GW, c8, rr);
+        else if (row_ok) load8(p.residual, p.res_dtype, r_off + col, nv, rr);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rr[j] = 0.f;
+        }
+        if (act == 3) {          // backward through GELU: residual holds the saved pre-activation
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= gelu_grad_fast_f(rr[j]);
+        } else if (act == 4) {   // backward through ReLU: residual holds the saved activation output
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = rr[j] > 0.f ? v[j] : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += rr[j];
+        }
+      }
+      if (E::GEN && p.accumulate && row_ok) {
+        float cc[8];
+        load8(p.c, p.c_dtype, c_off + col, nv, cc);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += cc[j];
+      }
+    }
+    if (tma) stg_store8(stg_c, p.c_dtype, lane, GW, c8, v);
+    else if (row_ok) store8(p.c, p.c_dtype, c_off + col, nv, v);
+  }
+  if (tma) {
+    fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+    __syncwarp();
+    if (lane == 0) {
+      if (p.splits > 1) tma_reduce_add_4d(tmap_c, stg_c, col0, row0, t.b0, t.b1);
+      else tma_store_4d(tmap_c, stg_c, col0, row0, t.b0, t.b1);
+      if (has_aux) tma_store_4d(tmap_aux, stg_aux, col0, row0, t.b0, t.b1);
+      bulk_commit();
+    }
+  }
+}
+
+template <int CFG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const GemmKP p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux,
+                 const __grid_constant__ CUtensorMap tmap_r, const GemmKP p) {
+  using E = Epi<CFG>;
+  // SWIZZLE_128B atoms need 1024-byte alignment.  The kernel has no static shared memory, so the dynamic window starts
+  // 1024-aligned; this is checked (trap) rather than paid for with a 1 KB slack that would cost a pipeline stage.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* stg_base = smem + p.stages * p.stage_bytes;                       // 1024-aligned (stage_bytes % 1024 == 0)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + EPI_WARPS * p.n_stg * STG_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_bar = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
+  float* bias_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + BAR_BYTES);   // EPI_WARPS x 64 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -142,17 +385,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (elect_one()) {
       prefetch_tmap(&tmap_a);
       prefetch_tmap(&tmap_b);
+      if (E::tma(p)) {
+        prefetch_tmap(&tmap_c);
+        if (E::aux(p)) prefetch_tmap(&tmap_aux);
+        if (E::res_tma(p)) prefetch_tmap(&tmap_r);
+      }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      for (int i = 0; i < STAGES; ++i) {
+      for (int i = 0; i < p.stages; ++i) {
         mbar_init(&full_bar[i], 1);
         mbar_init(&empty_bar[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tmem_full[i], 1);
-        mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+        mbar_init(&tmem_empty[i], EPI_WARPS);  // one arrive per epilogue warp
       }
+      for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
       fence_barrier_init();
     }
   } else if (warp == 2) {
@@ -174,9 +423,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const TileCoord t = decode_tile(p, tile);
         const int ab0 = p.a_use0 ? t.b0 : 0, ab1 = p.a_use1 ? t.b1 : 0;
         const int bb0 = p.b_use0 ? t.b0 : 0, bb1 = p.b_use1 ? t.b1 : 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sa = smem + stage * p.stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
           uint64_t* bar = &full_bar[stage];
           mbar_arrive_expect_tx(bar, stage_tx);
@@ -197,7 +446,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int j = 0; j < p.block_n / 64; ++j)
               tma_load_4d(sb + j * 8192, &tmap_b, bar, t.n_tile * p.block_n + j * 64, kb * BK, bb0, bb1);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -210,13 +459,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t acc_phase = 0;
       const uint32_t idesc = make_idesc_bf16(BM, p.block_n, p.a_major, p.b_major);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + stage * p.stage_bytes);
           const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -226,21 +476,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                                : make_smem_desc(sa + k * 2048, 8192, 1024);
             const uint64_t db = p.b_major == 0 ? make_smem_desc(sb + k * 32, 16, 1024)
                                                : make_smem_desc(sb + k * 2048, 8192, 1024);
-            umma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(d_tmem, da, db, idesc, (kb != t.kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
-    const int q = warp & 3;
+  } else if (warp >= CTRL_WARPS) {
+    // ------------------------------------------------------------------ epilogue: 8 warps, warp (q, half) owns TMEM lanes
+    // 32q..32q+31 and the column groups g with (g & 1) == half
+    const int e = warp - CTRL_WARPS;
+    const int q = e & 3;
+    const int half = e >> 2;
+    uint8_t* stg = stg_base + e * p.n_stg * STG_BYTES;
+    float* bias_s = bias_smem + e * 64;
+    const int mode = E::mode(p);
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t res_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const long long batch = static_cast<long long>(t.b1) * p.batch0 + t.b0;
@@ -248,109 +505,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const bool row_ok = row < p.M;
       const int col_base = t.n_tile * p.block_n;
       const int ncols = min(p.block_n, p.N - col_base);
+      const int n_groups = (ncols + p.gw - 1) / p.gw;
       const long long c_off = t.b0 * p.c_sb0 + t.b1 * p.c_sb1 + static_cast<long long>(row) * p.c_ld;
       const long long r_off = t.b0 * p.r_sb0 + t.b1 * p.r_sb1 + static_cast<long long>(row) * p.r_ld;
       const float* bias = p.bias ? p.bias + t.b0 * p.bias_sb0 : nullptr;
       float rvec = 0.f, rscale = 1.f;
-      if (p.mode == 2 && row_ok) {
+      if (mode == 2 && row_ok) {
         rvec = p.row_vec[batch * p.M + row];
         rscale = p.row_scale ? p.row_scale[batch * p.M + row] : 1.f;
       }
       float run_max = -INFINITY, run_sum = 0.f;
-      int run_idx = 0;
+      int run_idx = 0x7fffffff;
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
-      for (int chunk = 0; chunk * 32 < ncols; ++chunk) {
-        uint32_t r[32];
-        tmem_ld32(taddr + chunk * 32, r);
-        tmem_ld_wait();
-        const int c0 = col_base + chunk * 32;
-        if (p.mode == 1) {
-          float v[32];
-          float cm = -INFINITY;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = c0 + j;
-            float x = p.alpha * __uint_as_float(r[j]);
-            if (col < p.N) {
-              if (bias) x += __ldg(bias + col);
-            } else {
-              x = -INFINITY;
-            }
-            v[j] = x;
-            cm = fmaxf(cm, x);
-          }
-          if (cm > run_max) {
-            run_sum *= __expf(run_max - cm);
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (v[j] == cm) { run_idx = c0 + j; break; }
-            run_max = cm;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) run_sum += __expf(v[j] - run_max);
-        } else {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = c0 + g * 8;
-            const int nv = min(8, p.N - col);
-            if (nv <= 0) break;
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = p.alpha * __uint_as_float(r[g * 8 + j]);
-              if (bias && j < nv) x += __ldg(bias + col + j);
-              v[j] = x;
-            }
-            if (p.mode == 2) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = __expf(v[j] - rvec) * rscale;
-            } else {
-              if (p.aux && row_ok) store8(p.aux, MTASR_DT_BF16, c_off + col, nv, v);
-              if (p.act == 1) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gelu_f(v[j]);
-              } else if (p.act == 2) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-              }
-              if (p.residual && row_ok) {
-                float rr[8];
-                load8(p.residual, p.res_dtype, r_off + col, nv, rr);
-                if (p.act == 3) {        // backward through GELU: residual holds the saved pre-activation
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] *= gelu_grad_f(rr[j]);
-                } else if (p.act == 4) { // backward through ReLU: residual holds the saved activation output
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] = rr[j] > 0.f ? v[j] : 0.f;
-                } else {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j] += rr[j];
-                }
-              }
-              if (p.accumulate && row_ok) {
-                float cc[8];
-                load8(p.c, p.c_dtype, c_off + col, nv, cc);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] += cc[j];
-              }
-            }
-            if (row_ok) store8(p.c, p.c_dtype, c_off + col, nv, v);
-          }
-        }
+      for (int g = half; g < n_groups; g += 2) {
+        if (p.gw == 64)
+          epilogue_group<64, CFG>(p, &tmap_c, &tmap_aux, &tmap_r, stg, bias_s, &res_bar[e], res_phase, taddr, t, q, lane, g,
+                                  bias, rvec, rscale, row_ok, c_off, r_off, run_max, run_sum, run_idx);
+        else
+          epilogue_group<32, CFG>(p, &tmap_c, &tmap_aux, &tmap_r, stg, bias_s, &res_bar[e], res_phase, taddr, t, q, lane, g,
+                                  bias, rvec, rscale, row_ok, c_off, r_off, run_max, run_sum, run_idx);
       }
-      if (p.mode == 1 && row_ok) {
-        p.lse_part[(batch * p.M + row) * p.n_tiles + t.n_tile] =
-            make_float4(run_max, run_sum, __int_as_float(run_idx), 0.f);
-      }
+      // all TMEM reads of this tile are done (tcgen05.wait::ld inside every group): hand the accumulator back
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (mode == 1 && row_ok) {
+        p.lse_part[((batch * p.M + row) * p.n_tiles + t.n_tile) * 2 + half] =
+            make_float4(run_max, run_sum, __int_as_float(run_idx), 0.f);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (E::tma(p) && lane == 0) bulk_wait_all<0>();   // outstanding bulk stores must complete before the CTA exits
   }
 
   tc_fence_before();
@@ -360,6 +549,31 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
+
+typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const GemmKP);
+
+struct KernelEntry {
+  int cfg;
+  GemmKernelFn fn;
+};
+#define MTASR_GEMM_CFG(mode, act, aux, res) \
+  { make_cfg(mode, act, aux, res), gemm_bf16_kernel<make_cfg(mode, act, aux, res)> }
+// the epilogue combinations the model issues (TMA-staged outputs); anything else runs the generic kernel
+static const KernelEntry kKernels[] = {
+    MTASR_GEMM_CFG(0, 0, false, false),  // plain (+bias): QKV, every dgrad / wgrad, attention contractions, conv FE
+    MTASR_GEMM_CFG(0, 0, false, true),   // + residual: out-proj, FFN2, pos-conv dgrad
+    MTASR_GEMM_CFG(0, 1, false, false),  // GELU: conv FE (group-norm variant)
+    MTASR_GEMM_CFG(0, 1, true, false),   // GELU + pre-activation tap: FFN1
+    MTASR_GEMM_CFG(0, 1, true, true),    // GELU + tap + residual: pos-conv
+    MTASR_GEMM_CFG(0, 2, false, false),  // ReLU
+    MTASR_GEMM_CFG(0, 2, true, false),   // ReLU + tap: separator projections
+    MTASR_GEMM_CFG(0, 3, false, true),   // GELU backward: FFN2 dgrad
+    MTASR_GEMM_CFG(0, 4, false, true),   // ReLU backward
+    MTASR_GEMM_CFG(1, 0, false, false),  // row LSE / argmax partials: CTC head forward, greedy argmax
+    MTASR_GEMM_CFG(2, 0, false, false),  // softmax regeneration: CTC head backward
+    {CFG_GENERIC, gemm_bf16_kernel<CFG_GENERIC>},
+};
 
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -380,7 +594,9 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                      const uint32_t* box, const char* what) {
+                      const uint32_t* box, const char* what, int dtype = MTASR_DT_BF16, bool quiet = false,
+                      bool swizzle = true) {
+  const uint64_t esz = dtype == MTASR_DT_BF16 ? 2 : 4;
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(MTASR_ERR_DRIVER, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -393,17 +609,24 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64
     es[i] = 1;
   }
   for (int i = 1; i < rank; ++i) {
-    gstr[i - 1] = strides_elems[i] * 2;
-    if (gstr[i - 1] % 16 != 0 || gstr[i - 1] == 0)
+    gstr[i - 1] = strides_elems[i] * esz;
+    if (gstr[i - 1] % 16 != 0 || gstr[i - 1] == 0) {
+      if (quiet) return MTASR_ERR_INVALID_ARG;
       return set_error(MTASR_ERR_INVALID_ARG, "gemm: %s stride[%d]=%llu bytes is not a positive multiple of 16", what, i,
                        (unsigned long long)gstr[i - 1]);
+    }
   }
-  if (reinterpret_cast<uintptr_t>(base) % 16 != 0)
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) {
+    if (quiet) return MTASR_ERR_INVALID_ARG;
     return set_error(MTASR_ERR_INVALID_ARG, "gemm: %s base pointer not 16-byte aligned", what);
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  }
+  CUresult r = fn(map, dtype == MTASR_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank,
+                  const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
+    if (quiet) return MTASR_ERR_DRIVER;
     return set_error(MTASR_ERR_DRIVER,
                      "gemm: cuTensorMapEncodeTiled(%s) failed with %d (rank %d dims %llu,%llu,%llu,%llu strides %llu,%llu,%llu box %u,%u,%u)",
                      what, (int)r, rank, (unsigned long long)gdim[0], (unsigned long long)gdim[1],
@@ -412,6 +635,20 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const uint64
                      bx[0], bx[1], bx[2]);
   }
   return 0;
+}
+
+// Tensor map of an epilogue tensor x[b0][b1][m][n] (element strides ld / sb0 / sb1) with a (gw cols x 32 rows) box.
+static int encode_out_map(CUtensorMap* map, const void* base, int dtype, int M, int N, int batch0, int batch1, long long ld,
+                          long long sb0, long long sb1, int gw) {
+  if (ld <= 0) return MTASR_ERR_INVALID_ARG;
+  const uint64_t d2 = (batch0 > 1 && sb0 > 0) ? batch0 : 1, d3 = (batch1 > 1 && sb1 > 0) ? batch1 : 1;
+  if ((batch0 > 1 && sb0 <= 0) || (batch1 > 1 && sb1 <= 0)) return MTASR_ERR_INVALID_ARG;
+  const uint64_t dims[4] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M), d2, d3};
+  const uint64_t str[4] = {1, static_cast<uint64_t>(ld), d2 > 1 ? static_cast<uint64_t>(sb0) : static_cast<uint64_t>(ld),
+                           d3 > 1 ? static_cast<uint64_t>(sb1) : static_cast<uint64_t>(ld)};
+  const uint32_t box[4] = {static_cast<uint32_t>(gw), 32, 1, 1};
+  const bool sw128 = gw * (dtype == MTASR_DT_BF16 ? 2 : 4) == 128;
+  return encode_map(map, base, 4, dims, str, box, "epilogue tensor", dtype, true, sw128);
 }
 
 std::atomic<long long> g_launches{0};
@@ -432,9 +669,10 @@ using namespace mtasr;
 
 extern "C" int64_t mtasr_launch_count(void) { return g_launches.load(); }
 
+// Number of mode-1 partial slots per row: two epilogue warps (column halves) per N tile.
 extern "C" int mtasr_gemm_n_tiles(int32_t N, int32_t block_n) {
   if (block_n != 64 && block_n != 128 && block_n != 256) block_n = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  return (N + block_n - 1) / block_n;
+  return 2 * ((N + block_n - 1) / block_n);
 }
 
 extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
@@ -468,6 +706,8 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   MTASR_CHECK_ARG(nt < (1LL << 31), "gemm: too many tiles");
   p.num_tiles = static_cast<int>(nt);
   p.num_kb = (d->K + BK - 1) / BK;
+  p.splits = 1;
+  p.kb_per_split = p.num_kb;
   p.c = d->c; p.c_dtype = d->c_dtype; p.c_ld = d->c_ld; p.c_sb0 = d->c_sb0; p.c_sb1 = d->c_sb1;
   p.aux = reinterpret_cast<__nv_bfloat16*>(d->aux);
   p.bias = d->bias; p.bias_sb0 = d->bias_sb0;
@@ -517,16 +757,84 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   }
   if (rc) return rc;
 
+  // ---- epilogue path: swizzled smem staging + TMA tiled stores (and TMA-loaded residual) whenever the tensors can be
+  // described by a tensor map (16-byte aligned base / strides); otherwise per-thread vector loads/stores.
+  CUtensorMap mc, maux, mr;
+  memset(&mc, 0, sizeof(mc));
+  memset(&maux, 0, sizeof(maux));
+  memset(&mr, 0, sizeof(mr));
+  p.tma_epi = 0;
+  p.stg_aux = p.stg_res = -1;
+  p.n_stg = 0;
+  const bool any_f32 = (d->mode != 1 && d->c_dtype == MTASR_DT_F32) || (d->residual && d->res_dtype == MTASR_DT_F32);
+  p.gw = any_f32 ? 32 : 64;
+  if (bn < p.gw) p.gw = bn;
+  if (d->mode != 1 && !d->accumulate && getenv("MTASR_GEMM_DIRECT_EPILOGUE") == nullptr) {
+    bool ok = encode_out_map(&mc, d->c, d->c_dtype, d->M, d->N, d->batch0, d->batch1, d->c_ld, d->c_sb0, d->c_sb1, p.gw) == 0;
+    int n = 1;
+    if (ok && d->aux) {
+      ok = encode_out_map(&maux, d->aux, MTASR_DT_BF16, d->M, d->N, d->batch0, d->batch1, d->c_ld, d->c_sb0, d->c_sb1, p.gw) == 0;
+      p.stg_aux = n++;
+    }
+    bool res_ok = false;
+    if (ok && d->residual) {
+      res_ok = encode_out_map(&mr, d->residual, d->res_dtype, d->M, d->N, d->batch0, d->batch1, d->r_ld, d->r_sb0, d->r_sb1,
+                              p.gw) == 0;
+      if (res_ok) p.stg_res = n++;
+    }
+    if (ok) {
+      p.tma_epi = 1;
+      p.n_stg = n;
+    } else {
+      p.stg_aux = p.stg_res = -1;
+    }
+  }
+  // split-K: an un-batched plain fp32 GEMM that would leave more than half of the SMs idle (the K = B*T weight-gradient
+  // contractions with small M x N) is cut along K; partial tiles are summed by TMA reduce-add into a zeroed C.
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p.tma_epi && d->mode == 0 && d->act == 0 && !d->aux && !d->residual && !d->bias && d->c_dtype == MTASR_DT_F32 &&
+      d->batch0 == 1 && d->batch1 == 1 && d->alpha == 1.0f && p.num_tiles * 2 <= num_sms() && p.num_kb >= 16 &&
+      getenv("MTASR_GEMM_NO_SPLITK") == nullptr) {
+    int splits = num_sms() / p.num_tiles;
+    if (splits > p.num_kb / 8) splits = p.num_kb / 8;
+    if (splits > 1) {
+      p.kb_per_split = (p.num_kb + splits - 1) / splits;
+      p.splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+      p.num_tiles *= p.splits;
+      if (cudaMemset2DAsync(d->c, static_cast<size_t>(d->c_ld) * 4, 0, static_cast<size_t>(d->N) * 4, d->M, st) != cudaSuccess)
+        return set_error(MTASR_ERR_LAUNCH, "gemm: split-K memset failed");
+    }
+  }
+  p.stage_bytes = A_STAGE_BYTES + bn * BK * 2;
+  const int fixed = BAR_BYTES + BIAS_BYTES + EPI_WARPS * p.n_stg * STG_BYTES;
+  int stages = (SMEM_LIMIT - fixed) / p.stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return set_error(MTASR_ERR_UNSUPPORTED, "gemm: shared memory budget allows %d pipeline stages", stages);
+  p.stages = stages;
+  const int smem_bytes = fixed + stages * p.stage_bytes;
+
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    for (const KernelEntry& k : kKernels) {
+      cudaError_t e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+      if (e != cudaSuccess) attr_err = e;
+    }
   });
   if (attr_err != cudaSuccess)
     return set_error(MTASR_ERR_LAUNCH, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  // specialised kernel when the outputs are TMA-staged (mode 1 has no tensor output) and the residual is TMA-loaded
+  GemmKernelFn kernel = kKernels[sizeof(kKernels) / sizeof(kKernels[0]) - 1].fn;
+  const bool special_ok = getenv("MTASR_GEMM_GENERIC") == nullptr && !d->accumulate &&
+                          (d->mode == 1 || (p.tma_epi && (!d->residual || p.stg_res >= 0)));
+  if (special_ok) {
+    const int want = make_cfg(d->mode, d->mode == 0 ? d->act : 0, d->mode == 0 && d->aux != nullptr,
+                              d->mode == 0 && d->residual != nullptr);
+    for (const KernelEntry& k : kKernels)
+      if (k.cfg == want) kernel = k.fn;
+  }
 
   const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   ProfRec rec{};
   bool prof = false;
   {
@@ -539,7 +847,7 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
     rec.flops = 2.0 * d->M * static_cast<double>(d->N) * d->K * d->batch0 * d->batch1;
     cudaEventRecord(rec.e0, st);
   }
-  gemm_bf16_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ma, mb, p);
+  kernel<<<grid, GEMM_THREADS, smem_bytes, st>>>(ma, mb, mc, maux, mr, p);
   g_launches.fetch_add(1);
   if (prof) {
     cudaEventRecord(rec.e1, st);

@@ -223,6 +223,23 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def relpos_gate_fwd(x, wab, bab, cst, B, T, H):
+    gate = torch.empty(B, H, T, device=x.device, dtype=torch.float32)
+    check(_lib.load().mtasr_relpos_gate_fwd(_p(x), _dt(x), _p(wab), _p(bab), _p(cst), B, T, H, _p(gate), _stream()),
+          "mtasr_relpos_gate_fwd")
+    return gate
+
+
+def relpos_gate_bwd(x, wab, bab, cst, dgate, B, T, H):
+    dx = torch.empty(B, T, H * 64, device=x.device, dtype=torch.float32)
+    dwab = torch.zeros(128, device=x.device, dtype=torch.float32)
+    dbab = torch.zeros(2, device=x.device, dtype=torch.float32)
+    dcst = torch.zeros(H, device=x.device, dtype=torch.float32)
+    check(_lib.load().mtasr_relpos_gate_bwd(_p(x), _dt(x), _p(wab), _p(bab), _p(cst), _p(dgate), B, T, H, _p(dx), _p(dwab),
+                                            _p(dbab), _p(dcst), _stream()), "mtasr_relpos_gate_bwd")
+    return dx, dwab, dbab, dcst
+
+
 def attn_softmax_fwd(S, gate, table, klen, B, H, T, Tp, scale):
     P = torch.empty(B, H, T, Tp, device=S.device, dtype=torch.bfloat16)
     check(_lib.load().mtasr_attn_softmax_fwd(_p(S), _p(gate), _p(table), _p(klen), B, H, T, Tp, scale, _p(P), _stream()),

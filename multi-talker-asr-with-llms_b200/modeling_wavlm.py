@@ -248,14 +248,9 @@ class WavLMModel(WavLMPreTrainedModel):
 
     @staticmethod
     def _gate(h: torch.Tensor, attn) -> torch.Tensor:
-        """gru_rel_pos gate of hf:167-176 -> (B,H,T) fp32.  64->8 projection per head; tiny, kept as torch glue so
-        autograd delivers gradients to gru_rel_pos_linear / gru_rel_pos_const and back into the layer input."""
-        B, T, D = h.shape
-        H = attn.num_heads
-        proj = F.linear(h.view(B, T, H, D // H).float(), attn.gru_rel_pos_linear.weight.float(), attn.gru_rel_pos_linear.bias.float())
-        ab = torch.sigmoid(proj.view(B, T, H, 2, 4).sum(-1))
-        gate = ab[..., 0] * (ab[..., 1] * attn.gru_rel_pos_const.view(1, 1, H).float() - 1.0) + 2.0
-        return gate.permute(0, 2, 1).contiguous()
+        """gru_rel_pos gate of hf:167-176 -> (B,H,T) fp32 (ops.RelPosGateFn: one warp-per-frame kernel, with gradients
+        to gru_rel_pos_linear / gru_rel_pos_const and back into the layer input)."""
+        return ops.RelPosGateFn.apply(h, attn.gru_rel_pos_linear.weight, attn.gru_rel_pos_linear.bias, attn.gru_rel_pos_const)
 
     def _encoder_layer(self, x, layer, table, klen):
         at, ff = layer.attention, layer.feed_forward

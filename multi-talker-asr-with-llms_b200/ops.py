@@ -145,6 +145,42 @@ class FFNFn(Function):
         return dh, (dy if ctx.needs_input_grad[1] else None), dw1, db1, dw2, db2
 
 
+# ------------------------------------------------------------------------------------------------------ rel-pos gate
+class RelPosGateFn(Function):
+    """gru_rel_pos gate of hf:167-176 -> (B,H,T) fp32:  view(Linear_{64->8}(x_h), 2, 4).sum(-1) -> two sigmoids ->
+    ga * (gb * const_h - 1) + 2.  The 4-row sums of the tiny (8,64) weight are formed on the parameter side; the per-frame
+    work (and its backward into the layer input, the weight, the bias and gru_rel_pos_const) is one warp-per-frame kernel."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, const):
+        B, T, D = h.shape
+        if weight.shape != (8, 64) or D % 64 != 0:
+            raise NotImplementedError("mtasr_b200: gru_rel_pos gate expects head_dim 64 and an (8, 64) projection")
+        H = D // 64
+        w = weight.detach().float()
+        b = bias.detach().float()
+        wab = torch.cat([w[:4].sum(0), w[4:].sum(0)]).contiguous()
+        bab = torch.stack([b[:4].sum(), b[4:].sum()]).contiguous()
+        cst = const.detach().float().reshape(H).contiguous()
+        x = h.detach().contiguous()
+        gate = K.relpos_gate_fwd(x, wab, bab, cst, B, T, H)
+        ctx.dims = (B, T, H)
+        ctx.save_for_backward(x, wab, bab, cst)
+        ctx.const_shape = const.shape
+        return gate
+
+    @staticmethod
+    def backward(ctx, dgate):
+        x, wab, bab, cst = ctx.saved_tensors
+        B, T, H = ctx.dims
+        dx, dwab, dbab, dcst = K.relpos_gate_bwd(x, wab, bab, cst, dgate.contiguous().float(), B, T, H)
+        dh = dx.to(x.dtype) if ctx.needs_input_grad[0] else None
+        dw = torch.cat([dwab[:64].expand(4, 64), dwab[64:].expand(4, 64)], 0) if ctx.needs_input_grad[1] else None
+        db = torch.cat([dbab[0:1].expand(4), dbab[1:2].expand(4)]) if ctx.needs_input_grad[2] else None
+        dc = dcst.view(ctx.const_shape) if ctx.needs_input_grad[3] else None
+        return dh, dw, db, dc
+
+
 # ------------------------------------------------------------------------------------------------------ attention
 class AttentionFn(Function):
     """res + out_proj(softmax(Q K^T / sqrt(d) + gate * relpos + key mask) V)   (hf:147-241, torch:6244-6695).

@@ -47,7 +47,7 @@ def test_host_side_queries_and_argument_errors():
     lib = _lib.load()
     assert lib.mtasr_ctc_state_pad(0) == 64 and lib.mtasr_ctc_state_pad(31) == 64 and lib.mtasr_ctc_state_pad(32) == 128
     assert lib.mtasr_ctc_state_pad(255) == 512 and lib.mtasr_ctc_state_pad(256) == -1
-    assert lib.mtasr_gemm_n_tiles(128259, 0) == 502 and lib.mtasr_gemm_n_tiles(64, 0) == 1 and lib.mtasr_gemm_n_tiles(300, 128) == 3
+    assert lib.mtasr_gemm_n_tiles(128259, 0) == 1004 and lib.mtasr_gemm_n_tiles(64, 0) == 2 and lib.mtasr_gemm_n_tiles(300, 128) == 6
     assert lib.mtasr_gemm_bf16(None, None) == -1
     assert b"null descriptor" in lib.mtasr_last_error_string()
     d = _lib.GemmDesc()

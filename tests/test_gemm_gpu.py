@@ -166,3 +166,13 @@ def test_lse_and_exp_modes(cuda, V):
     Kn.gemm(Kn.Operand(h, K), Kn.Operand(w, K), M, V, K, Kn.Out(Pm, Pm.stride(0)), bias=bias, mode=2, row_vec=lse, row_scale=scale)
     ref = torch.softmax(logits, -1) * scale[:, None]
     assert _rel(Pm[:, :V], ref) < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 1024, 15968), (896, 128, 4000), (256, 192, 7000)])
+def test_split_k_wgrad(cuda, M, N, K):
+    """Weight-gradient shaped contractions with few output tiles are split along K (TMA reduce-add into a zeroed C)."""
+    from mtasr_b200 import kernels as Kn
+    dy, x = _rand((K, M), cuda, 1, 21), _rand((K, N), cuda, 1, 22)
+    dw = torch.full((M, N + 8), float("nan"), device=cuda)[:, :N]          # strided C view (ld = N + 8)
+    Kn.gemm(Kn.Operand(dy, M, major=1), Kn.Operand(x, N, major=1), M, N, K, Kn.Out(dw, dw.stride(0)))
+    assert _rel(dw, dy.float().t() @ x.float()) < 1e-5

@@ -90,3 +90,38 @@ def test_attn_softmax(cuda, B, H, T):
     dt_ref = torch.zeros_like(table)
     dt_ref.index_add_(1, idx.reshape(-1), (dz * gate[..., None]).sum(0).reshape(H, -1))
     assert _rel(dtable, dt_ref) < 1e-4
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,T,H", [(2, 37, 2), (3, 199, 16), (1, 50, 12)])
+def test_relpos_gate_fwd_bwd(cuda, B, T, H, dt):
+    """gru_rel_pos gate (hf:167-176) and its gradients vs the torch formulation of the reference."""
+    from mtasr_b200 import ops
+    torch.manual_seed(3)
+    D = H * 64
+    h = (torch.randn(B, T, D, device=cuda)).to(dt)
+    lin = torch.nn.Linear(64, 8).to(cuda)
+    const = (torch.rand(1, H, 1, 1, device=cuda) + 0.5).requires_grad_(True)
+    h1 = h.clone().requires_grad_(True)
+    gate = ops.RelPosGateFn.apply(h1, lin.weight, lin.bias, const)
+    h2 = h.float().clone().requires_grad_(True)
+    proj = lin(h2.view(B, T, H, 64).permute(0, 2, 1, 3))                       # (B,H,T,8)
+    ab = torch.sigmoid(proj.view(B, H, T, 2, 4).sum(-1))
+    ref = (ab[..., 0:1] * (ab[..., 1:2] * const - 1.0) + 2.0).squeeze(-1)     # (B,H,T)
+    assert _rel(gate, ref) < 1e-5
+    up = torch.randn(B, H, T, device=cuda)
+    g1 = torch.autograd.grad((gate * up).sum(), [h1, lin.weight, lin.bias, const])
+    g2 = torch.autograd.grad((ref * up).sum(), [h2, lin.weight, lin.bias, const])
+    tol = 1e-4 if dt == torch.float32 else 6e-3
+    assert _rel(g1[0], g2[0]) < tol
+    for a, b in zip(g1[1:], g2[1:]):
+        assert _rel(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N", [(1000, 1024), (15968, 3072), (77, 40), (333, 129)])
+def test_colsum_shapes(cuda, M, N, dt):
+    from mtasr_b200 import kernels as Kn
+    torch.manual_seed(4)
+    x = torch.randn(M, N, device=cuda).to(dt)
+    assert _rel(Kn.colsum(x), x.float().sum(0)) < 1e-5

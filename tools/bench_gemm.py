@@ -39,6 +39,33 @@ for name, N, K in [("qkv", 3072, 1024), ("out", 1024, 1024), ("ffn1", 4096, 1024
     dw = torch.empty(N, K, device=dev, dtype=torch.float32)
     ms = timeit(lambda: Kn.gemm(Kn.Operand(dy, N, major=1), Kn.Operand(x, K, major=1), N, K, M, Kn.Out(dw, K)))
     res.append((name + "_wgrad", ms, 2 * M * N * K / ms / 1e9))
+# epilogue-heavy variants as the model issues them
+x, w1, b1 = rnd(M, 1024), rnd(4096, 1024), torch.randn(4096, device=dev)
+a = torch.empty(M, 4096, device=dev, dtype=torch.bfloat16); u = torch.empty_like(a)
+ms = timeit(lambda: Kn.gemm(Kn.Operand(x, 1024), Kn.Operand(w1, 1024), M, 4096, 1024, Kn.Out(a, 4096), bias=b1, act=Kn.ACT_GELU, aux=u))
+res.append(("ffn1_gelu_aux", ms, 2 * M * 4096 * 1024 / ms / 1e9))
+w2, b2 = rnd(1024, 4096), torch.randn(1024, device=dev)
+resid = torch.randn(M, 1024, device=dev); y32 = torch.empty(M, 1024, device=dev)
+ms = timeit(lambda: Kn.gemm(Kn.Operand(a, 4096), Kn.Operand(w2, 4096), M, 1024, 4096, Kn.Out(y32, 1024), bias=b2, residual=Kn.Out(resid, 1024)))
+res.append(("ffn2_res_f32", ms, 2 * M * 4096 * 1024 / ms / 1e9))
+wo = rnd(1024, 1024)
+ms = timeit(lambda: Kn.gemm(Kn.Operand(x, 1024), Kn.Operand(wo, 1024), M, 1024, 1024, Kn.Out(y32, 1024), bias=b2, residual=Kn.Out(resid, 1024)))
+res.append(("out_res_f32", ms, 2 * M * 1024 * 1024 / ms / 1e9))
+dyb = rnd(M, 1024); du = torch.empty(M, 4096, device=dev, dtype=torch.bfloat16)
+ms = timeit(lambda: Kn.gemm(Kn.Operand(dyb, 1024), Kn.Operand(w2, 4096, major=1), M, 4096, 1024, Kn.Out(du, 4096), act=Kn.ACT_GELU_BWD, residual=Kn.Out(u, 4096)))
+res.append(("ffn2_dgrad_gelubwd", ms, 2 * M * 4096 * 1024 / ms / 1e9))
+Bq, Hh, Tt, dd = 32, 16, 499, 64
+Tp = 504
+qkv = rnd(Bq * Tt, 3 * 1024)
+S = torch.empty(Bq, Hh, Tt, Tp, device=dev)
+ms = timeit(lambda: Kn.gemm(Kn.Operand(qkv, 3072, sb0=dd, sb1=Tt * 3072, rows=Tt), Kn.Operand(qkv, 3072, sb0=dd, sb1=Tt * 3072, offset=1024, rows=Tt),
+                            Tt, Tt, dd, Kn.Out(S, Tp, sb0=Tt * Tp, sb1=Hh * Tt * Tp), batch=(Hh, Bq)))
+res.append(("attn_qk_f32", ms, 2 * Bq * Hh * Tt * Tt * dd / ms / 1e9))
+Pm = torch.zeros(Bq, Hh, Tt, Tp, device=dev, dtype=torch.bfloat16)
+O = torch.empty(Bq * Tt, 1024, device=dev, dtype=torch.bfloat16)
+ms = timeit(lambda: Kn.gemm(Kn.Operand(Pm, Tp, sb0=Tt * Tp, sb1=Hh * Tt * Tp), Kn.Operand(qkv, 3072, major=1, sb0=dd, sb1=Tt * 3072, offset=2048, rows=Tt),
+                            Tt, dd, Tt, Kn.Out(O, 1024, sb0=dd, sb1=Tt * 1024), batch=(Hh, Bq)))
+res.append(("attn_pv", ms, 2 * Bq * Hh * Tt * Tt * dd / ms / 1e9))
 V, K = 128259, 1024
 h, w = rnd(M, K), rnd(V, K)
 nt = Kn.gemm_n_tiles(V)
