@@ -173,6 +173,18 @@ int mtasr_attn_softmax_fwd(const float* S, const float* gate, const float* table
 int mtasr_attn_softmax_bwd(const void* P_bf16, const float* dP, const float* gate, const float* table, int32_t B,
                            int32_t H, int32_t T, int32_t Tp, float scale, void* dS_bf16, float* dgate, float* dtable,
                            void* stream);
+/* Fused attention forward (hf:147-271 + torch MHA hf:206-228), head_dim 64: qkv (B*T, 3*H*64) bf16 = [q | k | v] head-major,
+ * gate (B,H,T) f32, table (H,2T-1) f32 (Toeplitz rel-pos bias), klen (B) i32 valid key counts or NULL.
+ * out (B*T, H*64) bf16 = softmax_k(q.k*scale + gate*table[k-q+T-1]) v ; lse (B,H,T) f32 row log-sum-exp (for the backward).
+ * S / P tiles never leave TMEM / shared memory. */
+int mtasr_attn_fwd(const void* qkv_bf16, const float* gate, const float* table, const int32_t* klen, int32_t B, int32_t H,
+                   int32_t T, float scale, void* out_bf16, float* lse, void* stream);
+/* Fused attention backward.  out / dout (B*T, H*64) bf16 are the forward output and its gradient; lse from the forward.
+ * Writes dqkv (B*T, 3*H*64) bf16 = [dq | dk | dv].  dq32 (B*T, H*64) f32, dgate (B,H,T) f32 and dtable (H,2T-1) f32 are
+ * ACCUMULATED (zero them first); delta (B,H,T) f32 is scratch. */
+int mtasr_attn_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse, const float* gate,
+                   const float* table, const int32_t* klen, int32_t B, int32_t H, int32_t T, float scale, void* dqkv_bf16,
+                   float* dq32, float* delta, float* dgate, float* dtable, void* stream);
 /* y (B,Tpad,D) bf16 = zero-pad(x (B,T,D), pad_l rows left), rows t >= vlen[b] zeroed when vlen != NULL. */
 int mtasr_pad_cast(const void* x, int32_t x_dtype, int32_t B, int32_t T, int32_t D, int32_t pad_l, int32_t Tpad,
                    const int32_t* vlen, void* y_bf16, void* stream);

@@ -68,6 +68,8 @@ SIGNATURES = {
     "mtasr_colsum": (C.c_int, [_P, _I32, _I64, _I32, _I64, _P, _P]),
     "mtasr_relpos_gate_fwd": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
     "mtasr_relpos_gate_bwd": (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "mtasr_attn_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P]),
+    "mtasr_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P, _P]),
     "mtasr_attn_softmax_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P, _P]),
     "mtasr_attn_softmax_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P, _P, _P, _P]),
     "mtasr_pad_cast": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),

@@ -1,0 +1,819 @@
+// Fused self-attention with the gated relative-position bias folded into the softmax tile (hf:147-271,
+// torch F.multi_head_attention_forward hf:206-228) on tcgen05 / TMEM / TMA.
+//
+//   O[b,q,h,:] = softmax_k( Q K^T / sqrt(d) + gate[b,h,q] * table[h, k-q+T-1]  (k < klen[b]) ) V        d = 64
+//
+// The reference materialises the (B*H,T,T) fp32 bias and SDPA's score tensors every layer; the unfused path of this
+// repo wrote S (fp32) and P (bf16).  Here nothing of size T x T ever reaches HBM: one CTA owns a 128-query tile of one
+// (utterance, head); S tiles live in TMEM, P tiles in swizzled shared memory, O accumulates in TMEM.
+//
+// Forward, warp-specialised (256 threads): warp 0 TMA producer (Q once, then K/V tiles through a 4-slot ring),
+// warp 1 single-thread tcgen05.mma issuer, warp 2 TMEM allocator, warps 4..7 softmax (thread = query row).
+// Exact two-pass softmax: pass A runs QK^T only and reduces the row maximum (no exponentials), pass B recomputes the
+// S tiles, forms P = exp(z - max) once, accumulates the row sum in registers and O += P V in TMEM -- no accumulator
+// rescaling, no second exponential; the extra QK^T pass is cheap because the kernel is SFU(exp)-bound, not MMA-bound.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mtasr {
+
+static constexpr int AT_D = 64;          // head dim
+static constexpr int AT_BQ = 128;        // queries per CTA tile
+static constexpr int AT_BK = 128;        // keys per inner tile
+static constexpr int AT_TILE = 128 * 64 * 2;   // one 128 x 64 bf16 operand tile = 16 KB
+static constexpr int AT_KV_SLOTS = 4;
+static constexpr int AT_P_BYTES = 128 * 128 * 2;   // P tile: two 64-key chunks of 128 rows x 128 B
+static constexpr int AT_THREADS = 256;
+static constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnFwdP {
+  int B, H, T, nq, nk;            // nq / nk = number of 128-row query / key tiles
+  int n_items;
+  float scale_log2;               // softmax scale * log2(e)
+  const float* gate;              // (B,H,T)
+  const float* table;             // (H, 2T-1)
+  const int* klen;                // (B) or null
+  __nv_bfloat16* out;             // (B*T, H*64)
+  float* lse;                     // (B,H,T) natural-log row LSE of the biased scores (saved for the backward)
+};
+
+// K-major SW128 operand tile [rows][64] bf16: UMMA_K step ks (16 elements) starts 32 bytes further in the swizzle row.
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t base, int ks) { return make_smem_desc(base + ks * 32, 16, 1024); }
+// MN-major view of a [k-rows][64 mn] tile (rows are the contraction index): 16 k-rows = 2048 bytes per UMMA_K step;
+// `lbo` = byte distance between 64-wide MN chunks.
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t base, int ks, uint32_t lbo) {
+  return make_smem_desc(base + ks * 2048, lbo, 1024);
+}
+__device__ __forceinline__ uint32_t swz128(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }
+
+__host__ __device__ __forceinline__ int attn_table_bytes(int T) { return ((2 * T - 1 + 256) * 4 + 15) / 16 * 16; }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* q_s = smem;                                   // 16 KB
+  uint8_t* kv_s = q_s + AT_TILE;                         // 4 x 16 KB
+  uint8_t* p_s = kv_s + AT_KV_SLOTS * AT_TILE;           // 2 x 32 KB
+  float* tbl_s = reinterpret_cast<float*>(p_s + 2 * AT_P_BYTES);   // 2T-1 floats
+  // (+256 floats of slack: masked lanes of the last key tile may form addresses up to 128 entries past the table)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tbl_s) + attn_table_bytes(p.T));
+  uint64_t* q_full = bars;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;                  // [4]
+  uint64_t* kv_empty = kv_full + AT_KV_SLOTS;    // [4]
+  uint64_t* s_full = kv_empty + AT_KV_SLOTS;     // [2]
+  uint64_t* s_empty = s_full + 2;                // [2]
+  uint64_t* p_full = s_empty + 2;                // [2]
+  uint64_t* p_empty = p_full + 2;                // [2]
+  uint64_t* o_full = p_empty + 2;
+  uint64_t* o_empty = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    if (elect_one()) prefetch_tmap(&tmap_qkv);
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(q_full, 1);
+      mbar_init(q_empty, 1);
+      for (int i = 0; i < AT_KV_SLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
+        mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
+      }
+      mbar_init(o_full, 1);
+      mbar_init(o_empty, 4);
+      fence_barrier_init();
+    }
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_s[2] = {tmem_base, tmem_base + 128};
+  const uint32_t tm_o = tmem_base + 256;
+  const int nk = p.nk;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      int slot = 0;
+      uint32_t ph = 0, qph = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int qt = item % p.nq, h = (item / p.nq) % p.H, b = item / (p.nq * p.H);
+        mbar_wait(q_empty, qph ^ 1);
+        qph ^= 1;
+        mbar_arrive_expect_tx(q_full, AT_TILE);
+        tma_load_4d(q_s, &tmap_qkv, q_full, 0, qt * AT_BQ, h, b);
+        auto load = [&](int row0, int slice) {
+          mbar_wait(&kv_empty[slot], ph ^ 1);
+          mbar_arrive_expect_tx(&kv_full[slot], AT_TILE);
+          tma_load_4d(kv_s + slot * AT_TILE, &tmap_qkv, &kv_full[slot], 0, row0, slice, b);
+          if (++slot == AT_KV_SLOTS) { slot = 0; ph ^= 1; }
+        };
+        for (int j = 0; j < nk; ++j) load(j * AT_BK, p.H + h);            // pass A: K tiles
+        load(0, p.H + h);                                                // pass B: K_0, then K_{j+1}, V_j
+        for (int j = 0; j < nk; ++j) {
+          if (j + 1 < nk) load((j + 1) * AT_BK, p.H + h);
+          load(j * AT_BK, 2 * p.H + h);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);          // S = Q K^T: both K-major
+      const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);           // O += P V: A K-major, B (V) MN-major
+      int slot = 0;
+      uint32_t ph = 0, qph = 0, oph = 0;
+      uint32_t sph[2] = {0, 0}, pph[2] = {0, 0};
+      int sb = 0;   // S buffer / P buffer alternate per key tile, continuing across passes and items
+      auto issue_s = [&](int buf) {
+        mbar_wait(&kv_full[slot], ph);
+        mbar_wait(&s_empty[buf], sph[buf] ^ 1);
+        sph[buf] ^= 1;
+        tc_fence_after();
+        const uint32_t qa = smem_u32(q_s), ka = smem_u32(kv_s + slot * AT_TILE);
+#pragma unroll
+        for (int ks = 0; ks < AT_D / 16; ++ks) umma_f16(tm_s[buf], desc_kmajor(qa, ks), desc_kmajor(ka, ks), idesc_s, ks != 0);
+        umma_commit(&kv_empty[slot]);
+        umma_commit(&s_full[buf]);
+        if (++slot == AT_KV_SLOTS) { slot = 0; ph ^= 1; }
+      };
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        mbar_wait(q_full, qph);
+        qph ^= 1;
+        for (int j = 0; j < nk; ++j) { issue_s(sb); sb ^= 1; }          // pass A
+        int pb = sb;                                                     // pass B: P buffer index follows the S buffer
+        issue_s(sb); sb ^= 1;
+        for (int j = 0; j < nk; ++j) {
+          if (j + 1 < nk) { issue_s(sb); sb ^= 1; }
+          mbar_wait(&p_full[pb], pph[pb]);
+          pph[pb] ^= 1;
+          mbar_wait(&kv_full[slot], ph);
+          if (j == 0) { mbar_wait(o_empty, oph ^ 1); oph ^= 1; }
+          tc_fence_after();
+          const uint32_t pa = smem_u32(p_s + pb * AT_P_BYTES), va = smem_u32(kv_s + slot * AT_TILE);
+#pragma unroll
+          for (int ks = 0; ks < AT_BK / 16; ++ks)
+            umma_f16(tm_o, make_smem_desc(pa + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), desc_mnmajor(va, ks, 8192), idesc_o,
+                     (j | ks) != 0);
+          umma_commit(&kv_empty[slot]);
+          umma_commit(&p_empty[pb]);
+          if (++slot == AT_KV_SLOTS) { slot = 0; ph ^= 1; }
+          pb ^= 1;
+        }
+        umma_commit(o_full);
+        umma_commit(q_empty);
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- softmax warps: thread = query row
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    uint32_t sph[2] = {0, 0}, pph[2] = {0, 0}, oph = 0;
+    int sb = 0;
+    int cur_h = -1;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int qt = item % p.nq, h = (item / p.nq) % p.H, b = item / (p.nq * p.H);
+      named_bar_sync(1, 128);                      // every softmax thread is done with the previous item's table
+      if (h != cur_h) {
+        const float* trow = p.table + static_cast<long long>(h) * (2 * p.T - 1);
+        for (int i = threadIdx.x - 128; i < 2 * p.T - 1; i += 128) tbl_s[i] = trow[i] * LOG2E;
+        cur_h = h;
+      }
+      named_bar_sync(1, 128);
+      const int q = qt * AT_BQ + r;
+      const bool q_ok = q < p.T;
+      const int qc = q_ok ? q : p.T - 1;
+      const int kl = p.klen ? min(p.klen[b], p.T) : p.T;
+      const float g = p.gate[(static_cast<long long>(b) * p.H + h) * p.T + qc];
+      const float* trel = tbl_s + (p.T - 1 - qc);   // trel[k] = log2e * table[h, k - q + T - 1]
+      const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+
+      // pass A: exact row maximum of z (log2 units)
+      float m = -INFINITY;
+      for (int j = 0; j < nk; ++j) {
+        mbar_wait(&s_full[sb], sph[sb]);
+        sph[sb] ^= 1;
+        tc_fence_after();
+        const int k0 = j * AT_BK;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tm_s[sb] + lane_off + c * 32, v);
+          tmem_ld_wait();
+          const int kb = k0 + c * 32;
+          if (kb + 32 <= kl) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaf(__uint_as_float(v[i]), p.scale_log2, g * trel[kb + i]));
+          } else if (kb < kl) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kb + i < kl) m = fmaxf(m, fmaf(__uint_as_float(v[i]), p.scale_log2, g * trel[kb + i]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sb]);
+        sb ^= 1;
+      }
+      const float mm = m == -INFINITY ? 0.f : m;
+
+      // pass B: P = exp2(z - m) -> bf16 smem tile, l = row sum
+      float l = 0.f;
+      int pb = sb;
+      for (int j = 0; j < nk; ++j) {
+        mbar_wait(&s_full[sb], sph[sb]);
+        sph[sb] ^= 1;
+        mbar_wait(&p_empty[pb], pph[pb] ^ 1);
+        pph[pb] ^= 1;
+        tc_fence_after();
+        const int k0 = j * AT_BK;
+        uint8_t* pt = p_s + pb * AT_P_BYTES;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tm_s[sb] + lane_off + c * 32, v);
+          tmem_ld_wait();
+          const int kb = k0 + c * 32;
+          float e[32];
+          if (kb + 32 <= kl) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, g * trel[kb + i]) - mm);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              e[i] = kb + i < kl ? ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, g * trel[kb + i]) - mm) : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) l += e[i];
+          uint8_t* chunk = pt + (c >> 1) * 16384;
+#pragma unroll
+          for (int g16 = 0; g16 < 4; ++g16) {
+            uint4 u;
+            u.x = pack_bf16x2(e[g16 * 8 + 0], e[g16 * 8 + 1]); u.y = pack_bf16x2(e[g16 * 8 + 2], e[g16 * 8 + 3]);
+            u.z = pack_bf16x2(e[g16 * 8 + 4], e[g16 * 8 + 5]); u.w = pack_bf16x2(e[g16 * 8 + 6], e[g16 * 8 + 7]);
+            *reinterpret_cast<uint4*>(chunk + swz128(static_cast<uint32_t>(r * 128 + (c & 1) * 64 + g16 * 16))) = u;
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&p_full[pb]);
+          mbar_arrive(&s_empty[sb]);
+        }
+        sb ^= 1;
+        pb ^= 1;
+      }
+
+      // epilogue: O / l -> bf16, LSE
+      mbar_wait(o_full, oph);
+      oph ^= 1;
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld32(tm_o + lane_off, o0);
+      tmem_ld32(tm_o + lane_off + 32, o1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      if (q_ok) {
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.T + q) * (p.H * AT_D) + h * AT_D;
+#pragma unroll
+        for (int g16 = 0; g16 < 4; ++g16) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o0[g16 * 8 + 0]) * inv, __uint_as_float(o0[g16 * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o0[g16 * 8 + 2]) * inv, __uint_as_float(o0[g16 * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o0[g16 * 8 + 4]) * inv, __uint_as_float(o0[g16 * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o0[g16 * 8 + 6]) * inv, __uint_as_float(o0[g16 * 8 + 7]) * inv);
+          reinterpret_cast<uint4*>(orow)[g16] = u;
+        }
+#pragma unroll
+        for (int g16 = 0; g16 < 4; ++g16) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o1[g16 * 8 + 0]) * inv, __uint_as_float(o1[g16 * 8 + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(o1[g16 * 8 + 2]) * inv, __uint_as_float(o1[g16 * 8 + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(o1[g16 * 8 + 4]) * inv, __uint_as_float(o1[g16 * 8 + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(o1[g16 * 8 + 6]) * inv, __uint_as_float(o1[g16 * 8 + 7]) * inv);
+          reinterpret_cast<uint4*>(orow)[4 + g16] = u;
+        }
+        // natural-log LSE of the biased scores: z_log2 = z * log2e  =>  lse = (m + log2(l)) / log2e
+        p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l > 0.f ? (mm + log2f(l)) * 0.6931471805599453f : -INFINITY;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// One CTA owns a 128-key tile j of one (utterance, head) and walks the query tiles i.  Per (i, j):
+//   S  = Q_i K_j^T, dP = dO_i V_j^T                     (TMEM, 2 x 128 columns)
+//   P  = exp(z - lse),  dZ = P * (dP - delta),  dS = scale * dZ        (softmax warps, thread = query row)
+//   dV_j += P^T dO_i,  dK_j += dS^T Q_i,  dQ_i = dS K_j                (P / dS staged once in swizzled smem and consumed
+//                                                                       K-major or MN-major through the descriptors)
+// dK_j / dV_j accumulate in TMEM over i and are stored once; dQ_i partials are added to an fp32 scratch with vector
+// reductions (red.global.add.v4.f32); dgate[q] = sum_k dZ * table and the Toeplitz table gradient (sums of gate * dZ
+// along diagonals, read back from the dS tile by 4 reducer warps and accumulated in shared memory) complete the bias path.
+static constexpr int ATB_THREADS = 384;
+
+struct AttnBwdP {
+  int B, H, T, nq, nk;
+  int n_items;
+  float scale, scale_log2;
+  const float* gate;       // (B,H,T)
+  const float* table;      // (H,2T-1)
+  const int* klen;         // (B) or null
+  const float* lse;        // (B,H,T)
+  const float* delta;      // (B,H,T) = sum_d dO * O
+  __nv_bfloat16* dqkv;     // (B*T, 3*H*64): dK / dV written here
+  float* dq32;             // (B*T, H*64) fp32, zero-initialised, receives dQ partial sums
+  float* dgate;            // (B,H,T) zero-initialised (atomics)
+  float* dtable;           // (H,2T-1) zero-initialised (atomics)
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(ATB_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do, const AttnBwdP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* k_s = smem;                          // 16 KB
+  uint8_t* v_s = k_s + AT_TILE;                 // 16 KB
+  uint8_t* q_s = v_s + AT_TILE;                 // 2 x 16 KB
+  uint8_t* do_s = q_s + 2 * AT_TILE;            // 2 x 16 KB
+  uint8_t* p_s = do_s + 2 * AT_TILE;            // 32 KB
+  uint8_t* ds_s = p_s + AT_P_BYTES;             // 32 KB
+  float* tbl_s = reinterpret_cast<float*>(ds_s + AT_P_BYTES);                                  // 2T-1 (+slack)
+  float* acc_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tbl_s) + attn_table_bytes(p.T));   // 2T-1
+  float* g_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(acc_s) + attn_table_bytes(p.T));     // 128
+  uint64_t* bars = reinterpret_cast<uint64_t*>(g_s + 128);
+  uint64_t* kv_full = bars, *kv_empty = bars + 1;
+  uint64_t* qdo_full = bars + 2, *qdo_empty = bars + 4;     // [2] each
+  uint64_t* sdp_full = bars + 6, *sdp_empty = bars + 7;
+  uint64_t* pds_full = bars + 8, *pds_empty = bars + 9;
+  uint64_t* dq_full = bars + 10, *dq_empty = bars + 11;
+  uint64_t* dkv_full = bars + 12, *dkv_empty = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    if (elect_one()) { prefetch_tmap(&tmap_qkv); prefetch_tmap(&tmap_do); }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+      mbar_init(sdp_full, 1); mbar_init(sdp_empty, 4);
+      mbar_init(pds_full, 4); mbar_init(pds_empty, 5);     // MMA commit + 4 reducer warps
+      mbar_init(dq_full, 1); mbar_init(dq_empty, 4);
+      mbar_init(dkv_full, 1); mbar_init(dkv_empty, 4);
+      fence_barrier_init();
+    }
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320,
+                 tm_dq = tmem_base + 384;
+  const int nq = p.nq;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      uint32_t kvph = 0, qph[2] = {0, 0};
+      int st = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int jt = item % p.nk, h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
+        mbar_wait(kv_empty, kvph ^ 1);
+        kvph ^= 1;
+        mbar_arrive_expect_tx(kv_full, 2 * AT_TILE);
+        tma_load_4d(k_s, &tmap_qkv, kv_full, 0, jt * AT_BK, p.H + h, b);
+        tma_load_4d(v_s, &tmap_qkv, kv_full, 0, jt * AT_BK, 2 * p.H + h, b);
+        for (int i = 0; i < nq; ++i) {
+          mbar_wait(&qdo_empty[st], qph[st] ^ 1);
+          qph[st] ^= 1;
+          mbar_arrive_expect_tx(&qdo_full[st], 2 * AT_TILE);
+          tma_load_4d(q_s + st * AT_TILE, &tmap_qkv, &qdo_full[st], 0, i * AT_BQ, h, b);
+          tma_load_4d(do_s + st * AT_TILE, &tmap_do, &qdo_full[st], 0, i * AT_BQ, h, b);
+          st ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);   // S, dP: both operands K-major
+      const uint32_t idesc_mm = make_idesc_bf16(128, 64, 1, 1);    // dV, dK: both MN-major
+      const uint32_t idesc_km = make_idesc_bf16(128, 64, 0, 1);    // dQ: dS K-major, K_j MN-major
+      uint32_t kvph = 0, qph[2] = {0, 0}, sdp_ph = 0, pds_ph = 0, dq_ph = 0, dkv_ph = 0;
+      int st = 0;   // stage of the NEXT S/dP issue
+      const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s), pa = smem_u32(p_s), dsa = smem_u32(ds_s);
+      auto issue_sdp = [&]() {
+        mbar_wait(&qdo_full[st], qph[st]);
+        qph[st] ^= 1;
+        mbar_wait(sdp_empty, sdp_ph ^ 1);
+        sdp_ph ^= 1;
+        tc_fence_after();
+        const uint32_t qa = smem_u32(q_s + st * AT_TILE), doa = smem_u32(do_s + st * AT_TILE);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_f16(tm_s, desc_kmajor(qa, ks), desc_kmajor(ka, ks), idesc_kk, ks != 0);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_f16(tm_dp, desc_kmajor(doa, ks), desc_kmajor(va, ks), idesc_kk, ks != 0);
+        umma_commit(sdp_full);
+        st ^= 1;
+      };
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        mbar_wait(kv_full, kvph);
+        kvph ^= 1;
+        issue_sdp();
+        for (int i = 0; i < nq; ++i) {
+          const int cur = st ^ 1;                     // stage holding Q_i / dO_i
+          if (i + 1 < nq) issue_sdp();
+          const int stage_i = (i + 1 < nq) ? (st) : cur;   // after the extra issue `st` points back at tile i's stage
+          mbar_wait(pds_full, pds_ph);
+          pds_ph ^= 1;
+          mbar_wait(dq_empty, dq_ph ^ 1);
+          dq_ph ^= 1;
+          if (i == 0) { mbar_wait(dkv_empty, dkv_ph ^ 1); dkv_ph ^= 1; }
+          tc_fence_after();
+          const uint32_t qa = smem_u32(q_s + stage_i * AT_TILE), doa = smem_u32(do_s + stage_i * AT_TILE);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)   // dV += P^T dO_i
+            umma_f16(tm_dv, desc_mnmajor(pa, ks, 16384), desc_mnmajor(doa, ks, 8192), idesc_mm, (i | ks) != 0);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)   // dK += dS^T Q_i
+            umma_f16(tm_dk, desc_mnmajor(dsa, ks, 16384), desc_mnmajor(qa, ks, 8192), idesc_mm, (i | ks) != 0);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)   // dQ_i = dS K_j
+            umma_f16(tm_dq, make_smem_desc(dsa + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), desc_mnmajor(ka, ks, 8192),
+                     idesc_km, ks != 0);
+          umma_commit(dq_full);
+          umma_commit(pds_empty);
+          umma_commit(&qdo_empty[stage_i]);
+        }
+        umma_commit(dkv_full);
+        umma_commit(kv_empty);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ---------------------------------------------------------------- softmax / dZ warps: thread = query row
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    const int tid = threadIdx.x - 128;
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    uint32_t sdp_ph = 0, pds_ph = 0, dkv_ph = 0;
+    int cur_h = -1;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int jt = item % p.nk, h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
+      named_bar_sync(1, 128);
+      if (h != cur_h) {
+        const float* trow = p.table + static_cast<long long>(h) * (2 * p.T - 1);
+        for (int i = tid; i < 2 * p.T - 1; i += 128) tbl_s[i] = trow[i] * LOG2E;
+        cur_h = h;
+      }
+      named_bar_sync(1, 128);
+      const int kl = p.klen ? min(p.klen[b], p.T) : p.T;
+      const int k0 = jt * AT_BK;
+      const long long bh = static_cast<long long>(b) * p.H + h;
+      for (int i = 0; i < nq; ++i) {
+        const int q = i * AT_BQ + r;
+        const bool q_ok = q < p.T;
+        const int qc = q_ok ? q : p.T - 1;
+        const float g = p.gate[bh * p.T + qc];
+        const float lse2 = p.lse[bh * p.T + qc] * LOG2E;
+        const float delta = p.delta[bh * p.T + qc];
+        const float* trel = tbl_s + (p.T - 1 - qc);
+        float dg = 0.f;
+        mbar_wait(sdp_full, sdp_ph);
+        sdp_ph ^= 1;
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t sv[32], dv[32];
+          tmem_ld32(tm_s + lane_off + c * 32, sv);
+          tmem_ld32(tm_dp + lane_off + c * 32, dv);
+          tmem_ld_wait();
+          if (c == 3) {   // all TMEM reads of this tile are in registers: the next S / dP may be issued
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sdp_empty);
+          }
+          if (c == 0) {   // P / dS / gate staging of the previous tile must have been consumed
+            mbar_wait(pds_empty, pds_ph ^ 1);
+            pds_ph ^= 1;
+            g_s[r] = q_ok ? g : 0.f;
+          }
+          const int kb = k0 + c * 32;
+          float pe[32], de[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const bool ok = q_ok && (kb + e < kl);
+            const float t = trel[kb + e];
+            const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, g * t) - lse2) : 0.f;
+            const float dz = pv * (__uint_as_float(dv[e]) - delta);
+            dg = fmaf(dz, t, dg);
+            pe[e] = pv;
+            de[e] = dz * p.scale;
+          }
+          uint8_t* pc = p_s + (c >> 1) * 16384;
+          uint8_t* dc = ds_s + (c >> 1) * 16384;
+#pragma unroll
+          for (int g16 = 0; g16 < 4; ++g16) {
+            const uint32_t off = swz128(static_cast<uint32_t>(r * 128 + (c & 1) * 64 + g16 * 16));
+            uint4 u;
+            u.x = pack_bf16x2(pe[g16 * 8 + 0], pe[g16 * 8 + 1]); u.y = pack_bf16x2(pe[g16 * 8 + 2], pe[g16 * 8 + 3]);
+            u.z = pack_bf16x2(pe[g16 * 8 + 4], pe[g16 * 8 + 5]); u.w = pack_bf16x2(pe[g16 * 8 + 6], pe[g16 * 8 + 7]);
+            *reinterpret_cast<uint4*>(pc + off) = u;
+            u.x = pack_bf16x2(de[g16 * 8 + 0], de[g16 * 8 + 1]); u.y = pack_bf16x2(de[g16 * 8 + 2], de[g16 * 8 + 3]);
+            u.z = pack_bf16x2(de[g16 * 8 + 4], de[g16 * 8 + 5]); u.w = pack_bf16x2(de[g16 * 8 + 6], de[g16 * 8 + 7]);
+            *reinterpret_cast<uint4*>(dc + off) = u;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pds_full);
+        if (q_ok && dg != 0.f) atomicAdd(p.dgate + bh * p.T + q, dg * 0.6931471805599453f);   // table was scaled by log2e
+      }
+      // item epilogue: dK_j, dV_j (rows = keys of this tile) -> bf16 into dqkv
+      mbar_wait(dkv_full, dkv_ph);
+      dkv_ph ^= 1;
+      tc_fence_after();
+      const int key = k0 + r;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        uint32_t a0[32], a1[32];
+        const uint32_t src = which == 0 ? tm_dk : tm_dv;
+        tmem_ld32(src + lane_off, a0);
+        tmem_ld32(src + lane_off + 32, a1);
+        tmem_ld_wait();
+        if (key < p.T) {
+          __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * p.T + key) * (3 * p.H * AT_D) + (which == 0 ? 1 : 2) * p.H * AT_D +
+                               h * AT_D;
+#pragma unroll
+          for (int g16 = 0; g16 < 4; ++g16) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(a0[g16 * 8 + 0]), __uint_as_float(a0[g16 * 8 + 1]));
+            u.y = pack_bf16x2(__uint_as_float(a0[g16 * 8 + 2]), __uint_as_float(a0[g16 * 8 + 3]));
+            u.z = pack_bf16x2(__uint_as_float(a0[g16 * 8 + 4]), __uint_as_float(a0[g16 * 8 + 5]));
+            u.w = pack_bf16x2(__uint_as_float(a0[g16 * 8 + 6]), __uint_as_float(a0[g16 * 8 + 7]));
+            reinterpret_cast<uint4*>(dst)[g16] = u;
+            u.x = pack_bf16x2(__uint_as_float(a1[g16 * 8 + 0]), __uint_as_float(a1[g16 * 8 + 1]));
+            u.y = pack_bf16x2(__uint_as_float(a1[g16 * 8 + 2]), __uint_as_float(a1[g16 * 8 + 3]));
+            u.z = pack_bf16x2(__uint_as_float(a1[g16 * 8 + 4]), __uint_as_float(a1[g16 * 8 + 5]));
+            u.w = pack_bf16x2(__uint_as_float(a1[g16 * 8 + 6]), __uint_as_float(a1[g16 * 8 + 7]));
+            reinterpret_cast<uint4*>(dst)[4 + g16] = u;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dkv_empty);
+    }
+  } else if (warp >= 8) {
+    // ---------------------------------------------------------------- reducer warps: table-gradient diagonals + dQ drain
+    const int wq = warp & 3;
+    const int t = wq * 32 + lane;                 // 0..127
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    uint32_t pds_ph = 0, dq_ph = 0;
+    const float inv_scale = 1.f / p.scale;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int jt = item % p.nk, h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
+      for (int i = t; i < 2 * p.T - 1; i += 128) acc_s[i] = 0.f;
+      named_bar_sync(2, 128);
+      for (int i = 0; i < nq; ++i) {
+        mbar_wait(pds_full, pds_ph);
+        pds_ph ^= 1;
+        // local diagonals dl = kk - qq: this thread owns dl = t - 127 (<= 0) and dl = t + 1 (>= 1, only t <= 126)
+        const int base = (jt - i) * 128 + p.T - 1;
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          const int dl = which == 0 ? t - 127 : t + 1;
+          if (dl > 127) continue;
+          const int gidx = base + dl;
+          if (gidx < 0 || gidx > 2 * p.T - 2) continue;
+          const int q_lo = dl < 0 ? -dl : 0, q_hi = dl > 0 ? 127 - dl : 127;
+          float sum = 0.f;
+          for (int qq = q_lo; qq <= q_hi; ++qq) {
+            const int kk = qq + dl;
+            const uint32_t off = swz128(static_cast<uint32_t>(qq * 128 + (kk & 63) * 2));
+            const float dsv = bf2f(*reinterpret_cast<const __nv_bfloat16*>(ds_s + (kk >> 6) * 16384 + off));
+            sum = fmaf(dsv, g_s[qq], sum);
+          }
+          acc_s[gidx] += sum;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pds_empty);
+        // dQ_i partial: TMEM -> fp32 vector reductions into the scratch
+        mbar_wait(dq_full, dq_ph);
+        dq_ph ^= 1;
+        tc_fence_after();
+        uint32_t a0[32], a1[32];
+        tmem_ld32(tm_dq + lane_off, a0);
+        tmem_ld32(tm_dq + lane_off + 32, a1);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_empty);
+        const int q = i * AT_BQ + t;
+        if (q < p.T) {
+          float* dst = p.dq32 + (static_cast<long long>(b) * p.T + q) * (p.H * AT_D) + h * AT_D;
+#pragma unroll
+          for (int v4 = 0; v4 < 8; ++v4)
+            red_add_v4(dst + v4 * 4, __uint_as_float(a0[v4 * 4]), __uint_as_float(a0[v4 * 4 + 1]), __uint_as_float(a0[v4 * 4 + 2]),
+                       __uint_as_float(a0[v4 * 4 + 3]));
+#pragma unroll
+          for (int v4 = 0; v4 < 8; ++v4)
+            red_add_v4(dst + 32 + v4 * 4, __uint_as_float(a1[v4 * 4]), __uint_as_float(a1[v4 * 4 + 1]),
+                       __uint_as_float(a1[v4 * 4 + 2]), __uint_as_float(a1[v4 * 4 + 3]));
+        }
+      }
+      named_bar_sync(2, 128);
+      float* dt = p.dtable + static_cast<long long>(h) * (2 * p.T - 1);
+      for (int i = t; i < 2 * p.T - 1; i += 128) {
+        const float v = acc_s[i];
+        if (v != 0.f) atomicAdd(dt + i, v * inv_scale);
+      }
+      named_bar_sync(2, 128);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]  (the softmax-backward row term), one thread per (b,q,h)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, int B, int T, int H,
+                                  float* __restrict__ delta) {
+  const long long n = static_cast<long long>(B) * T * H;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int h = static_cast<int>(i % H);
+    const long long bq = i / H;
+    const uint4* a = reinterpret_cast<const uint4*>(o + bq * H * AT_D + h * AT_D);
+    const uint4* d = reinterpret_cast<const uint4*>(dout + bq * H * AT_D + h * AT_D);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 x = a[c], y = d[c];
+      float2 u, v;
+      u = unpack_bf16x2(x.x); v = unpack_bf16x2(y.x); s += u.x * v.x + u.y * v.y;
+      u = unpack_bf16x2(x.y); v = unpack_bf16x2(y.y); s += u.x * v.x + u.y * v.y;
+      u = unpack_bf16x2(x.z); v = unpack_bf16x2(y.z); s += u.x * v.x + u.y * v.y;
+      u = unpack_bf16x2(x.w); v = unpack_bf16x2(y.w); s += u.x * v.x + u.y * v.y;
+    }
+    const int b = static_cast<int>(bq / T), q = static_cast<int>(bq % T);
+    delta[(static_cast<long long>(b) * H + h) * T + q] = s;
+  }
+}
+
+// y[r][0..cols) (bf16, row stride ldy) = x[r][0..cols) (fp32, row stride ldx): dQ scratch -> the q block of dqkv
+__global__ void cast2d_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy, long long rows,
+                              int cols8) {
+  const long long n = rows * cols8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols8;
+    const int c = static_cast<int>(i % cols8) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(x + r * ldx + c);
+    const float4 b = *reinterpret_cast<const float4*>(x + r * ldx + c + 4);
+    uint4 u;
+    u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w); u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
+    *reinterpret_cast<uint4*>(y + r * ldy + c) = u;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn2 attn_encode_fn() {
+  static EncodeTiledFn2 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn2>(ptr);
+  }
+  return fn;
+}
+
+// (B*T, n_slices*64) bf16 matrix viewed as [b][slice][t][64]: box = 128 rows x 64 columns of one (b, slice);
+// rows >= T are out of bounds of dimension 1 and therefore zero-filled (never the next utterance's rows).
+static int encode_heads_map(CUtensorMap* map, const void* base, int B, int T, int n_slices, long long ld, const char* what) {
+  EncodeTiledFn2 fn = attn_encode_fn();
+  if (!fn) return set_error(MTASR_ERR_DRIVER, "attention: cuTensorMapEncodeTiled unavailable");
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0 || (ld * 2) % 16 != 0)
+    return set_error(MTASR_ERR_INVALID_ARG, "attention: %s must be 16-byte aligned with a 16-byte multiple row stride", what);
+  cuuint64_t dims[4] = {64, static_cast<cuuint64_t>(T), static_cast<cuuint64_t>(n_slices), static_cast<cuuint64_t>(B)};
+  cuuint64_t str[3] = {static_cast<cuuint64_t>(ld) * 2, 128, static_cast<cuuint64_t>(ld) * 2 * T};
+  cuuint32_t box[4] = {64, 128, 1, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, str, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(MTASR_ERR_DRIVER, "attention: cuTensorMapEncodeTiled(%s) failed with %d", what, (int)r);
+  return 0;
+}
+
+}  // namespace mtasr
+
+using namespace mtasr;
+
+extern "C" int mtasr_attn_fwd(const void* qkv, const float* gate, const float* table, const int32_t* klen, int32_t B, int32_t H,
+                              int32_t T, float scale, void* out, float* lse, void* stream) {
+  MTASR_CHECK_ARG(qkv && gate && table && out && lse && B > 0 && H > 0 && T > 0, "attn_fwd: bad arguments");
+  MTASR_CHECK_ARG(T <= 8192, "attn_fwd: T=%d too long for the shared-memory bias table", T);
+  CUtensorMap map;
+  if (int rc = encode_heads_map(&map, qkv, B, T, 3 * H, 3LL * H * AT_D, "qkv")) return rc;
+  AttnFwdP p;
+  p.B = B; p.H = H; p.T = T;
+  p.nq = (T + AT_BQ - 1) / AT_BQ;
+  p.nk = (T + AT_BK - 1) / AT_BK;
+  p.n_items = p.nq * H * B;
+  p.scale_log2 = scale * LOG2E;
+  p.gate = gate; p.table = table; p.klen = klen;
+  p.out = reinterpret_cast<__nv_bfloat16*>(out);
+  p.lse = lse;
+  const int smem = AT_TILE + AT_KV_SLOTS * AT_TILE + 2 * AT_P_BYTES + attn_table_bytes(T) + 256;
+  MTASR_CHECK_ARG(smem <= 232448, "attn_fwd: T=%d needs %d bytes of shared memory", T, smem);
+  if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return set_error(MTASR_ERR_LAUNCH, "attn_fwd: cannot set the shared-memory attribute");
+  const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  attn_fwd_kernel<<<grid, AT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map, p);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("attn_fwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* gate,
+                              const float* table, const int32_t* klen, int32_t B, int32_t H, int32_t T, float scale, void* dqkv,
+                              float* dq32, float* delta, float* dgate, float* dtable, void* stream) {
+  MTASR_CHECK_ARG(qkv && out && dout && lse && gate && table && dqkv && dq32 && delta && dgate && dtable && B > 0 && H > 0 && T > 0,
+                  "attn_bwd: bad arguments");
+  MTASR_CHECK_ARG(T <= 4096, "attn_bwd: T=%d too long for the shared-memory bias tables", T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n = static_cast<long long>(B) * T * H;
+  long long g = (n + 255) / 256;
+  if (g > num_sms() * 8) g = num_sms() * 8;
+  attn_delta_kernel<<<static_cast<unsigned>(g), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(out),
+                                                                reinterpret_cast<const __nv_bfloat16*>(dout), B, T, H, delta);
+  MTASR_COUNT_LAUNCH();
+  CUtensorMap mq, mdo;
+  if (int rc = encode_heads_map(&mq, qkv, B, T, 3 * H, 3LL * H * AT_D, "qkv")) return rc;
+  if (int rc = encode_heads_map(&mdo, dout, B, T, H, 1LL * H * AT_D, "dout")) return rc;
+  AttnBwdP p;
+  p.B = B; p.H = H; p.T = T;
+  p.nq = (T + AT_BQ - 1) / AT_BQ;
+  p.nk = (T + AT_BK - 1) / AT_BK;
+  p.n_items = p.nk * H * B;
+  p.scale = scale;
+  p.scale_log2 = scale * LOG2E;
+  p.gate = gate; p.table = table; p.klen = klen; p.lse = lse; p.delta = delta;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.dq32 = dq32; p.dgate = dgate; p.dtable = dtable;
+  const int smem = 6 * AT_TILE + 2 * AT_P_BYTES + 2 * attn_table_bytes(T) + 128 * 4 + 256;
+  MTASR_CHECK_ARG(smem <= 232448, "attn_bwd: T=%d needs %d bytes of shared memory", T, smem);
+  if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    return set_error(MTASR_ERR_LAUNCH, "attn_bwd: cannot set the shared-memory attribute");
+  const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  attn_bwd_kernel<<<grid, ATB_THREADS, smem, st>>>(mq, mdo, p);
+  MTASR_COUNT_LAUNCH();
+  // dQ scratch (fp32) -> q block of dqkv (bf16)
+  const long long rows = static_cast<long long>(B) * T;
+  const int cols8 = H * AT_D / 8;
+  long long g2 = (rows * cols8 + 255) / 256;
+  if (g2 > num_sms() * 8) g2 = num_sms() * 8;
+  cast2d_kernel<<<static_cast<unsigned>(g2), 256, 0, st>>>(dq32, 1LL * H * AT_D, reinterpret_cast<__nv_bfloat16*>(dqkv),
+                                                           3LL * H * AT_D, rows, cols8);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("attn_bwd");
+  return MTASR_OK;
+}

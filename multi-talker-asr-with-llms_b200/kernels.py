@@ -240,6 +240,29 @@ def relpos_gate_bwd(x, wab, bab, cst, dgate, B, T, H):
     return dx, dwab, dbab, dcst
 
 
+def attn_fwd(qkv, gate, table, klen, B, H, T, scale):
+    """Fused attention forward -> (out (B*T, H*64) bf16, lse (B,H,T) f32)."""
+    out = torch.empty(B * T, H * 64, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, T, device=qkv.device, dtype=torch.float32)
+    check(_lib.load().mtasr_attn_fwd(_p(qkv), _p(gate), _p(table), _p(klen), B, H, T, scale, _p(out), _p(lse), _stream()),
+          "mtasr_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(qkv, out, dout, lse, gate, table, klen, B, H, T, scale):
+    """Fused attention backward -> (dqkv (B*T, 3*H*64) bf16, dgate (B,H,T) f32, dtable (H,2T-1) f32)."""
+    dev = qkv.device
+    D = H * 64
+    dqkv = torch.empty(B * T, 3 * D, device=dev, dtype=torch.bfloat16)
+    dq32 = torch.zeros(B * T, D, device=dev, dtype=torch.float32)
+    delta = torch.empty(B, H, T, device=dev, dtype=torch.float32)
+    dgate = torch.zeros(B, H, T, device=dev, dtype=torch.float32)
+    dtable = torch.zeros(H, 2 * T - 1, device=dev, dtype=torch.float32)
+    check(_lib.load().mtasr_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(gate), _p(table), _p(klen), B, H, T, scale, _p(dqkv),
+                                     _p(dq32), _p(delta), _p(dgate), _p(dtable), _stream()), "mtasr_attn_bwd")
+    return dqkv, dgate, dtable
+
+
 def attn_softmax_fwd(S, gate, table, klen, B, H, T, Tp, scale):
     P = torch.empty(B, H, T, Tp, device=S.device, dtype=torch.bfloat16)
     check(_lib.load().mtasr_attn_softmax_fwd(_p(S), _p(gate), _p(table), _p(klen), B, H, T, Tp, scale, _p(P), _stream()),

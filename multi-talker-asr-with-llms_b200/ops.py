@@ -6,6 +6,7 @@ trainer back-propagates K+1 times per step, ref:src/trainer_seq2seq.py:1071-1141
 ref:utils/unfreeze_utils.py:39-96).  Parameters stay ordinary fp32 nn.Parameters; bf16 operand copies are made
 on the fly and cached per parameter version.
 """
+import os
 import weakref
 from typing import Optional
 
@@ -18,6 +19,7 @@ BF = torch.bfloat16
 F32 = torch.float32
 
 _bf16_cache = {}
+_UNFUSED_ATTN = os.environ.get("MTASR_UNFUSED_ATTN", "") not in ("", "0")   # debugging / A-B switch: materialise S and P
 
 
 def bf16_of(p: torch.Tensor) -> torch.Tensor:
@@ -199,27 +201,35 @@ class AttentionFn(Function):
         bqkv = torch.cat([bq.detach().float(), bk.detach().float(), bv.detach().float()], 0)
         wob = bf16_of(wo)
         qkv = K.linear_fwd(hb, wqkv, bqkv)                                   # (B*T, 3D) bf16: [q | k | v], head-major
-        Tp = (T + 7) // 8 * 8
-        S = torch.empty(B, H, T, Tp, device=h.device, dtype=F32)
-        K.gemm(K.Operand(qkv, 3 * D, sb0=d, sb1=T * 3 * D, rows=T), K.Operand(qkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=D, rows=T),
-               T, T, d, K.Out(S, Tp, sb0=T * Tp, sb1=H * T * Tp), batch=(H, B))
         scale = float(d) ** -0.5
         gate = gate.detach().contiguous().float()
         table = table.detach().contiguous().float()
-        P = K.attn_softmax_fwd(S, gate, table, klen, B, H, T, Tp, scale)
-        del S
-        O = torch.empty(B * T, D, device=h.device, dtype=BF)
-        K.gemm(K.Operand(P, Tp, sb0=T * Tp, sb1=H * T * Tp), K.Operand(qkv, 3 * D, major=1, sb0=d, sb1=T * 3 * D, offset=2 * D, rows=T),
-               T, d, T, K.Out(O, D, sb0=d, sb1=T * D), batch=(H, B))
+        fused = d == 64 and not _UNFUSED_ATTN
+        if fused:
+            O, lse = K.attn_fwd(qkv, gate, table, klen, B, H, T, scale)      # S / P tiles never leave TMEM / smem
+            P = None
+            Tp = 0
+        else:
+            Tp = (T + 7) // 8 * 8
+            S = torch.empty(B, H, T, Tp, device=h.device, dtype=F32)
+            K.gemm(K.Operand(qkv, 3 * D, sb0=d, sb1=T * 3 * D, rows=T), K.Operand(qkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=D, rows=T),
+                   T, T, d, K.Out(S, Tp, sb0=T * Tp, sb1=H * T * Tp), batch=(H, B))
+            P = K.attn_softmax_fwd(S, gate, table, klen, B, H, T, Tp, scale)
+            del S
+            lse = None
+            O = torch.empty(B * T, D, device=h.device, dtype=BF)
+            K.gemm(K.Operand(P, Tp, sb0=T * Tp, sb1=H * T * Tp), K.Operand(qkv, 3 * D, major=1, sb0=d, sb1=T * 3 * D, offset=2 * D, rows=T),
+                   T, d, T, K.Out(O, D, sb0=d, sb1=T * D), batch=(H, B))
         y = K.linear_fwd(O, wob, bo.detach().float(), residual=_flat2d(res), out_dtype=F32)
         ctx.dims = (B, T, D, H, Tp, scale)
         ctx.h_dtype = h.dtype
-        ctx.save_for_backward(hb, qkv, P, O, wqkv, wob, gate, table)
+        ctx.fused = fused
+        ctx.save_for_backward(hb, qkv, P if P is not None else lse, O, wqkv, wob, gate, table, klen)
         return y.view(B, T, D)
 
     @staticmethod
     def backward(ctx, dy):
-        hb, qkv, P, O, wqkv, wob, gate, table = ctx.saved_tensors
+        hb, qkv, P, O, wqkv, wob, gate, table, klen = ctx.saved_tensors
         B, T, D, H, Tp, scale = ctx.dims
         d = D // H
         need = ctx.needs_input_grad
@@ -227,20 +237,23 @@ class AttentionFn(Function):
         dO = K.linear_dgrad(dyb, wob)                                         # (B*T, D) bf16
         dwo = K.linear_wgrad(dyb, O) if need[8] else None
         dbo = K.colsum(dyb) if need[9] else None
-        dP = torch.empty(B, H, T, Tp, device=dy.device, dtype=F32)
-        K.gemm(K.Operand(dO, D, sb0=d, sb1=T * D, rows=T), K.Operand(qkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=2 * D, rows=T),
-               T, T, d, K.Out(dP, Tp, sb0=T * Tp, sb1=H * T * Tp), batch=(H, B))
-        dqkv = torch.empty(B * T, 3 * D, device=dy.device, dtype=BF)
-        # dV = P^T dO
-        K.gemm(K.Operand(P, Tp, major=1, sb0=T * Tp, sb1=H * T * Tp, rows=T), K.Operand(dO, D, major=1, sb0=d, sb1=T * D, rows=T),
-               T, d, T, K.Out(dqkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=2 * D), batch=(H, B))
-        dS, dgate, dtable = K.attn_softmax_bwd(P, dP, gate, table, B, H, T, Tp, scale)
-        del dP
-        # dQ = dS K ; dK = dS^T Q   (dS already carries the 1/sqrt(d) factor)
-        K.gemm(K.Operand(dS, Tp, sb0=T * Tp, sb1=H * T * Tp), K.Operand(qkv, 3 * D, major=1, sb0=d, sb1=T * 3 * D, offset=D, rows=T),
-               T, d, T, K.Out(dqkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=0), batch=(H, B))
-        K.gemm(K.Operand(dS, Tp, major=1, sb0=T * Tp, sb1=H * T * Tp, rows=T), K.Operand(qkv, 3 * D, major=1, sb0=d, sb1=T * 3 * D, offset=0, rows=T),
-               T, d, T, K.Out(dqkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=D), batch=(H, B))
+        if ctx.fused:
+            dqkv, dgate, dtable = K.attn_bwd(qkv, O, dO, P, gate, table, klen, B, H, T, scale)   # P slot holds the row LSE
+        else:
+            dP = torch.empty(B, H, T, Tp, device=dy.device, dtype=F32)
+            K.gemm(K.Operand(dO, D, sb0=d, sb1=T * D, rows=T), K.Operand(qkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=2 * D, rows=T),
+                   T, T, d, K.Out(dP, Tp, sb0=T * Tp, sb1=H * T * Tp), batch=(H, B))
+            dqkv = torch.empty(B * T, 3 * D, device=dy.device, dtype=BF)
+            # dV = P^T dO
+            K.gemm(K.Operand(P, Tp, major=1, sb0=T * Tp, sb1=H * T * Tp, rows=T), K.Operand(dO, D, major=1, sb0=d, sb1=T * D, rows=T),
+                   T, d, T, K.Out(dqkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=2 * D), batch=(H, B))
+            dS, dgate, dtable = K.attn_softmax_bwd(P, dP, gate, table, B, H, T, Tp, scale)
+            del dP
+            # dQ = dS K ; dK = dS^T Q   (dS already carries the 1/sqrt(d) factor)
+            K.gemm(K.Operand(dS, Tp, sb0=T * Tp, sb1=H * T * Tp), K.Operand(qkv, 3 * D, major=1, sb0=d, sb1=T * 3 * D, offset=D, rows=T),
+                   T, d, T, K.Out(dqkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=0), batch=(H, B))
+            K.gemm(K.Operand(dS, Tp, major=1, sb0=T * Tp, sb1=H * T * Tp, rows=T), K.Operand(qkv, 3 * D, major=1, sb0=d, sb1=T * 3 * D, offset=0, rows=T),
+                   T, d, T, K.Out(dqkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=D), batch=(H, B))
         dh = K.linear_dgrad(dqkv, wqkv, out_dtype=ctx.h_dtype).view(B, T, D) if need[0] else None
         dwq = dwk = dwv = dbq = dbk = dbv = None
         if need[2] or need[4] or need[6]:
