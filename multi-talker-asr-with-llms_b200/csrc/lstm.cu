@@ -11,6 +11,8 @@
 // Backward (BPTT) mirrors it: CTA j owns dh_{t-1}[:, 8j:8j+8], streams dgates_t (B x 4Hs bf16) through smem in
 // four Hs-wide chunks against its resident W_hh^T slice, split-K over the 8 warps with an smem reduction.
 // dW / dx / db are batched GEMMs / column sums over the saved dgates afterwards.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mtasr {
@@ -277,6 +279,316 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_bwd_kernel(const LstmBwdP p)
   }
 }
 
+// ------------------------------------------------------------------------------------------------ batch-sliced variant
+// The utterances of a batch are independent, so the recurrence is cut into slices of RB = 8 utterances; a GROUP of G CTAs
+// owns one slice and splits the hidden units (U = Hs / G per CTA, e.g. 28 of 896 with G = 32).  Compared with one
+// group over the whole batch this divides the per-step all-gather (h_{t-1}, or dgates_{t+1} in the backward) by the
+// number of slices and shrinks every barrier to G arrivals.  The per-step product is computed "transposed":
+//   gates^T[4U, 8] = W_slice[4U, Hs] . h^T[Hs, 8]            (mma.sync m16n8k16: weights are the M operand, the 8
+//   dh^T[U, 8]     = W_hh^T_slice[U, 4Hs] . dgates^T[4Hs, 8]   utterances exactly fill N -- no padded batch rows)
+// with K split over the 8 warps (independent accumulators per warp -> no long dependent MMA chain) and a shared-memory
+// reduction of the 8 partials.
+static constexpr int RB = 8;
+
+// Arrive on the group counter after this CTA's exchange stores: bar.sync orders every thread's stores before thread 0,
+// whose single gpu-scope fence (cumulative) then publishes them -- one fence per CTA instead of one per thread, and it
+// only has to wait for the few exchange stores issued so far (the bulky per-step saves are stored AFTER the arrive).
+__device__ __forceinline__ void group_arrive(unsigned int* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+  }
+}
+
+struct LstmBsP {
+  const float* xg;            // (B,T,4Hs)   fwd
+  const __nv_bfloat16* whh;   // (4Hs, ldw)
+  __nv_bfloat16* h_bf16;      // (B,T,Hs)    fwd out / exchange buffer
+  float* h_f32;               // optional
+  float* c_all;               // (B,T,Hs)
+  float* gates;               // (B,T,4Hs)
+  const float* dh_out;        // (B,T,Hs)    bwd
+  __nv_bfloat16* dgates;      // (B,T,4Hs)   bwd out / exchange buffer
+  unsigned int* bar;          // [S] group counters
+  int B, T, Hs, ldw, G, U;
+};
+
+__global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_bs_kernel(const LstmBsP p) {
+  extern __shared__ __align__(16) uint8_t lsm[];
+  const int Hs = p.Hs, T = p.T, U = p.U, G = p.G;
+  const int rs = Hs + LPAD;
+  const int M = 4 * U, m_tiles = (M + 15) / 16;
+  __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(lsm);          // [4U][rs]
+  __nv_bfloat16* Hsm = Ws + M * rs;                                   // [8][rs]
+  float* P = reinterpret_cast<float*>(Hsm + RB * rs);                 // [4 K-quarters][m_tiles*16][8]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s = blockIdx.x / G, j = blockIdx.x % G;
+  const int b0 = s * RB, nb = min(RB, p.B - b0);
+  const int u0 = j * U;
+  unsigned int* bar = p.bar + s;
+
+  for (int i = tid; i < M * (Hs / 8); i += LTHREADS) {
+    const int lc = i / (Hs / 8), kc = i % (Hs / 8);
+    const int gcol = (lc / U) * Hs + u0 + (lc % U);
+    *reinterpret_cast<uint4*>(Ws + lc * rs + kc * 8) =
+        *reinterpret_cast<const uint4*>(p.whh + static_cast<long long>(gcol) * p.ldw + kc * 8);
+  }
+  for (int i = tid; i < RB * rs; i += LTHREADS) Hsm[i] = f2bf(0.f);
+  __syncthreads();
+
+  // warp (kq, mh): K quarter kq = warp & 3, M-tile half mh = warp >> 2 (<= 4 independent accumulators per warp)
+  const int ksteps = Hs / 16;
+  const int kper = (ksteps + 3) / 4;
+  const int kq = warp & 3, mh = warp >> 2;
+  const int k_lo = kq * kper, k_hi = min(ksteps, k_lo + kper);
+  const int mt_half = (m_tiles + 1) / 2;
+  const int mt_lo = mh * mt_half;
+  const int pr = tid;                       // (b, u) pair owned by this thread
+  const bool has_pair = pr < nb * U;
+  const int pb = pr / U, pu = pr % U;
+  float creg = 0.f;
+  const int prow = m_tiles * 16;
+  float sv_h = 0.f, sv_c = 0.f, sv_i = 0.f, sv_f = 0.f, sv_g = 0.f, sv_o = 0.f;
+
+  for (int t = 0; t < T; ++t) {
+    float xv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (has_pair) {
+      const float* xr = p.xg + (static_cast<long long>(b0 + pb) * T + t) * 4 * Hs + u0 + pu;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) xv[g] = xr[g * Hs];
+    }
+    float gsum[4] = {0.f, 0.f, 0.f, 0.f};
+    if (t > 0) {
+      grid_wait(bar, static_cast<unsigned>(G) * static_cast<unsigned>(t));
+      for (int i = tid; i < nb * (Hs / 8); i += LTHREADS) {
+        const int b = i / (Hs / 8), kc = i % (Hs / 8);
+        *reinterpret_cast<uint4*>(Hsm + b * rs + kc * 8) =
+            ldcg16(p.h_bf16 + (static_cast<long long>(b0 + b) * T + (t - 1)) * Hs + kc * 8);
+      }
+      __syncthreads();
+      float acc[4][4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[mi][q] = 0.f;
+      for (int ks = k_lo; ks < k_hi; ++ks) {
+        const int k0 = ks * 16;
+        uint32_t hb0, hb1;
+        ldsm_x2(smem_addr(Hsm + (lane & 7) * rs + k0 + ((lane >> 3) & 1) * 8), hb0, hb1);
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi) {
+          const int mt = mt_lo + mi;
+          if (mi < mt_half && mt < m_tiles) {
+            const int row = min(mt * 16 + (lane & 15), M - 1);
+            uint32_t a0, a1, a2, a3;
+            ldsm_x4(smem_addr(Ws + row * rs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+            mma16816(acc[mi], a0, a1, a2, a3, hb0, hb1);
+          }
+        }
+      }
+      float* Pw = P + kq * prow * 8;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int mt = mt_lo + mi;
+        if (mi < mt_half && mt < m_tiles) {
+          const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
+          *reinterpret_cast<float2*>(Pw + r * 8 + c) = make_float2(acc[mi][0], acc[mi][1]);
+          *reinterpret_cast<float2*>(Pw + (r + 8) * 8 + c) = make_float2(acc[mi][2], acc[mi][3]);
+        }
+      }
+      __syncthreads();
+      if (has_pair) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int lc = g * U + pu;
+          float a = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) a += P[(w * prow + lc) * 8 + pb];
+          gsum[g] = a;
+        }
+      }
+    }
+    if (has_pair) {
+      const float ai = xv[0] + gsum[0], af = xv[1] + gsum[1], ag = xv[2] + gsum[2], ao = xv[3] + gsum[3];
+      const float ig = 1.f / (1.f + expf(-ai)), fg = 1.f / (1.f + expf(-af));
+      const float gg = tanhf(ag), og = 1.f / (1.f + expf(-ao));
+      const float c = fg * creg + ig * gg;
+      creg = c;
+      const float h = og * tanhf(c);
+      const long long o = (static_cast<long long>(b0 + pb) * T + t) * Hs + u0 + pu;
+      p.h_bf16[o] = f2bf(h);                       // the exchange store: published by the arrive below
+      sv_h = h; sv_c = c; sv_i = ig; sv_f = fg; sv_g = gg; sv_o = og;
+    }
+    if (t + 1 < T) group_arrive(bar);
+    if (has_pair) {                                // saves for the backward: off the critical path
+      const long long o = (static_cast<long long>(b0 + pb) * T + t) * Hs + u0 + pu;
+      if (p.h_f32) p.h_f32[o] = sv_h;
+      p.c_all[o] = sv_c;
+      float* gr = p.gates + (static_cast<long long>(b0 + pb) * T + t) * 4 * Hs + u0 + pu;
+      gr[0] = sv_i; gr[Hs] = sv_f; gr[2 * Hs] = sv_g; gr[3 * Hs] = sv_o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(LTHREADS, 1) lstm_bwd_bs_kernel(const LstmBsP p) {
+  extern __shared__ __align__(16) uint8_t lsm[];
+  const int Hs = p.Hs, T = p.T, U = p.U, G = p.G;
+  const int K4 = 4 * Hs;
+  const int wrs = K4 + LPAD, ars = Hs + LPAD;
+  const int m_tiles = (U + 15) / 16;        // <= 2
+  __nv_bfloat16* Wt = reinterpret_cast<__nv_bfloat16*>(lsm);        // [U][wrs]: Wt[u][col] = whh[col][u0+u]
+  __nv_bfloat16* Asm = Wt + U * wrs;                                // [8][ars] one Hs-wide chunk of the dgates slice
+  float* P = reinterpret_cast<float*>(Asm + RB * ars);              // [8 warps][m_tiles*16][8]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int s = blockIdx.x / G, j = blockIdx.x % G;
+  const int b0 = s * RB, nb = min(RB, p.B - b0);
+  const int u0 = j * U;
+  unsigned int* bar = p.bar + s;
+
+  for (int i = tid; i < U * K4; i += LTHREADS) {
+    const int u = i % U, col = i / U;
+    Wt[u * wrs + col] = p.whh[static_cast<long long>(col) * p.ldw + u0 + u];
+  }
+  for (int i = tid; i < RB * ars; i += LTHREADS) Asm[i] = f2bf(0.f);
+  __syncthreads();
+
+  const int ksteps = Hs / 16;
+  const int kper = (ksteps + 7) / 8;
+  const int k_lo = warp * kper, k_hi = min(ksteps, k_lo + kper);
+  const int pr = tid;
+  const bool has_pair = pr < nb * U;
+  const int pb = pr / U, pu = pr % U;
+  const int prow = m_tiles * 16;
+  float dc_carry = 0.f;
+  unsigned int step = 0;
+
+  const int nload = nb * (Hs / 8);               // 16-byte pieces of one Hs-wide chunk of the dgates slice
+  for (int t = T - 1; t >= 0; --t) {
+    float dh_rec = 0.f;
+    // this step's saved activations / upstream gradient: issued before the barrier wait so HBM latency is hidden
+    float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cv = 0.f, cprev = 0.f, dho = 0.f;
+    if (has_pair) {
+      const long long o = (static_cast<long long>(b0 + pb) * T + t) * Hs + u0 + pu;
+      const float* gr = p.gates + (static_cast<long long>(b0 + pb) * T + t) * K4 + u0 + pu;
+      ig = gr[0]; fg = gr[Hs]; gg = gr[2 * Hs]; og = gr[3 * Hs];
+      cv = p.c_all[o];
+      cprev = t > 0 ? p.c_all[o - Hs] : 0.f;
+      dho = p.dh_out[o];
+    }
+    if (t < T - 1) {
+      ++step;
+      grid_wait(bar, static_cast<unsigned>(G) * step);
+      // all four chunks of dgates_{t+1} are requested at once (registers) so the L2 latency is paid once per step
+      uint4 stage[4][4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int i = tid + v * LTHREADS;
+          if (i < nload) {
+            const int b = i / (Hs / 8), kc = i % (Hs / 8);
+            stage[g][v] = ldcg16(p.dgates + (static_cast<long long>(b0 + b) * T + (t + 1)) * K4 + g * Hs + kc * 8);
+          }
+        }
+      float acc[2][2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[a][b][q] = 0.f;
+      for (int g = 0; g < 4; ++g) {
+        __syncthreads();   // previous chunk fully consumed
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int i = tid + v * LTHREADS;
+          if (i < nload) {
+            const int b = i / (Hs / 8), kc = i % (Hs / 8);
+            *reinterpret_cast<uint4*>(Asm + b * ars + kc * 8) = stage[g][v];
+          }
+        }
+        __syncthreads();
+        for (int ks = k_lo; ks < k_hi; ks += 2) {
+#pragma unroll
+          for (int par = 0; par < 2; ++par) {     // two independent accumulator sets halve the dependent MMA chain
+            if (ks + par < k_hi) {
+              const int k0 = (ks + par) * 16;
+              uint32_t d0, d1;
+              ldsm_x2(smem_addr(Asm + (lane & 7) * ars + k0 + ((lane >> 3) & 1) * 8), d0, d1);
+#pragma unroll
+              for (int mt = 0; mt < 2; ++mt) {
+                if (mt < m_tiles) {
+                  const int row = min(mt * 16 + (lane & 15), U - 1);
+                  uint32_t a0, a1, a2, a3;
+                  ldsm_x4(smem_addr(Wt + row * wrs + g * Hs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+                  mma16816(acc[mt][par], a0, a1, a2, a3, d0, d1);
+                }
+              }
+            }
+          }
+        }
+      }
+      float* Pw = P + warp * prow * 8;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt < m_tiles) {
+          const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
+          *reinterpret_cast<float2*>(Pw + r * 8 + c) = make_float2(acc[mt][0][0] + acc[mt][1][0], acc[mt][0][1] + acc[mt][1][1]);
+          *reinterpret_cast<float2*>(Pw + (r + 8) * 8 + c) =
+              make_float2(acc[mt][0][2] + acc[mt][1][2], acc[mt][0][3] + acc[mt][1][3]);
+        }
+      }
+      __syncthreads();
+      if (has_pair) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) dh_rec += P[(w * prow + pu) * 8 + pb];
+      }
+    }
+    if (has_pair) {
+      const float dh = dho + dh_rec;
+      const float tc = tanhf(cv);
+      const float dc = dh * og * (1.f - tc * tc) + dc_carry;
+      dc_carry = dc * fg;
+      const float dai = dc * gg * ig * (1.f - ig);
+      const float daf = dc * cprev * fg * (1.f - fg);
+      const float dag = dc * ig * (1.f - gg * gg);
+      const float dao = dh * tc * og * (1.f - og);
+      __nv_bfloat16* dg = p.dgates + (static_cast<long long>(b0 + pb) * T + t) * K4 + u0 + pu;
+      dg[0] = f2bf(dai); dg[Hs] = f2bf(daf); dg[2 * Hs] = f2bf(dag); dg[3 * Hs] = f2bf(dao);
+    }
+    if (t > 0) group_arrive(bar);
+  }
+}
+
+// Pick the group size G (CTAs per 8-utterance slice): U = Hs / G hidden units per CTA must be integral, the 8 x U
+// (utterance, unit) pairs must fit one thread each, the weight slice must fit shared memory and all S * G CTAs must be
+// co-resident.  Returns 0 when the batch-sliced kernels do not apply (the whole-batch kernels are used instead).
+static int lstm_bs_pick(int B, int Hs, bool bwd, size_t* smem_out) {
+  if (Hs % 16 != 0) return 0;
+  const int S = (B + RB - 1) / RB;
+  for (int G = 64; G >= 1; --G) {
+    if (Hs % G != 0 || S * G > num_sms()) continue;
+    const int U = Hs / G;
+    if (RB * U > LTHREADS || RB * (Hs / 8) > 4 * LTHREADS) continue;
+    size_t smem;
+    if (!bwd) {
+      const int M = 4 * U, mt = (M + 15) / 16;
+      if (mt > 8) continue;
+      smem = static_cast<size_t>(M + RB) * (Hs + LPAD) * 2 + static_cast<size_t>(4) * mt * 16 * 8 * 4;
+    } else {
+      const int mt = (U + 15) / 16;
+      if (mt > 2) continue;
+      smem = static_cast<size_t>(U) * (4 * Hs + LPAD) * 2 + static_cast<size_t>(RB) * (Hs + LPAD) * 2 +
+             static_cast<size_t>(8) * mt * 16 * 8 * 4;
+    }
+    if (smem > 232448) continue;
+    *smem_out = smem;
+    return G;
+  }
+  return 0;
+}
+
 static size_t lstm_fwd_smem(int Hs, int Bp) {
   return static_cast<size_t>(32 + Bp) * (Hs + LPAD) * 2 + static_cast<size_t>(Bp) * 33 * 4;
 }
@@ -302,6 +614,26 @@ using namespace mtasr;
 extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw, int32_t B, int32_t T, int32_t Hs,
                               void* h_bf16, float* h_f32, float* c_all, float* gates, uint32_t* barrier, void* stream) {
   MTASR_CHECK_ARG(xg && whh_bf16 && h_bf16 && c_all && gates && barrier, "lstm_fwd: null pointer");
+  cudaStream_t st0 = static_cast<cudaStream_t>(stream);
+  {
+    size_t smem_bs = 0;
+    const int G = getenv("MTASR_LSTM_WHOLE_BATCH") ? 0 : lstm_bs_pick(B, Hs, false, &smem_bs);
+    if (G > 0 && T > 0 && ldw % 8 == 0) {
+      const int S = (B + RB - 1) / RB;
+      LstmBsP q{};
+      q.xg = xg; q.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16); q.h_bf16 = reinterpret_cast<__nv_bfloat16*>(h_bf16);
+      q.h_f32 = h_f32; q.c_all = c_all; q.gates = gates; q.bar = barrier;
+      q.B = B; q.T = T; q.Hs = Hs; q.ldw = ldw; q.G = G; q.U = Hs / G;
+      if (cudaFuncSetAttribute(lstm_fwd_bs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bs)) != cudaSuccess)
+        return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: cannot set smem attribute");
+      if (cudaMemsetAsync(barrier, 0, sizeof(uint32_t) * S, st0) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: memset failed");
+      void* args[] = {&q};
+      cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_fwd_bs_kernel), dim3(S * G), dim3(LTHREADS), args, smem_bs, st0);
+      MTASR_COUNT_LAUNCH();
+      if (e != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: cooperative launch failed: %s", cudaGetErrorString(e));
+      return MTASR_OK;
+    }
+  }
   if (int rc = lstm_check(B, T, Hs, ldw, "lstm_fwd")) return rc;
   LstmFwdP p;
   p.xg = xg; p.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16); p.h_bf16 = reinterpret_cast<__nv_bfloat16*>(h_bf16);
@@ -323,6 +655,26 @@ extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw
 extern "C" int mtasr_lstm_bwd(const float* dh_out, const float* gates, const float* c_all, const void* whh_bf16, int32_t ldw,
                               int32_t B, int32_t T, int32_t Hs, void* dgates_bf16, uint32_t* barrier, void* stream) {
   MTASR_CHECK_ARG(dh_out && gates && c_all && whh_bf16 && dgates_bf16 && barrier, "lstm_bwd: null pointer");
+  cudaStream_t st0 = static_cast<cudaStream_t>(stream);
+  {
+    size_t smem_bs = 0;
+    const int G = getenv("MTASR_LSTM_WHOLE_BATCH") ? 0 : lstm_bs_pick(B, Hs, true, &smem_bs);
+    if (G > 0 && T > 0 && ldw % 8 == 0) {
+      const int S = (B + RB - 1) / RB;
+      LstmBsP q{};
+      q.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16); q.c_all = const_cast<float*>(c_all); q.gates = const_cast<float*>(gates);
+      q.dh_out = dh_out; q.dgates = reinterpret_cast<__nv_bfloat16*>(dgates_bf16); q.bar = barrier;
+      q.B = B; q.T = T; q.Hs = Hs; q.ldw = ldw; q.G = G; q.U = Hs / G;
+      if (cudaFuncSetAttribute(lstm_bwd_bs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bs)) != cudaSuccess)
+        return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: cannot set smem attribute");
+      if (cudaMemsetAsync(barrier, 0, sizeof(uint32_t) * S, st0) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: memset failed");
+      void* args[] = {&q};
+      cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_bwd_bs_kernel), dim3(S * G), dim3(LTHREADS), args, smem_bs, st0);
+      MTASR_COUNT_LAUNCH();
+      if (e != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: cooperative launch failed: %s", cudaGetErrorString(e));
+      return MTASR_OK;
+    }
+  }
   if (int rc = lstm_check(B, T, Hs, ldw, "lstm_bwd")) return rc;
   LstmBwdP p;
   p.dh_out = dh_out; p.gates = gates; p.c_all = c_all; p.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16);

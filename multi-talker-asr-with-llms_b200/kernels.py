@@ -435,7 +435,7 @@ def lstm_fwd(xg: torch.Tensor, whh: torch.Tensor, ldw: int, want_h_f32: bool = F
     hf = torch.empty(B, T, Hs, device=dev, dtype=torch.float32) if want_h_f32 else None
     c = torch.empty(B, T, Hs, device=dev, dtype=torch.float32)
     gates = torch.empty(B, T, H4, device=dev, dtype=torch.float32)
-    bar = torch.zeros(1, device=dev, dtype=torch.int32)
+    bar = torch.zeros(64, device=dev, dtype=torch.int32)      # one counter per 8-utterance slice
     check(_lib.load().mtasr_lstm_fwd(_p(xg), _p(whh), ldw, B, T, Hs, _p(h), _p(hf), _p(c), _p(gates), _p(bar), _stream()),
           "mtasr_lstm_fwd")
     return h, hf, c, gates
@@ -445,7 +445,7 @@ def lstm_bwd(dh: torch.Tensor, gates: torch.Tensor, c: torch.Tensor, whh: torch.
     B, T, Hs = dh.shape
     dh = dh.contiguous()
     dgates = torch.empty(B, T, 4 * Hs, device=dh.device, dtype=torch.bfloat16)
-    bar = torch.zeros(1, device=dh.device, dtype=torch.int32)
+    bar = torch.zeros(64, device=dh.device, dtype=torch.int32)
     check(_lib.load().mtasr_lstm_bwd(_p(dh), _p(gates), _p(c), _p(whh), ldw, B, T, Hs, _p(dgates), _p(bar), _stream()),
           "mtasr_lstm_bwd")
     return dgates
