@@ -309,10 +309,13 @@ def main_ours(args):
     gemm_ms, exec_flops, gemm_launches = K.profile_end()
     fl = algorithmic_flops(cfg, S, args.speakers, 896, V_LLAMA3_CTC)
     alg_step = fl["total"] * B
+    # the QK^T / PV contractions run in the fused attention kernels, not in the GEMM kernel: not credited to it
+    alg_gemm = (fl["total"] - fl["attention_total"]) * B
     peak, peak_src = peaks()
     ms_step = ms / args.steps
-    roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05/TMEM/TMA)", "achieved": alg_step / (gemm_ms / 1e3) / 1e12,
-            "peak": peak, "unit": "TFLOP/s", "frac": alg_step / (gemm_ms / 1e3) / 1e12 / peak, "traffic": None,
+    roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05/TMEM/TMA)", "achieved": alg_gemm / (gemm_ms / 1e3) / 1e12,
+            "peak": peak, "unit": "TFLOP/s", "frac": alg_gemm / (gemm_ms / 1e3) / 1e12 / peak, "traffic": None,
+            "algorithmic_tflop_per_step_in_kernel": alg_gemm / 1e12,
             "peak_source": peak_src, "launches_per_step": gemm_launches, "kernel_ms_per_step": gemm_ms,
             "kernel_share_of_step": gemm_ms / ms_step, "algorithmic_tflop_per_step": alg_step / 1e12,
             "executed_tflop_per_step": exec_flops / 1e12,

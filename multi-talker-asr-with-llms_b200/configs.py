@@ -47,6 +47,7 @@ def algorithmic_flops(cfg: WavLMConfig, samples: int, n_spk: int, sep_hidden: in
     pos = 2.0 * T * D * (D // cfg.num_conv_pos_embedding_groups) * cfg.num_conv_pos_embeddings
     layer = 2.0 * T * (4 * D * D + 2 * D * F) + 4.0 * T * T * D
     enc = cfg.num_hidden_layers * layer
+    attn = cfg.num_hidden_layers * 4.0 * T * T * D          # QK^T + PV part of `enc` (runs in the fused attention kernels)
     ad, t = 0.0, T
     for _ in range(cfg.num_adapter_layers):
         t = (t + 2 * 1 - cfg.adapter_kernel_size) // cfg.adapter_stride + 1
@@ -57,5 +58,5 @@ def algorithmic_flops(cfg: WavLMConfig, samples: int, n_spk: int, sep_hidden: in
     fwd = fe + proj + pos + enc + ad + sep + voc
     trainable = proj + pos + enc + sep + voc + (ad if adapter_backward else 0.0)
     total = fwd + (2.0 * trainable if backward else 0.0)
-    return dict(frames=T, fwd=fwd, total=total, fe=fe, proj=proj, posconv=pos, transformer=enc, adapter=ad, separator=sep,
+    return dict(frames=T, fwd=fwd, total=total, attention_total=attn * (3.0 if backward else 1.0), fe=fe, proj=proj, posconv=pos, transformer=enc, adapter=ad, separator=sep,
                 vocab=voc)

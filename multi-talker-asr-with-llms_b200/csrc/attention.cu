@@ -23,7 +23,7 @@ static constexpr int AT_BK = 128;        // keys per inner tile
 static constexpr int AT_TILE = 128 * 64 * 2;   // one 128 x 64 bf16 operand tile = 16 KB
 static constexpr int AT_KV_SLOTS = 4;
 static constexpr int AT_P_BYTES = 128 * 128 * 2;   // P tile: two 64-key chunks of 128 rows x 128 B
-static constexpr int AT_THREADS = 256;
+static constexpr int AT_THREADS = 384;         // 4 control warps + 2 softmax warpgroups
 static constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnFwdP {
@@ -61,7 +61,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
   uint8_t* p_s = kv_s + AT_KV_SLOTS * AT_TILE;           // 2 x 32 KB
   float* tbl_s = reinterpret_cast<float*>(p_s + 2 * AT_P_BYTES);   // 2T-1 floats
   // (+256 floats of slack: masked lanes of the last key tile may form addresses up to 128 entries past the table)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(tbl_s) + attn_table_bytes(p.T));
+  float* xch_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tbl_s) + attn_table_bytes(p.T));   // 2 x 128 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch_s + 256);
   uint64_t* q_full = bars;
   uint64_t* q_empty = bars + 1;
   uint64_t* kv_full = bars + 2;                  // [4]
@@ -87,7 +88,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
         mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
       }
       mbar_init(o_full, 1);
-      mbar_init(o_empty, 4);
+      mbar_init(o_empty, 8);
       fence_barrier_init();
     }
   } else if (warp == 2) {
@@ -176,21 +177,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
       }
     }
   } else if (warp >= 4) {
-    // ---------------------------------------------------------------- softmax warps: thread = query row
+    // ---------------------------------------------------------------- softmax warps: thread = query row.
+    // Two warpgroups (warps 4-7 and 8-11) own the two S / P buffers: group g processes every key tile that lands in
+    // buffer g, so consecutive tiles are exponentiated concurrently; the partial row max / row sum of the two groups
+    // are combined through shared memory.
     const int wq = warp & 3;
+    const int grp = (warp - 4) >> 2;
     const int r = wq * 32 + lane;
-    uint32_t sph[2] = {0, 0}, pph[2] = {0, 0}, oph = 0;
-    int sb = 0;
+    const int st = threadIdx.x - 128;              // 0..255 over both groups
+    uint32_t sph = 0, pph = 0, oph = 0;            // phases of this group's S / P buffer and of the O accumulator
     int cur_h = -1;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int qt = item % p.nq, h = (item / p.nq) % p.H, b = item / (p.nq * p.H);
-      named_bar_sync(1, 128);                      // every softmax thread is done with the previous item's table
+      named_bar_sync(1, 256);                      // every softmax thread is done with the previous item's table / xch
       if (h != cur_h) {
         const float* trow = p.table + static_cast<long long>(h) * (2 * p.T - 1);
-        for (int i = threadIdx.x - 128; i < 2 * p.T - 1; i += 128) tbl_s[i] = trow[i] * LOG2E;
+        for (int i = st; i < 2 * p.T - 1; i += 256) tbl_s[i] = trow[i] * LOG2E;
         cur_h = h;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       const int q = qt * AT_BQ + r;
       const bool q_ok = q < p.T;
       const int qc = q_ok ? q : p.T - 1;
@@ -199,61 +204,71 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
       const float* trel = tbl_s + (p.T - 1 - qc);   // trel[k] = log2e * table[h, k - q + T - 1]
       const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
 
-      // pass A: exact row maximum of z (log2 units)
+      // pass A: exact row maximum of z (log2 units) over this group's tiles (tile j lives in buffer j & 1)
       float m = -INFINITY;
-      for (int j = 0; j < nk; ++j) {
-        mbar_wait(&s_full[sb], sph[sb]);
-        sph[sb] ^= 1;
+      for (int j = grp; j < nk; j += 2) {
+        mbar_wait(&s_full[grp], sph);
+        sph ^= 1;
         tc_fence_after();
         const int k0 = j * AT_BK;
+        // 32-column chunks, software-pipelined: the TMEM load of chunk c+1 is in flight while chunk c is reduced
+        uint32_t va[32], vb[32];
+        tmem_ld32(tm_s[grp] + lane_off, va);
+        tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tm_s[sb] + lane_off + c * 32, v);
-          tmem_ld_wait();
+          uint32_t(&cur)[32] = (c & 1) ? vb : va;
+          uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+          if (c + 1 < 4) tmem_ld32(tm_s[grp] + lane_off + (c + 1) * 32, nxt);
           const int kb = k0 + c * 32;
           if (kb + 32 <= kl) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaf(__uint_as_float(v[i]), p.scale_log2, g * trel[kb + i]));
+            for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]));
           } else if (kb < kl) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (kb + i < kl) m = fmaxf(m, fmaf(__uint_as_float(v[i]), p.scale_log2, g * trel[kb + i]));
+              if (kb + i < kl) m = fmaxf(m, fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]));
           }
+          if (c + 1 < 4) tmem_ld_wait();
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[sb]);
-        sb ^= 1;
+        if (lane == 0) mbar_arrive(&s_empty[grp]);
       }
+      xch_s[grp * 128 + r] = m;
+      named_bar_sync(1, 256);
+      m = fmaxf(m, xch_s[(grp ^ 1) * 128 + r]);
       const float mm = m == -INFINITY ? 0.f : m;
+      named_bar_sync(1, 256);                      // both groups have read the maxima before xch is reused for the sums
 
-      // pass B: P = exp2(z - m) -> bf16 smem tile, l = row sum
+      // pass B: P = exp2(z - m) -> bf16 smem tile, l = partial row sum (pass-B tile j lives in buffer (nk + j) & 1)
       float l = 0.f;
-      int pb = sb;
-      for (int j = 0; j < nk; ++j) {
-        mbar_wait(&s_full[sb], sph[sb]);
-        sph[sb] ^= 1;
-        mbar_wait(&p_empty[pb], pph[pb] ^ 1);
-        pph[pb] ^= 1;
+      for (int j = (grp + nk) & 1; j < nk; j += 2) {
+        mbar_wait(&s_full[grp], sph);
+        sph ^= 1;
+        mbar_wait(&p_empty[grp], pph ^ 1);
+        pph ^= 1;
         tc_fence_after();
         const int k0 = j * AT_BK;
-        uint8_t* pt = p_s + pb * AT_P_BYTES;
+        uint8_t* pt = p_s + grp * AT_P_BYTES;
+        uint32_t va[32], vb[32];
+        tmem_ld32(tm_s[grp] + lane_off, va);
+        tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tm_s[sb] + lane_off + c * 32, v);
-          tmem_ld_wait();
+          uint32_t(&cur)[32] = (c & 1) ? vb : va;
+          uint32_t(&nxt)[32] = (c & 1) ? va : vb;
+          if (c + 1 < 4) tmem_ld32(tm_s[grp] + lane_off + (c + 1) * 32, nxt);
           const int kb = k0 + c * 32;
           float e[32];
           if (kb + 32 <= kl) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              e[i] = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, g * trel[kb + i]) - mm);
+              e[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]) - mm);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              e[i] = kb + i < kl ? ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, g * trel[kb + i]) - mm) : 0.f;
+              e[i] = kb + i < kl ? ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]) - mm) : 0.f;
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) l += e[i];
@@ -265,32 +280,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
             u.z = pack_bf16x2(e[g16 * 8 + 4], e[g16 * 8 + 5]); u.w = pack_bf16x2(e[g16 * 8 + 6], e[g16 * 8 + 7]);
             *reinterpret_cast<uint4*>(chunk + swz128(static_cast<uint32_t>(r * 128 + (c & 1) * 64 + g16 * 16))) = u;
           }
+          if (c + 1 < 4) {
+            tmem_ld_wait();
+          }
+          if (c == 2) {   // the last chunk is in registers: the next QK^T may overwrite this S buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[grp]);
+          }
         }
         fence_proxy_async();
-        tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&p_full[pb]);
-          mbar_arrive(&s_empty[sb]);
-        }
-        sb ^= 1;
-        pb ^= 1;
+        if (lane == 0) mbar_arrive(&p_full[grp]);
       }
+      xch_s[grp * 128 + r] = l;
+      named_bar_sync(1, 256);
+      l += xch_s[(grp ^ 1) * 128 + r];
 
-      // epilogue: O / l -> bf16, LSE
+      // epilogue: O / l -> bf16 (group g stores head-dim columns 32g..32g+31), LSE
       mbar_wait(o_full, oph);
       oph ^= 1;
       tc_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld32(tm_o + lane_off, o0);
-      tmem_ld32(tm_o + lane_off + 32, o1);
+      uint32_t o0[32];
+      tmem_ld32(tm_o + lane_off + grp * 32, o0);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
       if (q_ok) {
         const float inv = l > 0.f ? 1.f / l : 0.f;
-        __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.T + q) * (p.H * AT_D) + h * AT_D;
+        __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.T + q) * (p.H * AT_D) + h * AT_D + grp * 32;
 #pragma unroll
         for (int g16 = 0; g16 < 4; ++g16) {
           uint4 u;
@@ -300,17 +319,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
           u.w = pack_bf16x2(__uint_as_float(o0[g16 * 8 + 6]) * inv, __uint_as_float(o0[g16 * 8 + 7]) * inv);
           reinterpret_cast<uint4*>(orow)[g16] = u;
         }
-#pragma unroll
-        for (int g16 = 0; g16 < 4; ++g16) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o1[g16 * 8 + 0]) * inv, __uint_as_float(o1[g16 * 8 + 1]) * inv);
-          u.y = pack_bf16x2(__uint_as_float(o1[g16 * 8 + 2]) * inv, __uint_as_float(o1[g16 * 8 + 3]) * inv);
-          u.z = pack_bf16x2(__uint_as_float(o1[g16 * 8 + 4]) * inv, __uint_as_float(o1[g16 * 8 + 5]) * inv);
-          u.w = pack_bf16x2(__uint_as_float(o1[g16 * 8 + 6]) * inv, __uint_as_float(o1[g16 * 8 + 7]) * inv);
-          reinterpret_cast<uint4*>(orow)[4 + g16] = u;
-        }
         // natural-log LSE of the biased scores: z_log2 = z * log2e  =>  lse = (m + log2(l)) / log2e
-        p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l > 0.f ? (mm + log2f(l)) * 0.6931471805599453f : -INFINITY;
+        if (grp == 0)
+          p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l > 0.f ? (mm + log2f(l)) * 0.6931471805599453f : -INFINITY;
       }
     }
   }
@@ -361,19 +372,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   uint8_t* v_s = k_s + AT_TILE;                 // 16 KB
   uint8_t* q_s = v_s + AT_TILE;                 // 2 x 16 KB
   uint8_t* do_s = q_s + 2 * AT_TILE;            // 2 x 16 KB
-  uint8_t* p_s = do_s + 2 * AT_TILE;            // 32 KB
-  uint8_t* ds_s = p_s + AT_P_BYTES;             // 32 KB
-  float* tbl_s = reinterpret_cast<float*>(ds_s + AT_P_BYTES);                                  // 2T-1 (+slack)
+  uint8_t* p_s = do_s + 2 * AT_TILE;            // 32 KB (single: only MMA 3 reads it, and quickly)
+  uint8_t* ds_s = p_s + AT_P_BYTES;             // 2 x 32 KB (double: MMA 4/5 AND the reducer warps read it, slowly)
+  float* tbl_s = reinterpret_cast<float*>(ds_s + 2 * AT_P_BYTES);                              // 2T-1 (+slack)
   float* acc_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tbl_s) + attn_table_bytes(p.T));   // 2T-1
-  float* g_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(acc_s) + attn_table_bytes(p.T));     // 128
-  uint64_t* bars = reinterpret_cast<uint64_t*>(g_s + 128);
+  float* g_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(acc_s) + attn_table_bytes(p.T));     // 2 x 128
+  uint64_t* bars = reinterpret_cast<uint64_t*>(g_s + 256);
   uint64_t* kv_full = bars, *kv_empty = bars + 1;
   uint64_t* qdo_full = bars + 2, *qdo_empty = bars + 4;     // [2] each
   uint64_t* sdp_full = bars + 6, *sdp_empty = bars + 7;
-  uint64_t* pds_full = bars + 8, *pds_empty = bars + 9;
-  uint64_t* dq_full = bars + 10, *dq_empty = bars + 11;
-  uint64_t* dkv_full = bars + 12, *dkv_empty = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* pds_full = bars + 8;                            // [2] P + dS[buf] (+ gate[buf]) written by the softmax warps
+  uint64_t* ds_empty = bars + 10;                           // [2] dS[buf] consumed by MMA 4/5 and the 4 reducer warps
+  uint64_t* p_empty = bars + 12;                            // P consumed by MMA 3
+  uint64_t* dq_full = bars + 13, *dq_empty = bars + 14;
+  uint64_t* dkv_full = bars + 15, *dkv_empty = bars + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) {
@@ -383,7 +396,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
       for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
       mbar_init(sdp_full, 1); mbar_init(sdp_empty, 4);
-      mbar_init(pds_full, 4); mbar_init(pds_empty, 5);     // MMA commit + 4 reducer warps
+      for (int i = 0; i < 2; ++i) { mbar_init(&pds_full[i], 4); mbar_init(&ds_empty[i], 5); }   // MMA commit + 4 reducer warps
+      mbar_init(p_empty, 1);
       mbar_init(dq_full, 1); mbar_init(dq_empty, 4);
       mbar_init(dkv_full, 1); mbar_init(dkv_empty, 4);
       fence_barrier_init();
@@ -428,9 +442,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       const uint32_t idesc_kk = make_idesc_bf16(128, 128, 0, 0);   // S, dP: both operands K-major
       const uint32_t idesc_mm = make_idesc_bf16(128, 64, 1, 1);    // dV, dK: both MN-major
       const uint32_t idesc_km = make_idesc_bf16(128, 64, 0, 1);    // dQ: dS K-major, K_j MN-major
-      uint32_t kvph = 0, qph[2] = {0, 0}, sdp_ph = 0, pds_ph = 0, dq_ph = 0, dkv_ph = 0;
+      uint32_t kvph = 0, qph[2] = {0, 0}, sdp_ph = 0, pds_ph[2] = {0, 0}, dq_ph = 0, dkv_ph = 0;
       int st = 0;   // stage of the NEXT S/dP issue
-      const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s), pa = smem_u32(p_s), dsa = smem_u32(ds_s);
+      int db = 0;   // dS buffer of the current tile (alternates per tile, continuing across items)
+      const uint32_t ka = smem_u32(k_s), va = smem_u32(v_s), pa = smem_u32(p_s);
       auto issue_sdp = [&]() {
         mbar_wait(&qdo_full[st], qph[st]);
         qph[st] ^= 1;
@@ -453,16 +468,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           const int cur = st ^ 1;                     // stage holding Q_i / dO_i
           if (i + 1 < nq) issue_sdp();
           const int stage_i = (i + 1 < nq) ? (st) : cur;   // after the extra issue `st` points back at tile i's stage
-          mbar_wait(pds_full, pds_ph);
-          pds_ph ^= 1;
+          mbar_wait(&pds_full[db], pds_ph[db]);
+          pds_ph[db] ^= 1;
           mbar_wait(dq_empty, dq_ph ^ 1);
           dq_ph ^= 1;
           if (i == 0) { mbar_wait(dkv_empty, dkv_ph ^ 1); dkv_ph ^= 1; }
           tc_fence_after();
           const uint32_t qa = smem_u32(q_s + stage_i * AT_TILE), doa = smem_u32(do_s + stage_i * AT_TILE);
+          const uint32_t dsa = smem_u32(ds_s + db * AT_P_BYTES);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)   // dV += P^T dO_i
             umma_f16(tm_dv, desc_mnmajor(pa, ks, 16384), desc_mnmajor(doa, ks, 8192), idesc_mm, (i | ks) != 0);
+          umma_commit(p_empty);            // P may be overwritten as soon as MMA 3 has read it
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)   // dK += dS^T Q_i
             umma_f16(tm_dk, desc_mnmajor(dsa, ks, 16384), desc_mnmajor(qa, ks, 8192), idesc_mm, (i | ks) != 0);
@@ -471,8 +488,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             umma_f16(tm_dq, make_smem_desc(dsa + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), desc_mnmajor(ka, ks, 8192),
                      idesc_km, ks != 0);
           umma_commit(dq_full);
-          umma_commit(pds_empty);
+          umma_commit(&ds_empty[db]);
           umma_commit(&qdo_empty[stage_i]);
+          db ^= 1;
         }
         umma_commit(dkv_full);
         umma_commit(kv_empty);
@@ -484,7 +502,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const int r = wq * 32 + lane;
     const int tid = threadIdx.x - 128;
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
-    uint32_t sdp_ph = 0, pds_ph = 0, dkv_ph = 0;
+    uint32_t sdp_ph = 0, pe_ph = 0, dse_ph[2] = {0, 0}, dkv_ph = 0;
+    int db = 0;
     int cur_h = -1;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int jt = item % p.nk, h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
@@ -521,10 +540,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(sdp_empty);
           }
-          if (c == 0) {   // P / dS / gate staging of the previous tile must have been consumed
-            mbar_wait(pds_empty, pds_ph ^ 1);
-            pds_ph ^= 1;
-            g_s[r] = q_ok ? g : 0.f;
+          if (c == 0) {   // P of the previous tile (MMA 3) and dS / gate of two tiles ago (MMA 4/5 + reducers) consumed
+            mbar_wait(p_empty, pe_ph ^ 1);
+            pe_ph ^= 1;
+            mbar_wait(&ds_empty[db], dse_ph[db] ^ 1);
+            dse_ph[db] ^= 1;
+            g_s[db * 128 + r] = q_ok ? g : 0.f;
           }
           const int kb = k0 + c * 32;
           float pe[32], de[32];
@@ -539,7 +560,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             de[e] = dz * p.scale;
           }
           uint8_t* pc = p_s + (c >> 1) * 16384;
-          uint8_t* dc = ds_s + (c >> 1) * 16384;
+          uint8_t* dc = ds_s + db * AT_P_BYTES + (c >> 1) * 16384;
 #pragma unroll
           for (int g16 = 0; g16 < 4; ++g16) {
             const uint32_t off = swz128(static_cast<uint32_t>(r * 128 + (c & 1) * 64 + g16 * 16));
@@ -554,7 +575,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         }
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(pds_full);
+        if (lane == 0) mbar_arrive(&pds_full[db]);
+        db ^= 1;
         if (q_ok && dg != 0.f) atomicAdd(p.dgate + bh * p.T + q, dg * 0.6931471805599453f);   // table was scaled by log2e
       }
       // item epilogue: dK_j, dV_j (rows = keys of this tile) -> bf16 into dqkv
@@ -597,15 +619,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const int wq = warp & 3;
     const int t = wq * 32 + lane;                 // 0..127
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
-    uint32_t pds_ph = 0, dq_ph = 0;
+    uint32_t pds_ph[2] = {0, 0}, dq_ph = 0;
+    int db = 0;
     const float inv_scale = 1.f / p.scale;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int jt = item % p.nk, h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
       for (int i = t; i < 2 * p.T - 1; i += 128) acc_s[i] = 0.f;
       named_bar_sync(2, 128);
       for (int i = 0; i < nq; ++i) {
-        mbar_wait(pds_full, pds_ph);
-        pds_ph ^= 1;
+        mbar_wait(&pds_full[db], pds_ph[db]);
+        pds_ph[db] ^= 1;
+        const uint8_t* dsb = ds_s + db * AT_P_BYTES;
+        const float* gsb = g_s + db * 128;
         // local diagonals dl = kk - qq: this thread owns dl = t - 127 (<= 0) and dl = t + 1 (>= 1, only t <= 126)
         const int base = (jt - i) * 128 + p.T - 1;
 #pragma unroll 1
@@ -619,13 +644,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           for (int qq = q_lo; qq <= q_hi; ++qq) {
             const int kk = qq + dl;
             const uint32_t off = swz128(static_cast<uint32_t>(qq * 128 + (kk & 63) * 2));
-            const float dsv = bf2f(*reinterpret_cast<const __nv_bfloat16*>(ds_s + (kk >> 6) * 16384 + off));
-            sum = fmaf(dsv, g_s[qq], sum);
+            const float dsv = bf2f(*reinterpret_cast<const __nv_bfloat16*>(dsb + (kk >> 6) * 16384 + off));
+            sum = fmaf(dsv, gsb[qq], sum);
           }
           acc_s[gidx] += sum;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(pds_empty);
+        if (lane == 0) mbar_arrive(&ds_empty[db]);
+        db ^= 1;
         // dQ_i partial: TMEM -> fp32 vector reductions into the scratch
         mbar_wait(dq_full, dq_ph);
         dq_ph ^= 1;
@@ -762,7 +788,7 @@ extern "C" int mtasr_attn_fwd(const void* qkv, const float* gate, const float* t
   p.gate = gate; p.table = table; p.klen = klen;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse;
-  const int smem = AT_TILE + AT_KV_SLOTS * AT_TILE + 2 * AT_P_BYTES + attn_table_bytes(T) + 256;
+  const int smem = AT_TILE + AT_KV_SLOTS * AT_TILE + 2 * AT_P_BYTES + attn_table_bytes(T) + 1024 + 256;
   MTASR_CHECK_ARG(smem <= 232448, "attn_fwd: T=%d needs %d bytes of shared memory", T, smem);
   if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return set_error(MTASR_ERR_LAUNCH, "attn_fwd: cannot set the shared-memory attribute");
@@ -799,7 +825,7 @@ extern "C" int mtasr_attn_bwd(const void* qkv, const void* out, const void* dout
   p.gate = gate; p.table = table; p.klen = klen; p.lse = lse; p.delta = delta;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.dq32 = dq32; p.dgate = dgate; p.dtable = dtable;
-  const int smem = 6 * AT_TILE + 2 * AT_P_BYTES + 2 * attn_table_bytes(T) + 128 * 4 + 256;
+  const int smem = 6 * AT_TILE + 3 * AT_P_BYTES + 2 * attn_table_bytes(T) + 256 * 4 + 256;
   MTASR_CHECK_ARG(smem <= 232448, "attn_bwd: T=%d needs %d bytes of shared memory", T, smem);
   if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return set_error(MTASR_ERR_LAUNCH, "attn_bwd: cannot set the shared-memory attribute");

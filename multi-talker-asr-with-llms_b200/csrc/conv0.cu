@@ -84,8 +84,8 @@ conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const flo
         for (int i = 0; i < C0_MAXI; ++i)
           if (i < ni) {
             const int c = 64 * i + 2 * lane;
-            const float v0 = gelu_f((acc[r][i][0] - mean) * rstd * gsm[c] + besm[c]);
-            const float v1 = gelu_f((acc[r][i][1] - mean) * rstd * gsm[c + 1] + besm[c + 1]);
+            const float v0 = gelu_fast_f((acc[r][i][0] - mean) * rstd * gsm[c] + besm[c]);
+            const float v1 = gelu_fast_f((acc[r][i][1] - mean) * rstd * gsm[c + 1] + besm[c + 1]);
             *reinterpret_cast<uint32_t*>(y_bf16 + f * C0 + c) = pack_bf16x2(v0, v1);
           }
       } else {
@@ -140,8 +140,8 @@ __global__ void groupnorm_gelu_kernel(const float* __restrict__ x, const float* 
     const long long bl = i / (C / 2);
     const int b = static_cast<int>(bl / L);
     const float2 v = *reinterpret_cast<const float2*>(x + bl * C + c);
-    const float o0 = gelu_f((v.x - mean[b * C + c]) * rstd[b * C + c] * gamma[c] + beta[c]);
-    const float o1 = gelu_f((v.y - mean[b * C + c + 1]) * rstd[b * C + c + 1] * gamma[c + 1] + beta[c + 1]);
+    const float o0 = gelu_fast_f((v.x - mean[b * C + c]) * rstd[b * C + c] * gamma[c] + beta[c]);
+    const float o1 = gelu_fast_f((v.y - mean[b * C + c + 1]) * rstd[b * C + c + 1] * gamma[c + 1] + beta[c + 1]);
     *reinterpret_cast<uint32_t*>(y + bl * C + c) = pack_bf16x2(o0, o1);
   }
 }

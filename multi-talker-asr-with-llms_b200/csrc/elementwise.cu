@@ -72,7 +72,7 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float t = (r[n * 8 + j] - mean) * rstd * gamma[c * 8 + j] + beta[c * 8 + j];
-          o[j] = post_gelu ? gelu_f(t) : t;
+          o[j] = post_gelu ? gelu_fast_f(t) : t;
         }
         if (y_bf16) st8_bf16(y_bf16 + row * D + c * 8, o);
         if (y_f32) st8_f32(y_f32 + row * D + c * 8, o);
@@ -254,89 +254,144 @@ colsum_kernel(const void* __restrict__ x, int dtype, long long M, int N, long lo
 //   gate = sigmoid(a) * (sigmoid(b) * const_h - 1) + 2
 // One warp per (b, t) row; lane l holds elements l and l+32 of each head slice.  wab = [wa | wb] (128 floats),
 // bab = [ba, bb].  Output gate (B,H,T) fp32.
+// One warp per (b, t) row, two lanes per head: lane l owns the contiguous 32 elements [32 (l & 1), +32) of head l >> 1
+// (four 128-bit loads for bf16, eight for fp32), so a head's dot products are one lane-local accumulation plus a single
+// shuffle with the partner lane.  H <= 16.  The summed weights live in shared memory (broadcast reads).
+__device__ __forceinline__ void gate_load32(const void* x, int x_dtype, long long off, float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float t[8];
+    ld8(x, x_dtype, off + c * 8, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[c * 8 + j] = t[j];
+  }
+}
+
 __global__ void __launch_bounds__(256)
 relpos_gate_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ wab, const float* __restrict__ bab,
                        const float* __restrict__ cst, int B, int T, int H, float* __restrict__ gate) {
+  __shared__ __align__(16) float w_s[128];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) w_s[i] = wab[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  const float wa0 = wab[lane], wa1 = wab[lane + 32], wb0 = wab[64 + lane], wb1 = wab[96 + lane];
+  const int h = lane >> 1, half = lane & 1;
+  const bool active = h < H;
+  const float* wa = w_s + half * 32;
+  const float* wb = w_s + 64 + half * 32;
   const float ba = bab[0], bb = bab[1];
+  const float c_h = active ? cst[h] : 0.f;
   const long long rows = static_cast<long long>(B) * T;
   const int D = H * 64;
   for (long long row = warp0; row < rows; row += nwarps) {
-    const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
-    for (int h = 0; h < H; ++h) {
-      float x0, x1;
-      if (x_dtype == MTASR_DT_BF16) {
-        const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x) + row * D + h * 64;
-        x0 = bf2f(xp[lane]); x1 = bf2f(xp[lane + 32]);
-      } else {
-        const float* xp = reinterpret_cast<const float*>(x) + row * D + h * 64;
-        x0 = xp[lane]; x1 = xp[lane + 32];
+    float a = 0.f, bv = 0.f;
+    if (active) {
+      float v[32];
+      gate_load32(x, x_dtype, row * D + h * 64 + half * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        a = fmaf(v[i], wa[i], a);
+        bv = fmaf(v[i], wb[i], bv);
       }
-      const float a = warp_sum(wa0 * x0 + wa1 * x1) + ba;
-      const float bv = warp_sum(wb0 * x0 + wb1 * x1) + bb;
-      if (lane == 0) {
-        const float ga = 1.f / (1.f + expf(-a)), gb = 1.f / (1.f + expf(-bv));
-        gate[(static_cast<long long>(b) * H + h) * T + t] = ga * (gb * cst[h] - 1.f) + 2.f;
-      }
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    bv += __shfl_xor_sync(0xffffffffu, bv, 1);
+    if (active && half == 0) {
+      const float ga = 1.f / (1.f + __expf(-(a + ba))), gb = 1.f / (1.f + __expf(-(bv + bb)));
+      const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
+      gate[(static_cast<long long>(b) * H + h) * T + t] = ga * (gb * c_h - 1.f) + 2.f;
     }
   }
 }
 
 // Backward: dx (B,T,D) fp32 = da*wa + db*wb per head slice; dwab (128), dbab (2), dcst (H) accumulated with atomics
 // (zero them first).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 3)
 relpos_gate_bwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ wab, const float* __restrict__ bab,
                        const float* __restrict__ cst, const float* __restrict__ dgate, int B, int T, int H,
                        float* __restrict__ dx, float* __restrict__ dwab, float* __restrict__ dbab, float* __restrict__ dcst) {
-  __shared__ float red[8][132];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + warp;
+  __shared__ __align__(16) float w_s[128];
+  __shared__ float red_s[132];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) w_s[i] = wab[i];
+  for (int i = threadIdx.x; i < 132; i += blockDim.x) red_s[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
-  const float wa0 = wab[lane], wa1 = wab[lane + 32], wb0 = wab[64 + lane], wb1 = wab[96 + lane];
+  const int h = lane >> 1, half = lane & 1;
+  const bool active = h < H;
+  const float* wa = w_s + half * 32;
+  const float* wb = w_s + 64 + half * 32;
   const float ba = bab[0], bb = bab[1];
+  const float c_h = active ? cst[h] : 0.f;
   const long long rows = static_cast<long long>(B) * T;
   const int D = H * 64;
-  float dwa0 = 0.f, dwa1 = 0.f, dwb0 = 0.f, dwb1 = 0.f, dba = 0.f, dbb = 0.f;
-  float dc = 0.f;   // lane h (< H) accumulates dcst[h]
+  float dwa[32], dwb[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { dwa[i] = 0.f; dwb[i] = 0.f; }
+  float dba = 0.f, dbb = 0.f, dc = 0.f;
   for (long long row = warp0; row < rows; row += nwarps) {
-    const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
-    for (int h = 0; h < H; ++h) {
-      float x0, x1;
-      if (x_dtype == MTASR_DT_BF16) {
-        const __nv_bfloat16* xp = reinterpret_cast<const __nv_bfloat16*>(x) + row * D + h * 64;
-        x0 = bf2f(xp[lane]); x1 = bf2f(xp[lane + 32]);
-      } else {
-        const float* xp = reinterpret_cast<const float*>(x) + row * D + h * 64;
-        x0 = xp[lane]; x1 = xp[lane + 32];
+    float v[32];
+    float a = 0.f, bv = 0.f;
+    if (active) {
+      gate_load32(x, x_dtype, row * D + h * 64 + half * 32, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        a = fmaf(v[i], wa[i], a);
+        bv = fmaf(v[i], wb[i], bv);
       }
-      const float a = warp_sum(wa0 * x0 + wa1 * x1) + ba;
-      const float bv = warp_sum(wb0 * x0 + wb1 * x1) + bb;
-      const float ga = 1.f / (1.f + expf(-a)), gb = 1.f / (1.f + expf(-bv));
-      const float c = cst[h];
+    }
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    bv += __shfl_xor_sync(0xffffffffu, bv, 1);
+    if (active) {
+      const float ga = 1.f / (1.f + __expf(-(a + ba))), gb = 1.f / (1.f + __expf(-(bv + bb)));
+      const int b = static_cast<int>(row / T), t = static_cast<int>(row % T);
       const float dg = dgate[(static_cast<long long>(b) * H + h) * T + t];
-      const float da = dg * (gb * c - 1.f) * ga * (1.f - ga);
-      const float db = dg * ga * c * gb * (1.f - gb);
-      if (lane == (h & 31)) dc += dg * ga * gb;
-      float* dxp = dx + row * D + h * 64;
-      dxp[lane] = da * wa0 + db * wb0;
-      dxp[lane + 32] = da * wa1 + db * wb1;
-      dwa0 += da * x0; dwa1 += da * x1; dwb0 += db * x0; dwb1 += db * x1;
-      dba += da; dbb += db;   // identical on every lane
+      const float da = dg * (gb * c_h - 1.f) * ga * (1.f - ga);
+      const float db = dg * ga * c_h * gb * (1.f - gb);
+      if (half == 0) { dc += dg * ga * gb; dba += da; dbb += db; }
+      float* dxp = dx + row * D + h * 64 + half * 32;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 o;
+        o.x = fmaf(da, wa[c * 4 + 0], db * wb[c * 4 + 0]);
+        o.y = fmaf(da, wa[c * 4 + 1], db * wb[c * 4 + 1]);
+        o.z = fmaf(da, wa[c * 4 + 2], db * wb[c * 4 + 2]);
+        o.w = fmaf(da, wa[c * 4 + 3], db * wb[c * 4 + 3]);
+        reinterpret_cast<float4*>(dxp)[c] = o;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        dwa[i] = fmaf(da, v[i], dwa[i]);
+        dwb[i] = fmaf(db, v[i], dwb[i]);
+      }
     }
   }
-  red[warp][lane] = dwa0; red[warp][lane + 32] = dwa1; red[warp][64 + lane] = dwb0; red[warp][96 + lane] = dwb1;
-  if (lane == 0) { red[warp][128] = dba; red[warp][129] = dbb; }
+  // lanes of equal parity hold partial sums for the same 32 weight entries: fold them, then one smem atomic per entry
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float sa = dwa[i], sb = dwb[i];
+#pragma unroll
+    for (int o = 2; o < 32; o <<= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    if (lane < 2) {
+      atomicAdd(red_s + half * 32 + i, sa);
+      atomicAdd(red_s + 64 + half * 32 + i, sb);
+    }
+  }
+  dba = warp_sum(dba);
+  dbb = warp_sum(dbb);
+  if (lane == 0) { atomicAdd(red_s + 128, dba); atomicAdd(red_s + 129, dbb); }
+  if (active && half == 0 && dc != 0.f) atomicAdd(dcst + h, dc);
   __syncthreads();
   for (int i = threadIdx.x; i < 130; i += blockDim.x) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w][i];
-    if (i < 128) atomicAdd(dwab + i, s);
-    else atomicAdd(dbab + (i - 128), s);
+    const float sv = red_s[i];
+    if (i < 128) atomicAdd(dwab + i, sv);
+    else atomicAdd(dbab + (i - 128), sv);
   }
-  if (lane < H && dc != 0.f) atomicAdd(dcst + lane, dc);
 }
 
 // ------------------------------------------------------------------------------------------------ attention softmax
@@ -579,6 +634,7 @@ extern "C" int mtasr_colsum(const void* x, int32_t dtype, int64_t M, int32_t N, 
 extern "C" int mtasr_relpos_gate_fwd(const void* x, int32_t x_dtype, const float* wab, const float* bab, const float* cst,
                                      int32_t B, int32_t T, int32_t H, float* gate, void* stream) {
   MTASR_CHECK_ARG(x && wab && bab && cst && gate && B > 0 && T > 0 && H > 0 && H <= 32, "relpos_gate_fwd: bad arguments");
+  MTASR_CHECK_ARG(H <= 16, "relpos_gate_fwd: H=%d > 16 heads not supported", H);
   relpos_gate_fwd_kernel<<<grid_for(static_cast<long long>(B) * T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, x_dtype, wab, bab, cst, B, T, H, gate);
   MTASR_COUNT_LAUNCH();
@@ -591,9 +647,10 @@ extern "C" int mtasr_relpos_gate_bwd(const void* x, int32_t x_dtype, const float
                                      float* dcst, void* stream) {
   MTASR_CHECK_ARG(x && wab && bab && cst && dgate && dx && dwab && dbab && dcst && B > 0 && T > 0 && H > 0 && H <= 32,
                   "relpos_gate_bwd: bad arguments");
-  long long g = (static_cast<long long>(B) * T + 63) / 64;
-  if (g > num_sms() * 2) g = num_sms() * 2;
-  relpos_gate_bwd_kernel<<<static_cast<unsigned>(g), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  MTASR_CHECK_ARG(H <= 16, "relpos_gate_bwd: H=%d > 16 heads not supported", H);
+  long long g = (static_cast<long long>(B) * T + 15) / 16;
+  if (g > num_sms() * 3) g = num_sms() * 3;
+  relpos_gate_bwd_kernel<<<static_cast<unsigned>(g), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       x, x_dtype, wab, bab, cst, dgate, B, T, H, dx, dwab, dbab, dcst);
   MTASR_COUNT_LAUNCH();
   MTASR_CHECK_LAUNCH("relpos_gate_bwd");

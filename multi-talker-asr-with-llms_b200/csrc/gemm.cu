@@ -793,12 +793,25 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   // contractions with small M x N) is cut along K; partial tiles are summed by TMA reduce-add into a zeroed C.
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p.tma_epi && d->mode == 0 && d->act == 0 && !d->aux && !d->residual && !d->bias && d->c_dtype == MTASR_DT_F32 &&
-      d->batch0 == 1 && d->batch1 == 1 && d->alpha == 1.0f && p.num_tiles * 2 <= num_sms() && p.num_kb >= 16 &&
-      getenv("MTASR_GEMM_NO_SPLITK") == nullptr) {
-    int splits = num_sms() / p.num_tiles;
-    if (splits > p.num_kb / 8) splits = p.num_kb / 8;
-    if (splits > 1) {
-      p.kb_per_split = (p.num_kb + splits - 1) / splits;
+      d->batch0 == 1 && d->batch1 == 1 && d->alpha == 1.0f && p.num_kb >= 16 && getenv("MTASR_GEMM_NO_SPLITK") == nullptr) {
+    // choose the split that best fills whole waves of SMs (wave quantisation: e.g. 500 tiles on 148 SMs run as 4 waves at
+    // 84 % occupancy, 2 x 500 half-K items as 7 waves at 97 %), keeping >= 32 k-blocks (K >= 2048) per item
+    const int sms = num_sms();
+    auto eff = [&](int sp) {
+      const long long items = static_cast<long long>(p.num_tiles) * sp;
+      const long long waves = (items + sms - 1) / sms;
+      return static_cast<double>(items) / static_cast<double>(waves * sms);
+    };
+    int best = 1;
+    double best_eff = eff(1);
+    const int max_split = p.num_tiles * 2 <= sms ? sms / p.num_tiles : 4;
+    for (int sp = 2; sp <= max_split; ++sp) {
+      if (p.num_kb / sp < (p.num_tiles * 2 <= sms ? 8 : 32)) break;
+      const double e = eff(sp);
+      if (e > best_eff + 0.04) { best = sp; best_eff = e; }
+    }
+    if (best > 1) {
+      p.kb_per_split = (p.num_kb + best - 1) / best;
       p.splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
       p.num_tiles *= p.splits;
       if (cudaMemset2DAsync(d->c, static_cast<size_t>(d->c_ld) * 4, 0, static_cast<size_t>(d->N) * 4, d->M, st) != cudaSuccess)
