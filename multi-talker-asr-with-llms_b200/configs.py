@@ -54,9 +54,11 @@ def algorithmic_flops(cfg: WavLMConfig, samples: int, n_spk: int, sep_hidden: in
         ad += 2.0 * t * (2 * D) * (cfg.adapter_kernel_size * D)
     sep = 2.0 * T * D * sep_hidden + 2 * (2.0 * T * (2 * sep_hidden) * (4 * sep_hidden)) \
         + n_spk * (2.0 * T * sep_hidden * sep_hidden + 2.0 * T * sep_hidden * D)
+    rec = 2 * (2.0 * T * sep_hidden * (4 * sep_hidden))        # recurrent half of the LSTM (runs in the persistent kernels)
     voc = n_spk * 2.0 * T * D * vocab
     fwd = fe + proj + pos + enc + ad + sep + voc
     trainable = proj + pos + enc + sep + voc + (ad if adapter_backward else 0.0)
     total = fwd + (2.0 * trainable if backward else 0.0)
-    return dict(frames=T, fwd=fwd, total=total, attention_total=attn * (3.0 if backward else 1.0), fe=fe, proj=proj, posconv=pos, transformer=enc, adapter=ad, separator=sep,
+    return dict(frames=T, fwd=fwd, total=total, attention_total=attn * (3.0 if backward else 1.0),
+                lstm_recurrent_total=rec * (3.0 if backward else 1.0), fe=fe, proj=proj, posconv=pos, transformer=enc, adapter=ad, separator=sep,
                 vocab=voc)

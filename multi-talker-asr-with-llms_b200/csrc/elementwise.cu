@@ -68,10 +68,12 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
     for (int n = 0; n < MAXV / 8; ++n) {
       const int c = lane + 32 * n;
       if (c < nchunk) {
-        float o[8];
+        float o[8], gm[8], bt[8];
+        ld8(gamma, MTASR_DT_F32, c * 8, gm);
+        ld8(beta, MTASR_DT_F32, c * 8, bt);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float t = (r[n * 8 + j] - mean) * rstd * gamma[c * 8 + j] + beta[c * 8 + j];
+          float t = (r[n * 8 + j] - mean) * rstd * gm[j] + bt[j];
           o[j] = post_gelu ? gelu_fast_f(t) : t;
         }
         if (y_bf16) st8_bf16(y_bf16 + row * D + c * 8, o);
@@ -87,23 +89,18 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
 
 // ------------------------------------------------------------------------------------------------ LayerNorm bwd
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; optional + dres (residual-stream gradient).
-// dgamma / dbeta: per-lane register partials over the rows a warp visits, combined in smem, one atomicAdd per column
-// per CTA (gamma/beta grads must be zero-initialised by the caller).
-__global__ void __launch_bounds__(256)
+// One warp per row; the parameter gradients are a separate column-reduction kernel (below) so that this one stays light
+// on registers (two resident CTAs per SM) -- keeping 2 x D/32 running sums per lane here cost more in occupancy than
+// re-reading dy and x costs in bandwidth.
+__global__ void __launch_bounds__(256, 2)
 layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                      const float* __restrict__ dres, long long rows, int D, float* __restrict__ dx_f32,
-                     __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  extern __shared__ float sm[];  // 2 * D floats
+                     __nv_bfloat16* __restrict__ dx_bf16) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
   const int nchunk = D >> 3;
-  float ag[MAXV], ab[MAXV];
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) { ag[i] = 0.f; ab[i] = 0.f; }
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
   for (long long row = warp0; row < rows; row += nwarps) {
     const float mu = mean[row], rs = rstd[row];
     float g[MAXV], xh[MAXV];
@@ -112,19 +109,18 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
     for (int n = 0; n < MAXV / 8; ++n) {
       const int c = lane + 32 * n;
       if (c < nchunk) {
-        float a[8], b[8];
+        float a[8], b[8], gm[8];
         ld8(dy, dy_dtype, row * D + c * 8, a);
         ld8(x, x_dtype, row * D + c * 8, b);
+        ld8(gamma, MTASR_DT_F32, c * 8, gm);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xhat = (b[j] - mu) * rs;
-          const float gg = a[j] * gamma[c * 8 + j];
+          const float gg = a[j] * gm[j];
           xh[n * 8 + j] = xhat;
           g[n * 8 + j] = gg;
           s1 += gg;
           s2 += gg * xhat;
-          ag[n * 8 + j] += a[j] * xhat;
-          ab[n * 8 + j] += a[j];
         }
       }
     }
@@ -148,23 +144,57 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
       }
     }
   }
-  if (dgamma || dbeta) {
+}
+
+// dgamma[c] += sum_rows dy * xhat, dbeta[c] += sum_rows dy (zero them first).  Column reduction: thread = 8 consecutive
+// columns, 8 row-lanes per CTA, 2 rows in flight per thread; CTA partials combined in smem, one atomic per column.
+__global__ void __launch_bounds__(256)
+layernorm_bwd_param_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
+                           const float* __restrict__ mean, const float* __restrict__ rstd, long long rows, int D,
+                           float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float redg[8][32][9], redb[8][32][9];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cx) * 8;
+  float sg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sb[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (col < D) {
+    const long long step = static_cast<long long>(gridDim.y) * 8;
+    long long m = static_cast<long long>(blockIdx.y) * 8 + ry;
+    for (; m + step < rows; m += 2 * step) {
+      float a0[8], b0[8], a1[8], b1[8];
+      ld8(dy, dy_dtype, m * D + col, a0);
+      ld8(x, x_dtype, m * D + col, b0);
+      ld8(dy, dy_dtype, (m + step) * D + col, a1);
+      ld8(x, x_dtype, (m + step) * D + col, b1);
+      const float mu0 = mean[m], rs0 = rstd[m], mu1 = mean[m + step], rs1 = rstd[m + step];
 #pragma unroll
-    for (int n = 0; n < MAXV / 8; ++n) {
-      const int c = lane + 32 * n;
-      if (c < nchunk) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          atomicAdd(&sm[c * 8 + j], ag[n * 8 + j]);
-          atomicAdd(&sm[D + c * 8 + j], ab[n * 8 + j]);
-        }
+      for (int j = 0; j < 8; ++j) {
+        sg[j] += a0[j] * ((b0[j] - mu0) * rs0) + a1[j] * ((b1[j] - mu1) * rs1);
+        sb[j] += a0[j] + a1[j];
       }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-      if (dgamma) atomicAdd(dgamma + i, sm[i]);
-      if (dbeta) atomicAdd(dbeta + i, sm[D + i]);
+    for (; m < rows; m += step) {
+      float a0[8], b0[8];
+      ld8(dy, dy_dtype, m * D + col, a0);
+      ld8(x, x_dtype, m * D + col, b0);
+      const float mu0 = mean[m], rs0 = rstd[m];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sg[j] += a0[j] * ((b0[j] - mu0) * rs0);
+        sb[j] += a0[j];
+      }
     }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { redg[ry][cx][j] = sg[j]; redb[ry][cx][j] = sb[j]; }
+  __syncthreads();
+  const int c = threadIdx.x;
+  const int gcol = blockIdx.x * 256 + c;
+  if (gcol < D) {
+    float tg = 0.f, tb = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { tg += redg[i][c >> 3][c & 7]; tb += redb[i][c >> 3][c & 7]; }
+    if (dgamma) atomicAdd(dgamma + gcol, tg);
+    if (dbeta) atomicAdd(dbeta + gcol, tb);
   }
 }
 
@@ -586,12 +616,21 @@ extern "C" int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void*
                                    float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, void* stream) {
   MTASR_CHECK_ARG(dy && x && mean && rstd && gamma && rows > 0 && (dx_f32 || dx_bf16 || dgamma), "layernorm_bwd: bad arguments");
   MTASR_CHECK_ARG(D % 8 == 0 && D <= 32 * MAXV, "layernorm_bwd: D=%d must be a multiple of 8 and <= 1024", D);
-  int grid = grid_for(rows, 8);
-  if (grid > 2 * num_sms()) grid = 2 * num_sms();
-  layernorm_bwd_kernel<<<grid, 256, 2 * D * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres, rows, D, dx_f32, reinterpret_cast<__nv_bfloat16*>(dx_bf16),
-      dgamma, dbeta);
-  MTASR_COUNT_LAUNCH();
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dx_f32 || dx_bf16) {
+    layernorm_bwd_kernel<<<grid_for(rows, 8), 256, 0, st>>>(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres, rows, D, dx_f32,
+                                                           reinterpret_cast<__nv_bfloat16*>(dx_bf16));
+    MTASR_COUNT_LAUNCH();
+  }
+  if (dgamma || dbeta) {
+    const int gx = (D + 255) / 256;
+    int gy = static_cast<int>((rows + 63) / 64);
+    const int cap = (num_sms() * 4 + gx - 1) / gx;
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    layernorm_bwd_param_kernel<<<dim3(gx, gy), 256, 0, st>>>(dy, dy_dtype, x, x_dtype, mean, rstd, rows, D, dgamma, dbeta);
+    MTASR_COUNT_LAUNCH();
+  }
   MTASR_CHECK_LAUNCH("layernorm_bwd");
   return MTASR_OK;
 }

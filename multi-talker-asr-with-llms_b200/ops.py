@@ -40,6 +40,26 @@ def bf16_of(p: torch.Tensor) -> torch.Tensor:
     return val
 
 
+_cat_cache = {}
+
+
+def cat_cached(params, dtype):
+    """torch.cat(params, 0) converted to `dtype`, cached on the identities / versions of the parameters (the fused
+    QKV weight and bias are rebuilt only after an optimizer step changed them)."""
+    key = tuple(id(p) for p in params) + (dtype,)
+    sig = tuple((p._version, p.data_ptr()) for p in params)
+    hit = _cat_cache.get(key)
+    if hit is not None and hit[0] == sig and all(r() is p for r, p in zip(hit[1], params)):
+        return hit[2]
+    val = torch.cat([p.detach().to(dtype) for p in params], 0).contiguous()
+    try:
+        refs = tuple(weakref.ref(p) for p in params)
+    except TypeError:
+        return val
+    _cat_cache[key] = (sig, refs, val)
+    return val
+
+
 def _flat2d(x: torch.Tensor) -> torch.Tensor:
     return x.contiguous().view(-1, x.shape[-1])
 
@@ -197,8 +217,8 @@ class AttentionFn(Function):
         B, T, D = h.shape
         d = D // H
         hb = K.cast_bf16(_flat2d(h))
-        wqkv = torch.cat([bf16_of(wq), bf16_of(wk), bf16_of(wv)], 0)
-        bqkv = torch.cat([bq.detach().float(), bk.detach().float(), bv.detach().float()], 0)
+        wqkv = cat_cached((wq, wk, wv), BF)
+        bqkv = cat_cached((bq, bk, bv), F32)
         wob = bf16_of(wo)
         qkv = K.linear_fwd(hb, wqkv, bqkv)                                   # (B*T, 3D) bf16: [q | k | v], head-major
         scale = float(d) ** -0.5
