@@ -130,6 +130,16 @@ int mtasr_lse_finalize(const float* part, int64_t rows, int32_t n_tiles, float* 
  * out (B,T) i64 right-padded with pad_id, lengths (B) i32. */
 int mtasr_ctc_collapse(const int64_t* ids, int32_t B, int32_t T, int64_t blank_id, int64_t pad_id, int64_t* out,
                        int32_t* lengths, void* stream);
+/* Token segments of ref:models/mt_ctctoken_builder.py:56-157 on a greedy path (B,T) i64 with frame mask (B,T) u8 (1 = valid):
+ * seg_start / seg_end (B,T) i32 hold the first / last frame of every emitted segment, nseg (B) i32 their count. */
+int mtasr_ctc_segments(const int64_t* path, const uint8_t* mask, int32_t B, int32_t T, int64_t blank, int32_t* seg_start,
+                       int32_t* seg_end, int32_t* nseg, void* stream);
+/* out (B,Lmax,D) f32 = per-segment mean of x (B,T,D) f32 (0 beyond nseg); conf (B,Lmax) = clamp(1 - mean pblank, 0, 1) or NULL.
+ * Backward: dx (B,T,D) f32 (zero it first) receives dout / segment length on the frames of each segment. */
+int mtasr_segment_mean_fwd(const float* x, const float* pblank, const int32_t* seg_start, const int32_t* seg_end,
+                           const int32_t* nseg, int32_t B, int32_t T, int32_t D, int32_t Lmax, float* out, float* conf, void* stream);
+int mtasr_segment_mean_bwd(const float* dout, const int32_t* seg_start, const int32_t* seg_end, const int32_t* nseg, int32_t B,
+                           int32_t T, int32_t D, int32_t Lmax, float* dx, void* stream);
 /* dense (B,T,V) f32 <-> compact lattice columns (B,T,Lp) f32 (scatter ADDS into dense). */
 int mtasr_ctc_gather_cols(const float* dense, const int64_t* ys, const int64_t* ylens, int32_t B, int32_t T, int32_t V,
                           int32_t Lp, int32_t ys_ld, int64_t blank, float* out, void* stream);

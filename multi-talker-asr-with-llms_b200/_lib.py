@@ -58,6 +58,9 @@ SIGNATURES = {
     "mtasr_ctc_beta_bwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "mtasr_lse_finalize": (C.c_int, [_P, _I64, _I32, _P, _P, _P]),
     "mtasr_ctc_collapse": (C.c_int, [_P, _I32, _I32, _I64, _I64, _P, _P, _P]),
+    "mtasr_ctc_segments": (C.c_int, [_P, _P, _I32, _I32, _I64, _P, _P, _P, _P]),
+    "mtasr_segment_mean_fwd": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "mtasr_segment_mean_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "mtasr_ctc_gather_cols": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I64, _P, _P]),
     "mtasr_ctc_scatter_cols": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I64, _P, _P]),
     "mtasr_ctc_gather_rows": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _P, _P, _P]),

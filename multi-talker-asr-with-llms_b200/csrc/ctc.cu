@@ -396,6 +396,78 @@ __global__ void ctc_scatter_rows_kernel(const float* __restrict__ dwg, const flo
   if (threadIdx.x == 0 && db && dbg) atomicAdd(db + v, dbg[static_cast<long long>(b) * Lp + c]);
 }
 
+// ------------------------------------------------------------------------------------------------ token segments
+// Segmentation of ref:models/mt_ctctoken_builder.py:56-157 on the greedy path: a segment is a maximal run of one
+// non-blank token and is EMITTED when a blank follows it or the valid region ends; a token change without a blank
+// restarts the run and silently drops the previous one (reference behaviour, kept); scanning stops at the first
+// masked frame.  One thread per utterance (the scan is sequential and tiny).
+__global__ void ctc_segments_kernel(const long long* __restrict__ path, const unsigned char* __restrict__ mask, int B, int T,
+                                    long long blank, int* __restrict__ seg_start, int* __restrict__ seg_end,
+                                    int* __restrict__ nseg) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const long long* pr = path + static_cast<long long>(b) * T;
+  const unsigned char* mr = mask + static_cast<long long>(b) * T;
+  int* ss = seg_start + static_cast<long long>(b) * T;
+  int* se = seg_end + static_cast<long long>(b) * T;
+  long long prev = -1;
+  int cs = -1, ce = -1, n = 0;
+  for (int t = 0; t < T; ++t) {
+    if (!mr[t]) break;
+    const long long tok = pr[t];
+    if (tok == blank) {
+      if (cs >= 0) { ss[n] = cs; se[n] = ce; ++n; cs = -1; }
+      prev = -1;
+      continue;
+    }
+    if (prev < 0 || tok != prev) { cs = t; ce = t; prev = tok; }
+    else ce = t;
+  }
+  if (cs >= 0) { ss[n] = cs; se[n] = ce; ++n; }
+  nseg[b] = n;
+}
+
+// out[b][j][:] = mean over frames seg_start[b][j]..seg_end[b][j] of x[b][t][:]  (j < nseg[b], else 0); conf analog on a
+// per-frame scalar.  One CTA per (b, j).
+__global__ void segment_mean_fwd_kernel(const float* __restrict__ x, const float* __restrict__ pblank, const int* __restrict__ seg_start,
+                                        const int* __restrict__ seg_end, const int* __restrict__ nseg, int T, int D, int Lmax,
+                                        float* __restrict__ out, float* __restrict__ conf) {
+  const int b = blockIdx.y, j = blockIdx.x;
+  float* o = out + (static_cast<long long>(b) * Lmax + j) * D;
+  if (j >= nseg[b]) {
+    for (int c = threadIdx.x; c < D; c += blockDim.x) o[c] = 0.f;
+    if (threadIdx.x == 0 && conf) conf[static_cast<long long>(b) * Lmax + j] = 0.f;
+    return;
+  }
+  const int s = seg_start[static_cast<long long>(b) * T + j], e = seg_end[static_cast<long long>(b) * T + j];
+  const float inv = 1.f / static_cast<float>(e - s + 1);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float a = 0.f;
+    for (int t = s; t <= e; ++t) a += x[(static_cast<long long>(b) * T + t) * D + c];
+    o[c] = a * inv;
+  }
+  if (threadIdx.x == 0 && conf) {
+    float a = 0.f;
+    for (int t = s; t <= e; ++t) a += pblank[static_cast<long long>(b) * T + t];
+    conf[static_cast<long long>(b) * Lmax + j] = fminf(fmaxf(1.f - a * inv, 0.f), 1.f);
+  }
+}
+
+// dx[b][t][:] += dout[b][j][:] / len(j) for the frames of every emitted segment (dx zero-initialised; segments are disjoint)
+__global__ void segment_mean_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg_start,
+                                        const int* __restrict__ seg_end, const int* __restrict__ nseg, int T, int D, int Lmax,
+                                        float* __restrict__ dx) {
+  const int b = blockIdx.y, j = blockIdx.x;
+  if (j >= nseg[b]) return;
+  const int s = seg_start[static_cast<long long>(b) * T + j], e = seg_end[static_cast<long long>(b) * T + j];
+  const float inv = 1.f / static_cast<float>(e - s + 1);
+  const float* g = dout + (static_cast<long long>(b) * Lmax + j) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    const float v = g[c] * inv;
+    for (int t = s; t <= e; ++t) dx[(static_cast<long long>(b) * T + t) * D + c] = v;
+  }
+}
+
 static int pick_ns(int max_states) {
   if (max_states <= 64) return 2;
   if (max_states <= 128) return 4;
@@ -528,5 +600,36 @@ extern "C" int mtasr_ctc_scatter_rows(const float* dwg, const float* dbg, const 
       dwg, dbg, reinterpret_cast<const long long*>(ys), reinterpret_cast<const long long*>(ylens), B, Lp, D, ys_ld, blank, dw, db);
   g_launches.fetch_add(1);
   MTASR_CHECK_LAUNCH("ctc_scatter_rows");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_ctc_segments(const int64_t* path, const uint8_t* mask, int32_t B, int32_t T, int64_t blank, int32_t* seg_start,
+                                  int32_t* seg_end, int32_t* nseg, void* stream) {
+  MTASR_CHECK_ARG(path && mask && seg_start && seg_end && nseg && B > 0 && T > 0, "ctc_segments: bad arguments");
+  ctc_segments_kernel<<<(B + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(path), mask, B, T,
+                                                                                   blank, seg_start, seg_end, nseg);
+  g_launches.fetch_add(1);
+  MTASR_CHECK_LAUNCH("ctc_segments");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_segment_mean_fwd(const float* x, const float* pblank, const int32_t* seg_start, const int32_t* seg_end,
+                                      const int32_t* nseg, int32_t B, int32_t T, int32_t D, int32_t Lmax, float* out, float* conf,
+                                      void* stream) {
+  MTASR_CHECK_ARG(x && seg_start && seg_end && nseg && out && B > 0 && T > 0 && D > 0 && Lmax > 0, "segment_mean_fwd: bad arguments");
+  MTASR_CHECK_ARG(conf == nullptr || pblank != nullptr, "segment_mean_fwd: conf needs pblank");
+  segment_mean_fwd_kernel<<<dim3(Lmax, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, pblank, seg_start, seg_end, nseg, T, D, Lmax,
+                                                                                        out, conf);
+  g_launches.fetch_add(1);
+  MTASR_CHECK_LAUNCH("segment_mean_fwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_segment_mean_bwd(const float* dout, const int32_t* seg_start, const int32_t* seg_end, const int32_t* nseg,
+                                      int32_t B, int32_t T, int32_t D, int32_t Lmax, float* dx, void* stream) {
+  MTASR_CHECK_ARG(dout && seg_start && seg_end && nseg && dx && B > 0 && T > 0 && D > 0 && Lmax > 0, "segment_mean_bwd: bad arguments");
+  segment_mean_bwd_kernel<<<dim3(Lmax, B), 256, 0, static_cast<cudaStream_t>(stream)>>>(dout, seg_start, seg_end, nseg, T, D, Lmax, dx);
+  g_launches.fetch_add(1);
+  MTASR_CHECK_LAUNCH("segment_mean_bwd");
   return MTASR_OK;
 }

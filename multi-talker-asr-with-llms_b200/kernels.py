@@ -356,6 +356,33 @@ def ctc_collapse(ids: torch.Tensor, blank_id: int, pad_id: int):
     return out, lens
 
 
+def ctc_segments(path: torch.Tensor, mask: torch.Tensor, blank: int):
+    B, T = path.shape
+    path = path.contiguous().to(torch.int64)
+    m8 = mask.contiguous().to(torch.uint8)
+    ss = torch.empty(B, T, device=path.device, dtype=torch.int32)
+    se = torch.empty(B, T, device=path.device, dtype=torch.int32)
+    n = torch.empty(B, device=path.device, dtype=torch.int32)
+    check(_lib.load().mtasr_ctc_segments(_p(path), _p(m8), B, T, blank, _p(ss), _p(se), _p(n), _stream()), "mtasr_ctc_segments")
+    return ss, se, n
+
+
+def segment_mean_fwd(x: torch.Tensor, pblank, ss, se, n, Lmax: int):
+    B, T, D = x.shape
+    out = torch.empty(B, Lmax, D, device=x.device, dtype=torch.float32)
+    conf = torch.empty(B, Lmax, device=x.device, dtype=torch.float32) if pblank is not None else None
+    check(_lib.load().mtasr_segment_mean_fwd(_p(x), _p(pblank), _p(ss), _p(se), _p(n), B, T, D, Lmax, _p(out), _p(conf), _stream()),
+          "mtasr_segment_mean_fwd")
+    return out, conf
+
+
+def segment_mean_bwd(dout: torch.Tensor, ss, se, n, T: int):
+    B, Lmax, D = dout.shape
+    dx = torch.zeros(B, T, D, device=dout.device, dtype=torch.float32)
+    check(_lib.load().mtasr_segment_mean_bwd(_p(dout), _p(ss), _p(se), _p(n), B, T, D, Lmax, _p(dx), _stream()), "mtasr_segment_mean_bwd")
+    return dx
+
+
 def ctc_gather_cols(dense, ys, ylens, Lp, blank):
     B, T, V = dense.shape
     out = torch.empty(B, T, Lp, device=dense.device, dtype=torch.float32)

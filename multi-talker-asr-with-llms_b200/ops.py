@@ -514,6 +514,48 @@ def ctc_head_argmax(hs: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> to
     return am.view(B, T)
 
 
+def ctc_head_path_and_pblank(hs: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, blank: int):
+    """Greedy path (B,T) int64 and blank posterior (B,T) fp32 = exp(logit_blank - LSE) without the (B,T,V) tensor:
+    one fused vocab GEMM (row LSE + argmax partials) plus the blank column from the gathered-row GEMM."""
+    B, T, D = hs.shape
+    V = w.shape[0]
+    hb = K.cast_bf16(_flat2d(hs))
+    wb = bf16_of(w)
+    bf = bias.detach().float()
+    nt = K.gemm_n_tiles(V)
+    part = torch.empty(B * T, nt, 4, device=hs.device, dtype=F32)
+    K.gemm(K.Operand(hb, D), K.Operand(wb, D), B * T, V, D, None, bias=bf, mode=1, lse_part=part)
+    lse, am = K.lse_finalize(part, B * T, nt, want_lse=True, want_argmax=True)
+    ys = torch.zeros(B, 1, device=hs.device, dtype=torch.int64)
+    ylens = torch.zeros(B, device=hs.device, dtype=torch.int64)
+    wg, bg = K.ctc_gather_rows(wb, bf, ys, ylens, 64, blank)               # column 0 of every lattice = blank
+    glog = torch.empty(B, T, 64, device=hs.device, dtype=F32)
+    K.gemm(K.Operand(hb, D, sb0=T * D), K.Operand(wg, D, sb0=64 * D), T, 64, D, K.Out(glog, 64, sb0=T * 64), batch=(B, 1),
+           bias=bg, bias_sb0=64)
+    pblank = torch.exp(glog[..., 0] - lse.view(B, T))
+    return am.view(B, T), pblank.contiguous()
+
+
+class SegmentMeanFn(Function):
+    """Per-segment mean of frame features (ref:models/mt_ctctoken_builder.py:100-126) with gradient to the features."""
+
+    @staticmethod
+    def forward(ctx, x, pblank, ss, se, n, Lmax):
+        xf = x.detach().float().contiguous()
+        out, conf = K.segment_mean_fwd(xf, pblank, ss, se, n, Lmax)
+        ctx.save_for_backward(ss, se, n)
+        ctx.T = x.shape[1]
+        ctx.x_dtype = x.dtype
+        ctx.mark_non_differentiable(conf)
+        return out.to(x.dtype), conf
+
+    @staticmethod
+    def backward(ctx, dout, _dconf):
+        ss, se, n = ctx.saved_tensors
+        dx = K.segment_mean_bwd(dout.contiguous().float(), ss, se, n, ctx.T)
+        return dx.to(ctx.x_dtype), None, None, None, None, None
+
+
 def ctc_head_logits(hs: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     """Dense (B,T,V) fp32 logits for the API-compat methods CTC.logits/.softmax/.log_softmax (not on the hot path)."""
     return LinearFn.apply(hs, w, bias, K.ACT_NONE, None, F32)
