@@ -17,10 +17,16 @@ namespace mtasr {
 
 static constexpr float NEG_INF = -INFINITY;
 
+// log(exp a + exp b + exp c) on the SFU (ex2 / lg2 approximations, ~1e-7 relative): the recursion is one dependent chain
+// per time step, so the instruction count of this function IS the latency of the kernel.  The argument of the log lies in
+// [1, 3], where lg2.approx is accurate to a few ulp; tests pin loss and gradients to the fp64 oracle at 1e-5.
 __device__ __forceinline__ float lse3(float a, float b, float c) {
   const float m = fmaxf(a, fmaxf(b, c));
   if (m == NEG_INF) return NEG_INF;
-  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+  const float k = 1.4426950408889634f;
+  const float nm = -m * k;
+  const float sum = ex2_approx(fmaf(a, k, nm)) + ex2_approx(fmaf(b, k, nm)) + ex2_approx(fmaf(c, k, nm));
+  return fmaf(__log2f(sum), 0.6931471805599453f, m);
 }
 
 // ------------------------------------------------------------------------------------------------ alpha

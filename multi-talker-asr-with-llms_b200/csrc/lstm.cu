@@ -312,6 +312,7 @@ struct LstmBsP {
   __nv_bfloat16* dgates;      // (B,T,4Hs)   bwd out / exchange buffer
   unsigned int* bar;          // [S] group counters
   int B, T, Hs, ldw, G, U;
+  int dbg;                    // timing experiments only (MTASR_LSTM_DBG): 1 skip MMA, 2 skip exchange load, 4 skip barrier
 };
 
 __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_bs_kernel(const LstmBsP p) {
@@ -360,7 +361,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_bs_kernel(const LstmBsP 
     }
     float gsum[4] = {0.f, 0.f, 0.f, 0.f};
     if (t > 0) {
-      grid_wait(bar, static_cast<unsigned>(G) * static_cast<unsigned>(t));
+      if (!(p.dbg & 4)) grid_wait(bar, static_cast<unsigned>(G) * static_cast<unsigned>(t));
+      if (!(p.dbg & 2))
       for (int i = tid; i < nb * (Hs / 8); i += LTHREADS) {
         const int b = i / (Hs / 8), kc = i % (Hs / 8);
         *reinterpret_cast<uint4*>(Hsm + b * rs + kc * 8) =
@@ -372,7 +374,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_bs_kernel(const LstmBsP 
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[mi][q] = 0.f;
-      for (int ks = k_lo; ks < k_hi; ++ks) {
+      for (int ks = (p.dbg & 1) ? k_hi : k_lo; ks < k_hi; ++ks) {
         const int k0 = ks * 16;
         uint32_t hb0, hb1;
         ldsm_x2(smem_addr(Hsm + (lane & 7) * rs + k0 + ((lane >> 3) & 1) * 8), hb0, hb1);
@@ -624,6 +626,7 @@ extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw
       q.xg = xg; q.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16); q.h_bf16 = reinterpret_cast<__nv_bfloat16*>(h_bf16);
       q.h_f32 = h_f32; q.c_all = c_all; q.gates = gates; q.bar = barrier;
       q.B = B; q.T = T; q.Hs = Hs; q.ldw = ldw; q.G = G; q.U = Hs / G;
+      q.dbg = getenv("MTASR_LSTM_DBG") ? atoi(getenv("MTASR_LSTM_DBG")) : 0;
       if (cudaFuncSetAttribute(lstm_fwd_bs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bs)) != cudaSuccess)
         return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: cannot set smem attribute");
       if (cudaMemsetAsync(barrier, 0, sizeof(uint32_t) * S, st0) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: memset failed");
