@@ -9,8 +9,8 @@ through `ops`/`kernels` (tcgen05 GEMM, fused row kernels).
 Deliberate, documented differences:
   * compute is bf16 operands / fp32 accumulation with an fp32 residual stream, whatever the autocast state;
   * `output_attentions=True` raises (attention probabilities exist only tile-wise per head);
-  * the feature encoder has no backward: it is frozen in every reference run (ref:run.sh:231); asking for its
-    gradients raises instead of silently falling back;
+  * the conv feature encoder has no backward: it is frozen in every reference run (ref:run.sh:231); asking for its
+    gradients raises instead of silently falling back (the adapter, which feeds the LLM, does have one);
   * dropout / LayerDrop inside the encoder are not applied (parity and throughput runs use p=0; ref RNG streams
     cannot be reproduced anyway).
 """
@@ -72,7 +72,15 @@ class WavLMAdapter(nn.Module):
 
 class AdapterFn(torch.autograd.Function):
     """3 x [conv1d(D -> 2D, k=3, s=2, p=1) as implicit GEMM -> GLU]; returns (x8, x4) like the reference's adapter
-    (tap after layer index 1).  Backward is not implemented yet (the CTC-only loss never reaches the adapter)."""
+    (tap after layer index 1; ref:models/modeling_wavlm.py:223-254, hf:792-807).
+
+    Backward per layer (all contractions on the tcgen05 GEMM, no transposed-conv buffers):
+      dy      = GLU'(y) * dout                                   (glu_bwd kernel)
+      dW[tap] = dy^T xp[2t + tap]   for the 3 taps in one batched launch over a stride-2 row view of the padded input
+      db      = column sum of dy
+      dx[2m]   = dy[m] W_1                                        (odd padded positions: only the centre tap)
+      dx[2m+1] = dy[m] W_2 + dy[m+1] W_0                          (even padded positions: a 2-tap implicit GEMM over dy)
+    """
 
     @staticmethod
     def forward(ctx, x, mod, *params):
@@ -83,6 +91,7 @@ class AdapterFn(torch.autograd.Function):
             h = K.layernorm_fwd(h, mod.proj_layer_norm.weight.detach(), mod.proj_layer_norm.bias.detach(),
                                 mod.proj_layer_norm.eps, out_bf16=False, out_f32=True)[1]
         tap = None
+        saved, meta = [], []
         for i, layer in enumerate(mod.layers):
             conv = layer.conv
             B, T, D = h.shape
@@ -97,16 +106,74 @@ class AdapterFn(torch.autograd.Function):
             K.gemm(K.Operand(xp, s * D, sb1=Tpad * D, inner=D, phase=s, rows=Tpad // s), K.Operand(wk, k * D), Lout, C2, k * D,
                    K.Out(y, C2, sb1=Lout * C2), batch=(1, B), bias=None if conv.bias is None else conv.bias.detach().float())
             hb, hf = K.glu_fwd(y, out_f32=True)
+            saved += [xp, y]
+            meta.append((B, T, D, k, s, pad, Tpad, Lout, C2))
             h = hf
             if i == 1:
                 tap = hf
+        ctx.meta = meta
+        ctx.has_proj = mod.proj is not None
+        ctx.n_params = len(params)
+        ctx.has_bias = [layer.conv.bias is not None for layer in mod.layers]
+        ctx.save_for_backward(*saved, *[layer.conv.weight for layer in mod.layers])
         return h, tap
 
     @staticmethod
-    def backward(ctx, *grads):
-        raise NotImplementedError(
-            "mtasr_b200: the adapter backward (hf:803-807 conv+GLU) is not implemented yet; the CTC loss does not depend on "
-            "it.  Training losses that consume `last_hidden_state` are outside this round's scope (SURVEY 8f).")
+    def backward(ctx, d_last, d_tap):
+        if ctx.has_proj:
+            raise NotImplementedError("mtasr_b200: adapter backward with output_hidden_size != hidden_size (proj + LayerNorm in "
+                                      "front of the adapter) is not implemented; wavlm-large / base-plus do not use it")
+        n = len(ctx.meta)
+        saved = ctx.saved_tensors
+        weights = saved[2 * n:]
+        grads_w, grads_b = [None] * n, [None] * n
+        dh = d_last
+        for i in reversed(range(n)):
+            B, T, D, k, s, pad, Tpad, Lout, C2 = ctx.meta[i]
+            if (k, s, pad) != (3, 2, 1):
+                raise NotImplementedError("mtasr_b200: adapter backward is written for kernel 3 / stride 2 / padding 1 (HF default)")
+            xp, y = saved[2 * i], saved[2 * i + 1]
+            if i == 1 and d_tap is not None:
+                dh = d_tap if dh is None else dh + d_tap
+            if dh is None:
+                continue
+            w = weights[i]
+            dy = K.glu_bwd(y, dh.contiguous())                                  # (B, Lout, 2D) bf16
+            dy2 = dy.view(B * Lout, C2)
+            grads_b[i] = K.colsum(dy2) if ctx.has_bias[i] else None
+            # ---- weight gradient: rows flattened over (b, t) with one zero row per utterance so that row r of the padded
+            # dy pairs with row 2r (+ tap) of the padded input
+            dyz = K.pad_cast(dy, 0, Lout + 1)                                   # (B, Lout+1, 2D), last row of each utterance 0
+            assert Tpad == 2 * (Lout + 1)
+            rows = B * (Lout + 1)
+            xpe = torch.zeros(B * Tpad + 4, D, device=dy.device, dtype=BF)      # slack rows for the tap offsets
+            xpe[: B * Tpad] = xp.view(B * Tpad, D)
+            dwk = torch.empty(k, C2, D, device=dy.device, dtype=F32)
+            K.gemm(K.Operand(dyz, C2, major=1, rows=rows), K.Operand(xpe, 2 * D, major=1, sb0=D, rows=rows), C2, D, rows,
+                   K.Out(dwk, D, sb0=C2 * D), batch=(k, 1))
+            grads_w[i] = dwk.permute(1, 2, 0).contiguous()                      # (2D, D, 3) torch conv layout
+            # ---- input gradient
+            dx = torch.empty(B, T, D, device=dy.device, dtype=F32)
+            wt = ops.bf16_of(w)                                                 # (2D, D, 3)
+            w1 = wt[:, :, 1].contiguous()                                       # (2D, D): B(n=c, k=o) MN-major
+            n_even = (T + 1) // 2                                               # x rows 0,2,4,...  <- dy[m] W_1
+            K.gemm(K.Operand(dy, C2, sb1=Lout * C2, rows=Lout), K.Operand(w1, D, major=1), min(n_even, Lout), D, C2,
+                   K.Out(dx, 2 * D, sb1=T * D), batch=(1, B))
+            n_odd = T // 2                                                      # x rows 1,3,5,...  <- dy[m] W_2 + dy[m+1] W_0
+            if n_odd > 0:
+                w20 = torch.stack([wt[:, :, 2], wt[:, :, 0]], 0).contiguous().view(2 * C2, D)   # rows (tap', o): K index
+                K.gemm(K.Operand(dyz, C2, sb1=(Lout + 1) * C2, inner=C2, phase=1, rows=Lout + 1), K.Operand(w20, D, major=1),
+                       n_odd, D, 2 * C2, K.Out(dx, 2 * D, sb1=T * D, offset=D), batch=(1, B))
+            if n_even > Lout:                                                   # cannot happen for k3 s2 p1, kept as a guard
+                dx[:, 2 * Lout::2] = 0
+            dh = dx
+        out = [dh, None]
+        it = 0
+        for i in range(n):
+            out.append(grads_w[i])
+            if ctx.has_bias[i]:
+                out.append(grads_b[i])
+        return tuple(out)
 
 
 def relpos_bucket(rel: torch.Tensor, num_buckets: int, max_distance: int) -> torch.Tensor:
