@@ -358,7 +358,12 @@ __device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMa
   }
 }
 
-template <int CFG>
+// NCTA = 1: one CTA per 128 x block_n tile (tcgen05 cta_group::1).
+// NCTA = 2: a CTA PAIR (cluster of 2, same TPC) per 256 x block_n tile (cta_group::2, UMMA M = 256): each CTA loads its own
+// 128 rows of A and HALF of the B tile, the leader's MMA thread issues for both and each CTA's TMEM receives its 128 x
+// block_n accumulator -- per-CTA shared-memory operand traffic drops from 48 KB to 32 KB per 64-wide k-block, which is
+// what kept the single-CTA kernel (96 B/clk of operand reads next to the epilogue staging traffic) off the tensor peak.
+template <int CFG, int NCTA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux,
@@ -380,6 +385,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int cta_rank = NCTA == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = cta_rank == 0;
+  const int first_tile = blockIdx.x / NCTA, tile_step = gridDim.x / NCTA;   // tiles are per CTA (pair)
+  const int b_rows = p.block_n / NCTA;                                       // B-tile rows (N columns) held by this CTA
 
   if (warp == 0) {
     if (elect_one()) {
@@ -394,21 +403,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     if (elect_one()) {
       for (int i = 0; i < p.stages; ++i) {
-        mbar_init(&full_bar[i], 1);
+        mbar_init(&full_bar[i], NCTA);         // one producer arrival per CTA of the pair (on the leader's copy)
         mbar_init(&empty_bar[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tmem_full[i], 1);
-        mbar_init(&tmem_empty[i], EPI_WARPS);  // one arrive per epilogue warp
+        mbar_init(&tmem_empty[i], EPI_WARPS * NCTA);  // one arrive per epilogue warp of every CTA of the pair
       }
       for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
       fence_barrier_init();
     }
   } else if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (NCTA == 2) {
+      tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
+  if (NCTA == 2) cluster_sync_all();   // the peer's barriers must be initialised before any remote arrive / TMA signal
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
@@ -418,9 +433,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t stage_tx = A_STAGE_BYTES + p.block_n * BK * 2;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      const uint32_t stage_tx = NCTA * (A_STAGE_BYTES + b_rows * BK * 2);   // bytes of BOTH CTAs land on the leader's barrier
+      for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+        TileCoord t = decode_tile(p, tile);
+        t.m_tile = t.m_tile * NCTA + cta_rank;
         const int ab0 = p.a_use0 ? t.b0 : 0, ab1 = p.a_use1 ? t.b1 : 0;
         const int bb0 = p.b_use0 ? t.b0 : 0, bb1 = p.b_use1 ? t.b1 : 0;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
@@ -428,37 +444,57 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* sa = smem + stage * p.stage_bytes;
           uint8_t* sb = sa + A_STAGE_BYTES;
           uint64_t* bar = &full_bar[stage];
-          mbar_arrive_expect_tx(bar, stage_tx);
-          if (p.a_major == 0) {
-            const int kk = kb * BK;
-            const int tap = kk / p.a_inner;
-            const int c0 = kk - tap * p.a_inner;
-            const int ph = tap % p.a_phase;
-            const int dr = tap / p.a_phase;
-            tma_load_5d(sa, &tmap_a, bar, c0, ph, t.m_tile * BM + dr, ab0, ab1);
+          if (leader) mbar_arrive_expect_tx(bar, stage_tx);
+          const int n0 = t.n_tile * p.block_n + cta_rank * b_rows;
+          if (NCTA == 2) {
+            if (p.a_major == 0) {
+              const int kk = kb * BK;
+              const int tap = kk / p.a_inner;
+              const int c0 = kk - tap * p.a_inner;
+              const int ph = tap % p.a_phase;
+              const int dr = tap / p.a_phase;
+              tma_load_5d_pair(sa, &tmap_a, bar, c0, ph, t.m_tile * BM + dr, ab0, ab1);
+            } else {
+              tma_load_4d_pair(sa, &tmap_a, bar, t.m_tile * BM, kb * BK, ab0, ab1);
+              tma_load_4d_pair(sa + 8192, &tmap_a, bar, t.m_tile * BM + 64, kb * BK, ab0, ab1);
+            }
+            if (p.b_major == 0) {
+              tma_load_4d_pair(sb, &tmap_b, bar, kb * BK, n0, bb0, bb1);
+            } else {
+              for (int j = 0; j < b_rows / 64; ++j) tma_load_4d_pair(sb + j * 8192, &tmap_b, bar, n0 + j * 64, kb * BK, bb0, bb1);
+            }
+            if (!leader) mbar_arrive_leader(bar);
           } else {
-            tma_load_4d(sa, &tmap_a, bar, t.m_tile * BM, kb * BK, ab0, ab1);
-            tma_load_4d(sa + 8192, &tmap_a, bar, t.m_tile * BM + 64, kb * BK, ab0, ab1);
-          }
-          if (p.b_major == 0) {
-            tma_load_4d(sb, &tmap_b, bar, kb * BK, t.n_tile * p.block_n, bb0, bb1);
-          } else {
-            for (int j = 0; j < p.block_n / 64; ++j)
-              tma_load_4d(sb + j * 8192, &tmap_b, bar, t.n_tile * p.block_n + j * 64, kb * BK, bb0, bb1);
+            if (p.a_major == 0) {
+              const int kk = kb * BK;
+              const int tap = kk / p.a_inner;
+              const int c0 = kk - tap * p.a_inner;
+              const int ph = tap % p.a_phase;
+              const int dr = tap / p.a_phase;
+              tma_load_5d(sa, &tmap_a, bar, c0, ph, t.m_tile * BM + dr, ab0, ab1);
+            } else {
+              tma_load_4d(sa, &tmap_a, bar, t.m_tile * BM, kb * BK, ab0, ab1);
+              tma_load_4d(sa + 8192, &tmap_a, bar, t.m_tile * BM + 64, kb * BK, ab0, ab1);
+            }
+            if (p.b_major == 0) {
+              tma_load_4d(sb, &tmap_b, bar, kb * BK, n0, bb0, bb1);
+            } else {
+              for (int j = 0; j < b_rows / 64; ++j) tma_load_4d(sb + j * 8192, &tmap_b, bar, n0 + j * 64, kb * BK, bb0, bb1);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only for a pair)
+    if (leader && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t idesc = make_idesc_bf16(BM, p.block_n, p.a_major, p.b_major);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const uint32_t idesc = make_idesc_bf16(BM * NCTA, p.block_n, p.a_major, p.b_major);
+      for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
         const TileCoord t = decode_tile(p, tile);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -476,12 +512,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                                : make_smem_desc(sa + k * 2048, 8192, 1024);
             const uint64_t db = p.b_major == 0 ? make_smem_desc(sb + k * 32, 16, 1024)
                                                : make_smem_desc(sb + k * 2048, 8192, 1024);
-            umma_f16(d_tmem, da, db, idesc, (kb != t.kb0 || k != 0) ? 1u : 0u);
+            if (NCTA == 2) umma_f16_pair(d_tmem, da, db, idesc, (kb != t.kb0 || k != 0) ? 1u : 0u);
+            else umma_f16(d_tmem, da, db, idesc, (kb != t.kb0 || k != 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (NCTA == 2) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if (NCTA == 2) umma_commit_pair(&tmem_full[acc]);
+        else umma_commit(&tmem_full[acc]);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -498,8 +539,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
+      TileCoord t = decode_tile(p, tile);
+      t.m_tile = t.m_tile * NCTA + cta_rank;
       const long long batch = static_cast<long long>(t.b1) * p.batch0 + t.b0;
       const int row = t.m_tile * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
@@ -531,7 +573,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // all TMEM reads of this tile are done (tcgen05.wait::ld inside every group): hand the accumulator back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_leader(&tmem_empty[acc]);   // the leader's MMA thread waits for both CTAs' epilogues
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (mode == 1 && row_ok) {
         p.lse_part[((batch * p.M + row) * p.n_tiles + t.n_tile) * 2 + half] =
             make_float4(run_max, run_sum, __int_as_float(run_idx), 0.f);
@@ -543,10 +588,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 
   tc_fence_before();
+  if (NCTA == 2) cluster_sync_all();   // neither CTA may free TMEM / exit while the pair's MMAs or remote arrives are in flight
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (NCTA == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -555,10 +602,11 @@ typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtenso
 
 struct KernelEntry {
   int cfg;
-  GemmKernelFn fn;
+  GemmKernelFn fn;    // one CTA per tile
+  GemmKernelFn fn2;   // CTA pair per 256-row tile
 };
 #define MTASR_GEMM_CFG(mode, act, aux, res) \
-  { make_cfg(mode, act, aux, res), gemm_bf16_kernel<make_cfg(mode, act, aux, res)> }
+  { make_cfg(mode, act, aux, res), gemm_bf16_kernel<make_cfg(mode, act, aux, res), 1>, gemm_bf16_kernel<make_cfg(mode, act, aux, res), 2> }
 // the epilogue combinations the model issues (TMA-staged outputs); anything else runs the generic kernel
 static const KernelEntry kKernels[] = {
     MTASR_GEMM_CFG(0, 0, false, false),  // plain (+bias): QKV, every dgrad / wgrad, attention contractions, conv FE
@@ -572,7 +620,7 @@ static const KernelEntry kKernels[] = {
     MTASR_GEMM_CFG(0, 4, false, true),   // ReLU backward
     MTASR_GEMM_CFG(1, 0, false, false),  // row LSE / argmax partials: CTC head forward, greedy argmax
     MTASR_GEMM_CFG(2, 0, false, false),  // softmax regeneration: CTC head backward
-    {CFG_GENERIC, gemm_bf16_kernel<CFG_GENERIC>},
+    {CFG_GENERIC, gemm_bf16_kernel<CFG_GENERIC, 1>, gemm_bf16_kernel<CFG_GENERIC, 2>},
 };
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -700,7 +748,13 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   p.a_use1 = (d->a_sb1 != 0 && d->batch1 > 1);
   p.b_use0 = (d->b_sb0 != 0 && d->batch0 > 1);
   p.b_use1 = (d->b_sb1 != 0 && d->batch1 > 1);
-  p.m_tiles = (d->M + BM - 1) / BM;
+  // CTA pairs (256-row tiles, cta_group::2) whenever the M extent gives at least two full pairs of row tiles and each CTA's
+  // half of the B tile is a whole number of 64-wide swizzle chunks
+  const int m_tiles1 = (d->M + BM - 1) / BM;
+  const char* pair_env = getenv("MTASR_GEMM_PAIR");
+  const bool pair_allowed = pair_env == nullptr || pair_env[0] != '0';
+  const int ncta = (pair_allowed && bn >= 128 && m_tiles1 >= 4) ? 2 : 1;
+  p.m_tiles = (m_tiles1 + ncta - 1) / ncta;          // tiles of 128 * ncta rows
   p.n_tiles = (d->N + bn - 1) / bn;
   const long long nt = static_cast<long long>(p.m_tiles) * p.n_tiles * d->batch0 * d->batch1;
   MTASR_CHECK_ARG(nt < (1LL << 31), "gemm: too many tiles");
@@ -745,7 +799,7 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
     const uint64_t dims[4] = {static_cast<uint64_t>(d->K), rows, nb0b, nb1b};
     const uint64_t str[4] = {1, safe_b, p.b_use0 ? static_cast<uint64_t>(d->b_sb0) : safe_b,
                              p.b_use1 ? static_cast<uint64_t>(d->b_sb1) : safe_b};
-    const uint32_t box[4] = {BK, static_cast<uint32_t>(bn), 1, 1};
+    const uint32_t box[4] = {BK, static_cast<uint32_t>(bn / ncta), 1, 1};   // a CTA of a pair loads half of the B tile
     rc = encode_map(&mb, d->b, 4, dims, str, box, "B(k-major)");
   } else {
     const uint64_t rows = d->b_rows > 0 ? static_cast<uint64_t>(d->b_rows) : static_cast<uint64_t>(d->K);
@@ -796,7 +850,7 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
       d->batch0 == 1 && d->batch1 == 1 && d->alpha == 1.0f && p.num_kb >= 16 && getenv("MTASR_GEMM_NO_SPLITK") == nullptr) {
     // choose the split that best fills whole waves of SMs (wave quantisation: e.g. 500 tiles on 148 SMs run as 4 waves at
     // 84 % occupancy, 2 x 500 half-K items as 7 waves at 97 %), keeping >= 32 k-blocks (K >= 2048) per item
-    const int sms = num_sms();
+    const int sms = num_sms() / ncta;   // schedulable units: CTAs or CTA pairs
     auto eff = [&](int sp) {
       const long long items = static_cast<long long>(p.num_tiles) * sp;
       const long long waves = (items + sms - 1) / sms;
@@ -818,7 +872,7 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
         return set_error(MTASR_ERR_LAUNCH, "gemm: split-K memset failed");
     }
   }
-  p.stage_bytes = A_STAGE_BYTES + bn * BK * 2;
+  p.stage_bytes = A_STAGE_BYTES + (bn / ncta) * BK * 2;
   const int fixed = BAR_BYTES + BIAS_BYTES + EPI_WARPS * p.n_stg * STG_BYTES;
   int stages = (SMEM_LIMIT - fixed) / p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -832,22 +886,26 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
     for (const KernelEntry& k : kKernels) {
       cudaError_t e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
       if (e != cudaSuccess) attr_err = e;
+      e = cudaFuncSetAttribute(k.fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+      if (e != cudaSuccess) attr_err = e;
     }
   });
   if (attr_err != cudaSuccess)
     return set_error(MTASR_ERR_LAUNCH, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   // specialised kernel when the outputs are TMA-staged (mode 1 has no tensor output) and the residual is TMA-loaded
-  GemmKernelFn kernel = kKernels[sizeof(kKernels) / sizeof(kKernels[0]) - 1].fn;
+  const KernelEntry* entry = &kKernels[sizeof(kKernels) / sizeof(kKernels[0]) - 1];
   const bool special_ok = getenv("MTASR_GEMM_GENERIC") == nullptr && !d->accumulate &&
                           (d->mode == 1 || (p.tma_epi && (!d->residual || p.stg_res >= 0)));
   if (special_ok) {
     const int want = make_cfg(d->mode, d->mode == 0 ? d->act : 0, d->mode == 0 && d->aux != nullptr,
                               d->mode == 0 && d->residual != nullptr);
     for (const KernelEntry& k : kKernels)
-      if (k.cfg == want) kernel = k.fn;
+      if (k.cfg == want) entry = &k;
   }
+  GemmKernelFn kernel = ncta == 2 ? entry->fn2 : entry->fn;
 
-  const int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  const int units = num_sms() / ncta;
+  const int grid = (p.num_tiles < units ? p.num_tiles : units) * ncta;
   ProfRec rec{};
   bool prof = false;
   {
@@ -860,7 +918,24 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
     rec.flops = 2.0 * d->M * static_cast<double>(d->N) * d->K * d->batch0 * d->batch1;
     cudaEventRecord(rec.e0, st);
   }
-  kernel<<<grid, GEMM_THREADS, smem_bytes, st>>>(ma, mb, mc, maux, mr, p);
+  if (ncta == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, ma, mb, mc, maux, mr, p);
+    if (le != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "gemm: cluster launch failed: %s", cudaGetErrorString(le));
+  } else {
+    kernel<<<grid, GEMM_THREADS, smem_bytes, st>>>(ma, mb, mc, maux, mr, p);
+  }
   g_launches.fetch_add(1);
   if (prof) {
     cudaEventRecord(rec.e1, st);
