@@ -12,6 +12,8 @@
 // Exact two-pass softmax: pass A runs QK^T only and reduces the row maximum (no exponentials), pass B recomputes the
 // S tiles, forms P = exp(z - max) once, accumulates the row sum in registers and O += P V in TMEM -- no accumulator
 // rescaling, no second exponential; the extra QK^T pass is cheap because the kernel is SFU(exp)-bound, not MMA-bound.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -343,7 +345,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
 // dK_j / dV_j accumulate in TMEM over i and are stored once; dQ_i partials are added to an fp32 scratch with vector
 // reductions (red.global.add.v4.f32); dgate[q] = sum_k dZ * table and the Toeplitz table gradient (sums of gate * dZ
 // along diagonals, read back from the dS tile by 4 reducer warps and accumulated in shared memory) complete the bias path.
-static constexpr int ATB_THREADS = 384;
+static constexpr int ATB_THREADS = 512;   // 4 control warps + 2 softmax warpgroups (key columns 0-63 / 64-127) + 4 reducer warps
 
 struct AttnBwdP {
   int B, H, T, nq, nk;
@@ -358,6 +360,7 @@ struct AttnBwdP {
   float* dq32;             // (B*T, H*64) fp32, zero-initialised, receives dQ partial sums
   float* dgate;            // (B,H,T) zero-initialised (atomics)
   float* dtable;           // (H,2T-1) zero-initialised (atomics)
+  int dbg;                 // timing experiments only (MTASR_ATTN_DBG): 1 skip table-gradient diagonals, 2 skip dQ reductions
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -395,11 +398,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     if (elect_one()) {
       mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
       for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
-      mbar_init(sdp_full, 1); mbar_init(sdp_empty, 4);
-      for (int i = 0; i < 2; ++i) { mbar_init(&pds_full[i], 4); mbar_init(&ds_empty[i], 5); }   // MMA commit + 4 reducer warps
+      mbar_init(sdp_full, 1); mbar_init(sdp_empty, 8);
+      for (int i = 0; i < 2; ++i) { mbar_init(&pds_full[i], 8); mbar_init(&ds_empty[i], 5); }   // MMA commit + 4 reducer warps
       mbar_init(p_empty, 1);
       mbar_init(dq_full, 1); mbar_init(dq_empty, 4);
-      mbar_init(dkv_full, 1); mbar_init(dkv_empty, 4);
+      mbar_init(dkv_full, 1); mbar_init(dkv_empty, 8);
       fence_barrier_init();
     }
   } else if (warp == 2) {
@@ -496,44 +499,48 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         umma_commit(kv_empty);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ---------------------------------------------------------------- softmax / dZ warps: thread = query row
+  } else if (warp >= 4 && warp < 12) {
+    // ---------------------------------------------------------------- softmax / dZ warps: thread = query row; warpgroup
+    // `grp` owns key columns [64 grp, 64 grp + 64) of every tile (= one 64-key swizzle chunk of the P / dS staging)
     const int wq = warp & 3;
+    const int grp = (warp - 4) >> 2;
     const int r = wq * 32 + lane;
-    const int tid = threadIdx.x - 128;
+    const int tid = threadIdx.x - 128;             // 0..255 over both groups
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
     uint32_t sdp_ph = 0, pe_ph = 0, dse_ph[2] = {0, 0}, dkv_ph = 0;
     int db = 0;
     int cur_h = -1;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int jt = item % p.nk, h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       if (h != cur_h) {
         const float* trow = p.table + static_cast<long long>(h) * (2 * p.T - 1);
-        for (int i = tid; i < 2 * p.T - 1; i += 128) tbl_s[i] = trow[i] * LOG2E;
+        for (int i = tid; i < 2 * p.T - 1; i += 256) tbl_s[i] = trow[i] * LOG2E;
         cur_h = h;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       const int kl = p.klen ? min(p.klen[b], p.T) : p.T;
-      const int k0 = jt * AT_BK;
+      const int k0 = jt * AT_BK + grp * 64;
       const long long bh = static_cast<long long>(b) * p.H + h;
       for (int i = 0; i < nq; ++i) {
         const int q = i * AT_BQ + r;
         const bool q_ok = q < p.T;
         const int qc = q_ok ? q : p.T - 1;
         const float g = p.gate[bh * p.T + qc];
-        const float lse2 = p.lse[bh * p.T + qc] * LOG2E;
+        const float nlse2 = -p.lse[bh * p.T + qc] * LOG2E;
         const float delta = p.delta[bh * p.T + qc];
         const float* trel = tbl_s + (p.T - 1 - qc);
         float dg = 0.f;
         mbar_wait(sdp_full, sdp_ph);
         sdp_ph ^= 1;
         tc_fence_after();
+        uint8_t* pc = p_s + grp * 16384;
+        uint8_t* dc = ds_s + db * AT_P_BYTES + grp * 16384;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t sv[32], dv[32];
-          tmem_ld32(tm_s + lane_off + c * 32, sv);
-          tmem_ld32(tm_dp + lane_off + c * 32, dv);
+          uint32_t sv[16], dv[16];
+          tmem_ld16(tm_s + lane_off + grp * 64 + c * 16, sv);
+          tmem_ld16(tm_dp + lane_off + grp * 64 + c * 16, dv);
           tmem_ld_wait();
           if (c == 3) {   // all TMEM reads of this tile are in registers: the next S / dP may be issued
             tc_fence_before();
@@ -545,25 +552,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             pe_ph ^= 1;
             mbar_wait(&ds_empty[db], dse_ph[db] ^ 1);
             dse_ph[db] ^= 1;
-            g_s[db * 128 + r] = q_ok ? g : 0.f;
+            if (grp == 0) g_s[db * 128 + r] = q_ok ? g : 0.f;
           }
-          const int kb = k0 + c * 32;
-          float pe[32], de[32];
+          const int kb = k0 + c * 16;
+          float pe[16], de[16];
+          if (q_ok && kb + 16 <= kl) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const bool ok = q_ok && (kb + e < kl);
-            const float t = trel[kb + e];
-            const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, g * t) - lse2) : 0.f;
-            const float dz = pv * (__uint_as_float(dv[e]) - delta);
-            dg = fmaf(dz, t, dg);
-            pe[e] = pv;
-            de[e] = dz * p.scale;
+            for (int e = 0; e < 16; ++e) {
+              const float t = trel[kb + e];
+              const float pv = ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, fmaf(g, t, nlse2)));
+              const float dz = pv * (__uint_as_float(dv[e]) - delta);
+              dg = fmaf(dz, t, dg);
+              pe[e] = pv;
+              de[e] = dz * p.scale;
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const bool ok = q_ok && (kb + e < kl);
+              const float t = trel[kb + e];
+              const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, fmaf(g, t, nlse2))) : 0.f;
+              const float dz = pv * (__uint_as_float(dv[e]) - delta);
+              dg = fmaf(dz, t, dg);
+              pe[e] = pv;
+              de[e] = dz * p.scale;
+            }
           }
-          uint8_t* pc = p_s + (c >> 1) * 16384;
-          uint8_t* dc = ds_s + db * AT_P_BYTES + (c >> 1) * 16384;
 #pragma unroll
-          for (int g16 = 0; g16 < 4; ++g16) {
-            const uint32_t off = swz128(static_cast<uint32_t>(r * 128 + (c & 1) * 64 + g16 * 16));
+          for (int g16 = 0; g16 < 2; ++g16) {
+            const uint32_t off = swz128(static_cast<uint32_t>(r * 128 + c * 32 + g16 * 16));
             uint4 u;
             u.x = pack_bf16x2(pe[g16 * 8 + 0], pe[g16 * 8 + 1]); u.y = pack_bf16x2(pe[g16 * 8 + 2], pe[g16 * 8 + 3]);
             u.z = pack_bf16x2(pe[g16 * 8 + 4], pe[g16 * 8 + 5]); u.w = pack_bf16x2(pe[g16 * 8 + 6], pe[g16 * 8 + 7]);
@@ -579,34 +596,30 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         db ^= 1;
         if (q_ok && dg != 0.f) atomicAdd(p.dgate + bh * p.T + q, dg * 0.6931471805599453f);   // table was scaled by log2e
       }
-      // item epilogue: dK_j, dV_j (rows = keys of this tile) -> bf16 into dqkv
+      // item epilogue: group 0 stores dK_j, group 1 stores dV_j (rows = keys of this tile) as bf16 into dqkv
       mbar_wait(dkv_full, dkv_ph);
       dkv_ph ^= 1;
       tc_fence_after();
-      const int key = k0 + r;
+      const int key = jt * AT_BK + r;
+      {
+        const uint32_t src = grp == 0 ? tm_dk : tm_dv;
+        __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * p.T + (key < p.T ? key : 0)) * (3 * p.H * AT_D) +
+                             (grp == 0 ? 1 : 2) * p.H * AT_D + h * AT_D;
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        uint32_t a0[32], a1[32];
-        const uint32_t src = which == 0 ? tm_dk : tm_dv;
-        tmem_ld32(src + lane_off, a0);
-        tmem_ld32(src + lane_off + 32, a1);
-        tmem_ld_wait();
-        if (key < p.T) {
-          __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * p.T + key) * (3 * p.H * AT_D) + (which == 0 ? 1 : 2) * p.H * AT_D +
-                               h * AT_D;
+        for (int c = 0; c < 4; ++c) {
+          uint32_t a0[16];
+          tmem_ld16(src + lane_off + c * 16, a0);
+          tmem_ld_wait();
+          if (key < p.T) {
 #pragma unroll
-          for (int g16 = 0; g16 < 4; ++g16) {
-            uint4 u;
-            u.x = pack_bf16x2(__uint_as_float(a0[g16 * 8 + 0]), __uint_as_float(a0[g16 * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(a0[g16 * 8 + 2]), __uint_as_float(a0[g16 * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(a0[g16 * 8 + 4]), __uint_as_float(a0[g16 * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(a0[g16 * 8 + 6]), __uint_as_float(a0[g16 * 8 + 7]));
-            reinterpret_cast<uint4*>(dst)[g16] = u;
-            u.x = pack_bf16x2(__uint_as_float(a1[g16 * 8 + 0]), __uint_as_float(a1[g16 * 8 + 1]));
-            u.y = pack_bf16x2(__uint_as_float(a1[g16 * 8 + 2]), __uint_as_float(a1[g16 * 8 + 3]));
-            u.z = pack_bf16x2(__uint_as_float(a1[g16 * 8 + 4]), __uint_as_float(a1[g16 * 8 + 5]));
-            u.w = pack_bf16x2(__uint_as_float(a1[g16 * 8 + 6]), __uint_as_float(a1[g16 * 8 + 7]));
-            reinterpret_cast<uint4*>(dst)[4 + g16] = u;
+            for (int g16 = 0; g16 < 2; ++g16) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(a0[g16 * 8 + 0]), __uint_as_float(a0[g16 * 8 + 1]));
+              u.y = pack_bf16x2(__uint_as_float(a0[g16 * 8 + 2]), __uint_as_float(a0[g16 * 8 + 3]));
+              u.z = pack_bf16x2(__uint_as_float(a0[g16 * 8 + 4]), __uint_as_float(a0[g16 * 8 + 5]));
+              u.w = pack_bf16x2(__uint_as_float(a0[g16 * 8 + 6]), __uint_as_float(a0[g16 * 8 + 7]));
+              reinterpret_cast<uint4*>(dst)[c * 2 + g16] = u;
+            }
           }
         }
       }
@@ -614,7 +627,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(dkv_empty);
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ---------------------------------------------------------------- reducer warps: table-gradient diagonals + dQ drain
     const int wq = warp & 3;
     const int t = wq * 32 + lane;                 // 0..127
@@ -634,7 +647,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         // local diagonals dl = kk - qq: this thread owns dl = t - 127 (<= 0) and dl = t + 1 (>= 1, only t <= 126)
         const int base = (jt - i) * 128 + p.T - 1;
 #pragma unroll 1
-        for (int which = 0; which < 2; ++which) {
+        for (int which = (p.dbg & 1) ? 2 : 0; which < 2; ++which) {
           const int dl = which == 0 ? t - 127 : t + 1;
           if (dl > 127) continue;
           const int gidx = base + dl;
@@ -664,7 +677,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(dq_empty);
         const int q = i * AT_BQ + t;
-        if (q < p.T) {
+        if (q < p.T && !(p.dbg & 2)) {
           float* dst = p.dq32 + (static_cast<long long>(b) * p.T + q) * (p.H * AT_D) + h * AT_D;
 #pragma unroll
           for (int v4 = 0; v4 < 8; ++v4)
@@ -825,6 +838,7 @@ extern "C" int mtasr_attn_bwd(const void* qkv, const void* out, const void* dout
   p.gate = gate; p.table = table; p.klen = klen; p.lse = lse; p.delta = delta;
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.dq32 = dq32; p.dgate = dgate; p.dtable = dtable;
+  p.dbg = getenv("MTASR_ATTN_DBG") ? atoi(getenv("MTASR_ATTN_DBG")) : 0;
   const int smem = 6 * AT_TILE + 3 * AT_P_BYTES + 2 * attn_table_bytes(T) + 256 * 4 + 256;
   MTASR_CHECK_ARG(smem <= 232448, "attn_bwd: T=%d needs %d bytes of shared memory", T, smem);
   if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)

@@ -218,9 +218,19 @@ class WavLMModel(WavLMPreTrainedModel):
     def _prefix_mask(lengths: torch.Tensor, T: int) -> torch.Tensor:
         return torch.arange(T, device=lengths.device)[None, :] < lengths.to(torch.long)[:, None]
 
+    def _get_feature_vector_attention_mask(self, feature_vector_length: int, attention_mask, add_adapter=None):
+        """hf:661-679 restated without the (B, S) int64 cumulative sums (only their last element is used there): valid
+        length -> conv-stack (+ adapter) length arithmetic -> prefix mask."""
+        add_adapter = self.config.add_adapter if add_adapter is None else add_adapter
+        n = self._conv_lengths(attention_mask.sum(dim=-1))
+        if add_adapter:
+            for _ in range(self.config.num_adapter_layers):
+                n = torch.div(n - 1, self.config.adapter_stride, rounding_mode="floor") + 1
+        return self._prefix_mask(n, feature_vector_length)
+
     def _get_feature_vector_attention_mask_x0(self, feature_vector_length: int, attention_mask, add_adapter=None):
         """ref:models/modeling_wavlm.py:508-533 -- frame-rate (no adapter) prefix mask."""
-        n = self._conv_lengths(attention_mask.cumsum(dim=-1)[:, -1])
+        n = self._conv_lengths(attention_mask.sum(dim=-1))
         return self._prefix_mask(n, feature_vector_length)
 
     def _get_feat_extract_output_lengths_x4(self, input_lengths, add_adapter: Optional[bool] = None):
@@ -233,12 +243,12 @@ class WavLMModel(WavLMPreTrainedModel):
         return n
 
     def _get_feature_vector_attention_mask_x4(self, feature_vector_length: int, attention_mask, add_adapter=None):
-        n = self._get_feat_extract_output_lengths_x4(attention_mask.cumsum(dim=-1)[:, -1], add_adapter=add_adapter)
+        n = self._get_feat_extract_output_lengths_x4(attention_mask.sum(dim=-1), add_adapter=add_adapter)
         return self._prefix_mask(n, feature_vector_length)
 
     def get_downsampled_feature_mask(self, feature_vector_length: int, attention_mask, extra_total_stride: int = 4):
         """ref:models/modeling_wavlm.py:467-506."""
-        n = self._conv_lengths(attention_mask.cumsum(dim=-1)[:, -1])
+        n = self._conv_lengths(attention_mask.sum(dim=-1))
         if extra_total_stride > 1:
             n = torch.div(n, extra_total_stride, rounding_mode="floor")
         lengths = n.to(torch.long).clamp_min(0).clamp_max(feature_vector_length)
