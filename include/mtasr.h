@@ -164,6 +164,14 @@ int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t
                         const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D, float* dx_f32,
                         void* dx_bf16, float* dgamma, float* dbeta, void* stream);
 int mtasr_cast_f32_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* fp32-accurate GEMM mode (north_star tolerance "<= 1e-4 in fp32"; the reference's fp32 run is torch fp32 matmul,
+ * ref:models/modeling_wavlm.py:412-465 outside autocast).  x (n fp32 values, rows of chunks of c values, c % 8 == 0)
+ * -> y (terms*n bf16).  terms 3: every chunk becomes [lo | hi | hi] (order 0, A-side operand) or [hi | lo | hi]
+ * (order 1, B-side), hi = bf16(x), lo = bf16(x - hi): one bf16 GEMM over the 3x longer contraction evaluates
+ * a_lo b_hi + a_hi b_lo + a_hi b_hi with fp32 accumulation (~2^-17 per product; small products first, because the
+ * tensor core's accumulation truncates).  terms 6: three-way split x = x1 + x2 + x3, A side [a3|a2|a1|a2|a1|a1],
+ * B side [b1|b2|b3|b1|b2|b1] (all products down to 2^-24). */
+int mtasr_split_bf16(const float* x, int64_t n, int32_t c, int32_t order, int32_t terms, void* y_bf16, void* stream);
 /* out[n] = sum_m x[m][n] (bias gradients) */
 int mtasr_colsum(const void* x, int32_t dtype, int64_t M, int32_t N, int64_t ld, float* out, void* stream);
 /* gru_rel_pos gate of hf:167-176 for every (b, t, head), head_dim 64: wab (128) = [sum of weight rows 0..3 | rows 4..7]
@@ -179,6 +187,9 @@ int mtasr_relpos_gate_bwd(const void* x, int32_t x_dtype, const float* wab, cons
  * S (B,H,T,Tp) f32, gate (B,H,T) f32, table (H,2T-1) f32, klen (B) i32 or NULL, P (B,H,T,Tp) bf16. */
 int mtasr_attn_softmax_fwd(const float* S, const float* gate, const float* table, const int32_t* klen, int32_t B,
                            int32_t H, int32_t T, int32_t Tp, float scale, void* P_bf16, void* stream);
+/* same softmax, written as the split A-side operand Ps (B,H,T,terms*Tp) bf16 (terms 3 or 6, see mtasr_split_bf16). */
+int mtasr_attn_softmax_fwd_split(const float* S, const float* gate, const float* table, const int32_t* klen, int32_t B,
+                                 int32_t H, int32_t T, int32_t Tp, float scale, int32_t terms, void* Ps_bf16, void* stream);
 /* dS = scale * P*(dP - rowdot) bf16; dgate (B,H,T); dtable (H,2T-1) ACCUMULATED (zero it first). */
 int mtasr_attn_softmax_bwd(const void* P_bf16, const float* dP, const float* gate, const float* table, int32_t B,
                            int32_t H, int32_t T, int32_t Tp, float scale, void* dS_bf16, float* dgate, float* dtable,
@@ -227,6 +238,9 @@ int mtasr_conv0_fwd(const float* x, const float* w, const float* bias, const flo
                     void* stream);
 int mtasr_groupnorm_gelu(const float* x, const float* gamma, const float* beta, float eps, int32_t B, int32_t L, int32_t C,
                          float* mean_ws, float* rstd_ws, void* y_bf16, void* stream);
+/* same, fp32 output (fp32-accurate parity mode) */
+int mtasr_groupnorm_gelu_f32(const float* x, const float* gamma, const float* beta, float eps, int32_t B, int32_t L,
+                             int32_t C, float* mean_ws, float* rstd_ws, float* y_f32, void* stream);
 /* du = dy * act'(.) as bf16: act 3 = GELU from the saved pre-activation, act 4 = ReLU from the saved output. */
 int mtasr_act_bwd(const void* dy, int32_t dy_dtype, const void* src_bf16, int32_t act, int64_t n, void* du_bf16,
                   void* stream);

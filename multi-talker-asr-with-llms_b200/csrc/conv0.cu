@@ -132,7 +132,7 @@ groupnorm_stats_kernel(const float* __restrict__ x, int L, int C, float eps, flo
 __global__ void groupnorm_gelu_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                       const float* __restrict__ rstd, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, int B, int L, int C,
-                                      __nv_bfloat16* __restrict__ y) {
+                                      __nv_bfloat16* __restrict__ y, float* __restrict__ y32) {
   const long long n2 = static_cast<long long>(B) * L * (C / 2);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n2;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -142,7 +142,8 @@ __global__ void groupnorm_gelu_kernel(const float* __restrict__ x, const float* 
     const float2 v = *reinterpret_cast<const float2*>(x + bl * C + c);
     const float o0 = gelu_fast_f((v.x - mean[b * C + c]) * rstd[b * C + c] * gamma[c] + beta[c]);
     const float o1 = gelu_fast_f((v.y - mean[b * C + c + 1]) * rstd[b * C + c + 1] * gamma[c + 1] + beta[c + 1]);
-    *reinterpret_cast<uint32_t*>(y + bl * C + c) = pack_bf16x2(o0, o1);
+    if (y) *reinterpret_cast<uint32_t*>(y + bl * C + c) = pack_bf16x2(o0, o1);
+    if (y32) *reinterpret_cast<float2*>(y32 + bl * C + c) = make_float2(o0, o1);
   }
 }
 
@@ -169,9 +170,9 @@ extern "C" int mtasr_conv0_fwd(const float* x, const float* w, const float* bias
   return MTASR_OK;
 }
 
-extern "C" int mtasr_groupnorm_gelu(const float* x, const float* gamma, const float* beta, float eps, int32_t B,
-                                    int32_t L, int32_t C, float* mean_ws, float* rstd_ws, void* y_bf16, void* stream) {
-  MTASR_CHECK_ARG(x && gamma && beta && mean_ws && rstd_ws && y_bf16 && B > 0 && L > 0 && C > 0 && C % 2 == 0,
+static int groupnorm_gelu_launch(const float* x, const float* gamma, const float* beta, float eps, int32_t B, int32_t L,
+                                 int32_t C, float* mean_ws, float* rstd_ws, void* y_bf16, float* y_f32, void* stream) {
+  MTASR_CHECK_ARG(x && gamma && beta && mean_ws && rstd_ws && (y_bf16 || y_f32) && B > 0 && L > 0 && C > 0 && C % 2 == 0,
                   "groupnorm_gelu: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   groupnorm_stats_kernel<<<dim3((C + 31) / 32, B), 256, 0, st>>>(x, L, C, eps, mean_ws, rstd_ws);
@@ -181,8 +182,20 @@ extern "C" int mtasr_groupnorm_gelu(const float* x, const float* gamma, const fl
   const long long cap = static_cast<long long>(num_sms()) * 8;
   if (grid > cap) grid = cap;
   groupnorm_gelu_kernel<<<static_cast<unsigned>(grid), 256, 0, st>>>(x, mean_ws, rstd_ws, gamma, beta, B, L, C,
-                                                                     reinterpret_cast<__nv_bfloat16*>(y_bf16));
+                                                                     reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32);
   MTASR_COUNT_LAUNCH();
   MTASR_CHECK_LAUNCH("groupnorm_gelu");
   return MTASR_OK;
+}
+
+extern "C" int mtasr_groupnorm_gelu(const float* x, const float* gamma, const float* beta, float eps, int32_t B,
+                                    int32_t L, int32_t C, float* mean_ws, float* rstd_ws, void* y_bf16, void* stream) {
+  MTASR_CHECK_ARG(y_bf16 != nullptr, "groupnorm_gelu: bad arguments");
+  return groupnorm_gelu_launch(x, gamma, beta, eps, B, L, C, mean_ws, rstd_ws, y_bf16, nullptr, stream);
+}
+
+extern "C" int mtasr_groupnorm_gelu_f32(const float* x, const float* gamma, const float* beta, float eps, int32_t B,
+                                        int32_t L, int32_t C, float* mean_ws, float* rstd_ws, float* y_f32, void* stream) {
+  MTASR_CHECK_ARG(y_f32 != nullptr, "groupnorm_gelu_f32: bad arguments");
+  return groupnorm_gelu_launch(x, gamma, beta, eps, B, L, C, mean_ws, rstd_ws, nullptr, y_f32, stream);
 }

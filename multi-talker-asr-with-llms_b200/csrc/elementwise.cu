@@ -213,6 +213,48 @@ __global__ void cast_tail_kernel(const float* __restrict__ x, __nv_bfloat16* __r
   if (i < n) y[i] = f2bf(x[i]);
 }
 
+// fp32 -> bf16 operand split for the fp32-accurate GEMM mode.  terms = 3: x = hi + lo + O(2^-18 |x|), every chunk of `c`
+// consecutive fp32 values of a row becomes [lo | hi | hi] (order 0, A side) / [hi | lo | hi] (order 1, B side), so ONE
+// bf16 GEMM over the 3x longer contraction evaluates a_lo b_hi + a_hi b_lo + a_hi b_hi with fp32 accumulation.
+// terms = 6: three-way split x = x1 + x2 + x3 + O(2^-27 |x|), A side [a3|a2|a1|a2|a1|a1], B side [b1|b2|b3|b1|b2|b1]
+// = all products down to 2^-24.
+__device__ __forceinline__ void split_parts(const float (&t)[8], float (&p1)[8], float (&p2)[8], float (&p3)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    p1[j] = bf2f(f2bf(t[j]));
+    const float r1 = t[j] - p1[j];
+    p2[j] = bf2f(f2bf(r1));
+    p3[j] = r1 - p2[j];
+  }
+}
+__global__ void split_bf16_kernel(const float* __restrict__ x, long long n8, int c8, int order, int terms,
+                                  __nv_bfloat16* __restrict__ y) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float t[8], p1[8], p2[8], p3[8];
+    ld8(x, MTASR_DT_F32, i * 8, t);
+    split_parts(t, p1, p2, p3);
+    const long long chunk = i / c8;
+    const int off = static_cast<int>(i % c8) * 8;
+    const int cs = c8 * 8;
+    __nv_bfloat16* o = y + chunk * (static_cast<long long>(terms) * cs) + off;
+    // small products first: the tensor core adds every K=16 group into the fp32 accumulator with truncation, so the
+    // error grows with (number of accumulation steps) x |accumulator|; the low-order terms are accumulated while the
+    // accumulator is still ~2^-8 / 2^-16 of its final size and only the x1 y1 chain runs at full magnitude.
+    if (terms == 3) {
+      st8_bf16(o, order == 0 ? p2 : p1);
+      st8_bf16(o + cs, order == 0 ? p1 : p2);
+      st8_bf16(o + 2 * cs, p1);
+    } else if (order == 0) {
+      st8_bf16(o, p3); st8_bf16(o + cs, p2); st8_bf16(o + 2 * cs, p1);
+      st8_bf16(o + 3 * cs, p2); st8_bf16(o + 4 * cs, p1); st8_bf16(o + 5 * cs, p1);
+    } else {
+      st8_bf16(o, p1); st8_bf16(o + cs, p2); st8_bf16(o + 2 * cs, p3);
+      st8_bf16(o + 3 * cs, p1); st8_bf16(o + 4 * cs, p2); st8_bf16(o + 5 * cs, p1);
+    }
+  }
+}
+
 // out[n] += sum_m x[m][n]  (bias gradients).  Vector path (N % 8 == 0, 16-byte aligned rows): each thread owns 8
 // consecutive columns (one 128-bit load per row for bf16, two for fp32), 8 row-lanes per CTA, 4 rows in flight per
 // thread; CTA partials are combined in smem and added with one atomic per column.
@@ -432,7 +474,7 @@ relpos_gate_bwd_kernel(const void* __restrict__ x, int x_dtype, const float* __r
 __global__ void __launch_bounds__(256)
 attn_softmax_fwd_kernel(const float* __restrict__ S, const float* __restrict__ gate, const float* __restrict__ table,
                         const int* __restrict__ klen, int B, int H, int T, int Tp, float scale,
-                        __nv_bfloat16* __restrict__ P) {
+                        __nv_bfloat16* __restrict__ P, int terms) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
@@ -445,7 +487,7 @@ attn_softmax_fwd_kernel(const float* __restrict__ S, const float* __restrict__ g
     const float g = gate[row];
     const float* srow = S + row * Tp;
     const float* trow = table + static_cast<long long>(h) * (2 * T - 1) + (T - 1 - q);
-    __nv_bfloat16* prow = P + row * Tp;
+    __nv_bfloat16* prow = P + row * Tp * terms;   // terms 1: plain bf16 P; 3 / 6: split A-side operand (split_bf16_kernel)
     float m = -INFINITY;
     for (int k = lane; k < kl; k += 32) m = fmaxf(m, srow[k] * scale + g * trow[k]);
     m = warp_max(m);
@@ -456,7 +498,24 @@ attn_softmax_fwd_kernel(const float* __restrict__ S, const float* __restrict__ g
     for (int k = lane; k < Tp; k += 32) {
       float p = 0.f;
       if (k < kl) p = __expf(srow[k] * scale + g * trow[k] - m) * inv;
-      prow[k] = f2bf(p);
+      const __nv_bfloat16 p1 = f2bf(p);
+      prow[k] = p1;
+      if (terms > 1) {   // A-side operand of the fp32-accurate P V contraction
+        const float r1 = p - bf2f(p1);
+        const __nv_bfloat16 p2 = f2bf(r1);
+        if (terms == 3) {            // [lo | hi | hi]
+          prow[k] = p2;
+          prow[Tp + k] = p1;
+          prow[2 * Tp + k] = p1;
+        } else {                     // [p3 | p2 | p1 | p2 | p1 | p1]
+          prow[k] = f2bf(r1 - bf2f(p2));
+          prow[Tp + k] = p2;
+          prow[2 * Tp + k] = p1;
+          prow[3 * Tp + k] = p2;
+          prow[4 * Tp + k] = p1;
+          prow[5 * Tp + k] = p1;
+        }
+      }
     }
   }
 }
@@ -701,9 +760,34 @@ extern "C" int mtasr_attn_softmax_fwd(const float* S, const float* gate, const f
   MTASR_CHECK_ARG(S && gate && table && P && B > 0 && H > 0 && T > 0 && Tp >= T, "attn_softmax_fwd: bad arguments");
   const long long rows = static_cast<long long>(B) * H * T;
   attn_softmax_fwd_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      S, gate, table, klen, B, H, T, Tp, scale, reinterpret_cast<__nv_bfloat16*>(P));
+      S, gate, table, klen, B, H, T, Tp, scale, reinterpret_cast<__nv_bfloat16*>(P), 1);
   MTASR_COUNT_LAUNCH();
   MTASR_CHECK_LAUNCH("attn_softmax_fwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_attn_softmax_fwd_split(const float* S, const float* gate, const float* table, const int32_t* klen,
+                                            int32_t B, int32_t H, int32_t T, int32_t Tp, float scale, int32_t terms,
+                                            void* Ps, void* stream) {
+  MTASR_CHECK_ARG(S && gate && table && Ps && B > 0 && H > 0 && T > 0 && Tp >= T && (terms == 3 || terms == 6),
+                  "attn_softmax_fwd_split: bad arguments");
+  const long long rows = static_cast<long long>(B) * H * T;
+  attn_softmax_fwd_kernel<<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      S, gate, table, klen, B, H, T, Tp, scale, reinterpret_cast<__nv_bfloat16*>(Ps), terms);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("attn_softmax_fwd_split");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_split_bf16(const float* x, int64_t n, int32_t c, int32_t order, int32_t terms, void* y_bf16, void* stream) {
+  MTASR_CHECK_ARG(x && y_bf16 && n > 0 && c > 0 && c % 8 == 0 && n % c == 0 && (order == 0 || order == 1) && (terms == 3 || terms == 6),
+                  "split_bf16: n=%lld must be a multiple of the chunk c=%d, c a multiple of 8, terms 3 or 6", static_cast<long long>(n), c);
+  MTASR_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_bf16) & 15) == 0, "split_bf16: unaligned pointer");
+  const long long n8 = n / 8;
+  split_bf16_kernel<<<grid_for(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n8, c / 8, order, terms,
+                                                                                       reinterpret_cast<__nv_bfloat16*>(y_bf16));
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("split_bf16");
   return MTASR_OK;
 }
 

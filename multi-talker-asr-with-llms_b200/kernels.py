@@ -216,6 +216,25 @@ def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def split_bf16(x: torch.Tensor, chunk: int, order: int, terms: int = 3) -> torch.Tensor:
+    """fp32 (..., n*chunk) -> bf16 (..., n*terms*chunk) split operand (order 0 = A side, 1 = B side; include/mtasr.h)."""
+    if x.dtype != torch.float32:
+        raise TypeError("split_bf16 takes fp32")
+    x = x.contiguous()
+    if x.shape[-1] % chunk:
+        raise ValueError(f"split_bf16: last dim {x.shape[-1]} is not a multiple of the chunk {chunk}")
+    y = empty_act(tuple(x.shape[:-1]) + (terms * x.shape[-1],), torch.bfloat16, x.device)
+    check(_lib.load().mtasr_split_bf16(_p(x), x.numel(), chunk, order, terms, _p(y), _stream()), "mtasr_split_bf16")
+    return y
+
+
+def attn_softmax_fwd_split(S, gate, table, klen, B, H, T, Tp, scale, terms):
+    Ps = torch.empty(B, H, T, terms * Tp, device=S.device, dtype=torch.bfloat16)
+    check(_lib.load().mtasr_attn_softmax_fwd_split(_p(S), _p(gate), _p(table), _p(klen), B, H, T, Tp, scale, terms, _p(Ps), _stream()),
+          "mtasr_attn_softmax_fwd_split")
+    return Ps
+
+
 def colsum(x: torch.Tensor) -> torch.Tensor:
     M, N = x.shape
     out = torch.empty(N, device=x.device, dtype=torch.float32)
@@ -443,10 +462,15 @@ def conv0_fwd(x: torch.Tensor, w: torch.Tensor, bias, gamma, beta, eps: float, k
     return y
 
 
-def groupnorm_gelu(x: torch.Tensor, gamma, beta, eps: float) -> torch.Tensor:
+def groupnorm_gelu(x: torch.Tensor, gamma, beta, eps: float, out_f32: bool = False) -> torch.Tensor:
     B, L, Cc = x.shape
     mean = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
     rstd = torch.empty(B, Cc, device=x.device, dtype=torch.float32)
+    if out_f32:
+        y = torch.empty(B, L, Cc, device=x.device, dtype=torch.float32)
+        check(_lib.load().mtasr_groupnorm_gelu_f32(_p(x), _p(gamma), _p(beta), eps, B, L, Cc, _p(mean), _p(rstd), _p(y), _stream()),
+              "mtasr_groupnorm_gelu_f32")
+        return y
     y = empty_act((B, L, Cc), torch.bfloat16, x.device)
     check(_lib.load().mtasr_groupnorm_gelu(_p(x), _p(gamma), _p(beta), eps, B, L, Cc, _p(mean), _p(rstd), _p(y), _stream()),
           "mtasr_groupnorm_gelu")

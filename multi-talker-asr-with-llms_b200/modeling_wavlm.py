@@ -36,6 +36,7 @@ from transformers.utils import ModelOutput
 
 from . import kernels as K
 from . import ops
+from . import precise
 
 BF, F32 = torch.bfloat16, torch.float32
 
@@ -393,6 +394,9 @@ class WavLMModel(WavLMPreTrainedModel):
         if self.adapter is None:
             raise ValueError("WavLMModel requires config.add_adapter=True (as the reference does, ref:models/modeling_wavlm.py:452-461)")
 
+        if precise.get_precision() == "fp32":
+            return self._forward_fp32(input_values, attention_mask, mask_time_indices, output_hidden_states, return_dict)
+
         feats = self._feature_extractor_fwd(input_values)                    # (B,T,C) bf16
         B, T, C = feats.shape
         fmask = None
@@ -411,3 +415,54 @@ class WavLMModel(WavLMPreTrainedModel):
             return (last, normed_f) + ((all_h,) if all_h is not None else ())
         return WavLMBaseModelOutput(last_hidden_state=last, encoder_hidden_state=enc_out, wavlm_down_hidden_states=down,
                                     extract_features=normed_f, hidden_states=all_h, attentions=None)
+
+    def _forward_fp32(self, input_values, attention_mask, mask_time_indices, output_hidden_states, return_dict):
+        """Same graph as `forward` with fp32 activations and split-operand (3 x bf16) contractions (precise.py): the
+        "<= 1e-4 in fp32" parity mode.  Forward only."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("mtasr_b200: precision 'fp32' is a forward-only parity mode; wrap the call in torch.no_grad() "
+                                      "(training runs use the bf16-operand path)")
+        cfg = self.config
+        with torch.no_grad():
+            feats = precise.feature_extractor(self, input_values)                # (B,T,C) fp32
+            B, T, C = feats.shape
+            fmask = None
+            if attention_mask is not None:
+                fmask = self._get_feature_vector_attention_mask(T, attention_mask, add_adapter=False)
+            fp = self.feature_projection
+            normed = precise.layer_norm(feats, fp.layer_norm)
+            hidden = precise.linear(normed, fp.projection.weight, fp.projection.bias)
+            hidden = self._mask_hidden_states(hidden, mask_time_indices=mask_time_indices, attention_mask=fmask)
+            enc = self.encoder
+            klen = None
+            if fmask is not None:
+                hidden = hidden * fmask.unsqueeze(-1).to(hidden.dtype)
+                klen = fmask.sum(1).to(torch.int32).contiguous()
+            conv = enc.pos_conv_embed.conv
+            hidden = precise.pos_conv(hidden.contiguous(), conv.weight, conv.bias, conv.groups)
+            if not cfg.do_stable_layer_norm:
+                hidden = precise.layer_norm(hidden, enc.layer_norm)
+            table = self._relpos_table(T, hidden.device)
+            all_h = () if output_hidden_states else None
+            for layer in enc.layers:
+                if output_hidden_states:
+                    all_h = all_h + (hidden,)
+                at, ff = layer.attention, layer.feed_forward
+                if cfg.do_stable_layer_norm:
+                    h1 = precise.layer_norm(hidden, layer.layer_norm)
+                    hidden = precise.attention(h1, hidden, at, self._gate(h1, at), table, klen, at.num_heads)
+                    h2 = precise.layer_norm(hidden, layer.final_layer_norm)
+                    hidden = precise.ffn(h2, hidden, ff)
+                else:
+                    y = precise.attention(hidden, hidden, at, self._gate(hidden, at), table, klen, at.num_heads)
+                    y = precise.layer_norm(y, layer.layer_norm)
+                    hidden = precise.layer_norm(precise.ffn(y, y, ff), layer.final_layer_norm)
+            if cfg.do_stable_layer_norm:
+                hidden = precise.layer_norm(hidden, enc.layer_norm)
+            if output_hidden_states:
+                all_h = all_h + (hidden,)
+            last, down = precise.adapter(self.adapter, hidden)
+        if not return_dict:
+            return (last, normed) + ((all_h,) if all_h is not None else ())
+        return WavLMBaseModelOutput(last_hidden_state=last, encoder_hidden_state=hidden, wavlm_down_hidden_states=down,
+                                    extract_features=normed, hidden_states=all_h, attentions=None)

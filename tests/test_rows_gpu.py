@@ -125,3 +125,35 @@ def test_colsum_shapes(cuda, M, N, dt):
     torch.manual_seed(4)
     x = torch.randn(M, N, device=cuda).to(dt)
     assert _rel(Kn.colsum(x), x.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("terms", [3, 6])
+@pytest.mark.parametrize("order", [0, 1])
+def test_split_bf16_bit_exact_and_gemm_accuracy(cuda, order, terms):
+    """mtasr_split_bf16: x1 = bf16(x), x2 = bf16(x - x1), x3 = bf16(x - x1 - x2) laid out per chunk in the A-side /
+    B-side product order -- bit-exact against the same roundings in torch -- and the split-operand GEMM it feeds
+    reproduces an fp64 product to ~4e-6 (two-way split) / fp32 rounding level (three-way)."""
+    from mtasr_b200 import kernels as Kn
+    torch.manual_seed(1)
+    rows, c, n = 37, 64, 3
+    x = torch.randn(rows, n * c, device=cuda) * 3
+    y = Kn.split_bf16(x, c, order, terms).view(rows, n, terms, c)
+    p1 = x.to(torch.bfloat16)
+    r1 = x - p1.float()
+    p2 = r1.to(torch.bfloat16)
+    p3 = (r1 - p2.float()).to(torch.bfloat16)
+    p1, p2, p3 = (t.view(rows, n, c) for t in (p1, p2, p3))
+    if terms == 3:
+        parts = (p2, p1, p1) if order == 0 else (p1, p2, p1)
+    else:
+        parts = (p3, p2, p1, p2, p1, p1) if order == 0 else (p1, p2, p3, p1, p2, p1)
+    for j in range(terms):
+        assert torch.equal(y[:, :, j], parts[j])
+    if order == 0:
+        M, N, Kd = 300, 200, 512
+        a, b = torch.randn(M, Kd, device=cuda), torch.randn(N, Kd, device=cuda)
+        out = torch.empty(M, N, device=cuda)
+        Kn.gemm(Kn.Operand(Kn.split_bf16(a, Kd, 0, terms), terms * Kd), Kn.Operand(Kn.split_bf16(b, Kd, 1, terms), terms * Kd),
+                M, N, terms * Kd, Kn.Out(out, N))
+        ref = (a.double() @ b.double().t()).float()
+        assert _rel(out, ref) < (1e-5 if terms == 3 else 1e-6), _rel(out, ref)
