@@ -118,7 +118,10 @@ int mtasr_ctc_alpha_fwd(const float* glog, const float* lse, const int64_t* ys, 
                         const int64_t* ylens, int32_t B, int32_t T, int32_t Lp, int32_t ys_ld, int32_t max_label_len,
                         float* alpha_ws, double* coff_ws, float* nll_out, double* nll_raw, void* stream);
 /* beta recursion + gradient: dG (B,T,Lp) = gout[b] * d nll_b / d lp(t, column) (= -gout*occupancy),
- * rowscale (B,T) = gout[b] on valid frames of feasible utterances else 0 (scales the dense softmax term). */
+ * rowscale (B,T) = gout[b] on valid frames of feasible utterances else 0 (scales the dense softmax term).
+ * dG must arrive ZEROED: only the (t < hlens[b], column <= ylens[b]) entries of feasible utterances are written.
+ * Both recursions stream their per-frame inputs through a double-buffered shared-memory ring (cp.async), one warp
+ * (= one CTA) per utterance; glog / alpha_ws must be 16-byte aligned and Lp a multiple of 4. */
 int mtasr_ctc_beta_bwd(const float* glog, const float* lse, const int64_t* ys, const int64_t* hlens,
                        const int64_t* ylens, int32_t B, int32_t T, int32_t Lp, int32_t ys_ld, int32_t max_label_len,
                        const float* alpha_ws, const double* coff_ws, const double* nll_raw, const float* gout,

@@ -18,27 +18,62 @@ namespace mtasr {
 static constexpr float NEG_INF = -INFINITY;
 
 // log(exp a + exp b + exp c) on the SFU (ex2 / lg2 approximations, ~1e-7 relative): the recursion is one dependent chain
-// per time step, so the instruction count of this function IS the latency of the kernel.  The argument of the log lies in
-// [1, 3], where lg2.approx is accurate to a few ulp; tests pin loss and gradients to the fp64 oracle at 1e-5.
+// per time step, so the instruction count of this function IS the latency of the kernel.  Branch-free on purpose: with
+// a branch per call the NS calls of one step become NS serialised BSSY/BSYNC regions and their MUFU latencies add up
+// instead of overlapping.  All-(-inf) input: the exponentials are 0, lg2(0) = -inf, result -inf.  The argument of the
+// log otherwise lies in [1, 3], where lg2.approx is accurate to a few ulp; tests pin loss and gradients to the fp64
+// oracle at 1e-5.
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float lse3(float a, float b, float c) {
-  const float m = fmaxf(a, fmaxf(b, c));
-  if (m == NEG_INF) return NEG_INF;
+  const float m0 = fmaxf(a, fmaxf(b, c));
+  const float m = m0 == NEG_INF ? 0.f : m0;
   const float k = 1.4426950408889634f;
   const float nm = -m * k;
   const float sum = ex2_approx(fmaf(a, k, nm)) + ex2_approx(fmaf(b, k, nm)) + ex2_approx(fmaf(c, k, nm));
-  return fmaf(__log2f(sum), 0.6931471805599453f, m);
+  return fmaf(lg2_approx(sum), 0.6931471805599453f, m);
+}
+
+// Ampere-style asynchronous copies (global -> shared without a register round trip): the recursions below are one
+// dependent chain per time step, so every global-memory latency inside the step is exposed.  All per-frame inputs are
+// therefore streamed through a double-buffered shared-memory ring, CH frames per chunk, one chunk ahead of the recursion.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem))), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Warp-wide float max in one REDUX instead of five shuffle+max rounds: floats are mapped to integers of the same order.
+__device__ __forceinline__ float warp_max_redux(float v) {
+  int i = __float_as_int(v);
+  i ^= (i >> 31) & 0x7fffffff;
+  i = __reduce_max_sync(0xffffffffu, i);
+  i ^= (i >> 31) & 0x7fffffff;
+  return __int_as_float(i);
 }
 
 // ------------------------------------------------------------------------------------------------ alpha
+// One warp (= one CTA) per utterance.  smem: [2][CH][Lp] lattice-column logits + [2][CH] row LSE.
 template <int NS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32)
 ctc_alpha_kernel(const float* __restrict__ glog, const float* __restrict__ lse, const long long* __restrict__ ys,
                  const long long* __restrict__ hlens, const long long* __restrict__ ylens, int B, int T, int Lp,
-                 int ys_ld, float* __restrict__ alpha_ws, double* __restrict__ coff_ws, float* __restrict__ nll_out,
+                 int ys_ld, int CH, float* __restrict__ alpha_ws, double* __restrict__ coff_ws, float* __restrict__ nll_out,
                  double* __restrict__ nll_raw) {
+  extern __shared__ __align__(16) unsigned char ctc_smem[];
   constexpr int SP = 32 * NS;
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.x;
   if (b >= B) return;
   int Tb = static_cast<int>(hlens[b]);
   Tb = Tb < 0 ? 0 : (Tb > T ? T : Tb);
@@ -67,66 +102,78 @@ ctc_alpha_kernel(const float* __restrict__ glog, const float* __restrict__ lse, 
   const float* ls = lse + static_cast<long long>(b) * T;
   float* aw = alpha_ws + static_cast<long long>(b) * T * SP;
   double* cw = coff_ws + static_cast<long long>(b) * T;
+  float* sg = reinterpret_cast<float*>(ctc_smem);
+  float* sl = sg + 2 * CH * Lp;
+
+  auto issue = [&](int c) {
+    const int t0 = c * CH;
+    const int n = min(CH, Tb - t0);
+    if (n > 0) {
+      float* dst = sg + (c & 1) * CH * Lp;
+      const float* src = g + static_cast<long long>(t0) * Lp;
+      for (int i = lane; i < n * (Lp >> 2); i += 32) cp_async16(dst + i * 4, src + i * 4);
+      for (int i = lane; i < n; i += 32) cp_async4(sl + (c & 1) * CH + i, ls + t0 + i);
+    }
+    cp_async_commit();
+  };
 
   float a[NS];
-  float nxt[NS];
-  {
-    const float l0 = ls[0];
 #pragma unroll
-    for (int j = 0; j < NS; ++j) {
-      const int s = lane * NS + j;
-      a[j] = (ok[j] && s <= 1) ? g[col[j]] - l0 : NEG_INF;
-    }
-  }
+  for (int j = 0; j < NS; ++j) a[j] = NEG_INF;
   double coff = 0.0;
-  // prefetch t = 1
-  if (Tb > 1) {
-    const float l1 = ls[1];
-#pragma unroll
-    for (int j = 0; j < NS; ++j) nxt[j] = ok[j] ? g[Lp + col[j]] - l1 : NEG_INF;
-  }
-  for (int t = 0; t < Tb; ++t) {
-    if (t > 0) {
+  const int nchunk = (Tb + CH - 1) / CH;
+  issue(0);
+  for (int c = 0; c < nchunk; ++c) {
+    issue(c + 1);
+    cp_async_wait<1>();
+    __syncwarp();
+    const float* cg = sg + (c & 1) * CH * Lp;
+    const float* cl = sl + (c & 1) * CH;
+    const int t0 = c * CH;
+    const int n = min(CH, Tb - t0);
+    for (int f = 0; f < n; ++f) {
+      const int t = t0 + f;
       float cur[NS];
+      const float l = cl[f];
 #pragma unroll
-      for (int j = 0; j < NS; ++j) cur[j] = nxt[j];
-      if (t + 1 < Tb) {
-        const float l1 = ls[t + 1];
-        const float* gr = g + static_cast<long long>(t + 1) * Lp;
+      for (int j = 0; j < NS; ++j) cur[j] = ok[j] ? cg[f * Lp + col[j]] - l : NEG_INF;
+      if (t == 0) {
 #pragma unroll
-        for (int j = 0; j < NS; ++j) nxt[j] = ok[j] ? gr[col[j]] - l1 : NEG_INF;
+        for (int j = 0; j < NS; ++j) a[j] = (lane * NS + j <= 1) ? cur[j] : NEG_INF;
+      } else {
+        float pm1 = __shfl_up_sync(0xffffffffu, a[NS - 1], 1);
+        float pm2 = __shfl_up_sync(0xffffffffu, a[NS - 2], 1);
+        if (lane == 0) { pm1 = NEG_INF; pm2 = NEG_INF; }
+        float na[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          const float s1 = j >= 1 ? a[j - 1] : pm1;
+          const float s2 = j >= 2 ? a[j - 2] : (j == 1 ? pm1 : pm2);
+          na[j] = cur[j] + lse3(a[j], s1, skip[j] ? s2 : NEG_INF);   // cur = -inf for states past the lattice
+        }
+#pragma unroll
+        for (int j = 0; j < NS; ++j) a[j] = na[j];
       }
-      float pm1 = __shfl_up_sync(0xffffffffu, a[NS - 1], 1);
-      float pm2 = __shfl_up_sync(0xffffffffu, a[NS - 2], 1);
-      if (lane == 0) { pm1 = NEG_INF; pm2 = NEG_INF; }
-      float na[NS];
+      // normalise
+      float m = NEG_INF;
 #pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        const float s1 = j >= 1 ? a[j - 1] : pm1;
-        const float s2 = j >= 2 ? a[j - 2] : (j == 1 ? pm1 : pm2);
-        na[j] = ok[j] ? cur[j] + lse3(a[j], s1, skip[j] ? s2 : NEG_INF) : NEG_INF;
+      for (int j = 0; j < NS; ++j) m = fmaxf(m, a[j]);
+      m = warp_max_redux(m);
+      if (m == NEG_INF) m = 0.f;  // dead lattice: stays -inf, nll becomes +inf below
+#pragma unroll
+      for (int j = 0; j < NS; ++j) a[j] -= m;
+      coff += static_cast<double>(m);
+      float4* dst = reinterpret_cast<float4*>(aw + static_cast<long long>(t) * SP + lane * NS);
+      if constexpr (NS % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < NS; j += 4) dst[j >> 2] = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < NS; ++j) aw[static_cast<long long>(t) * SP + lane * NS + j] = a[j];
       }
-#pragma unroll
-      for (int j = 0; j < NS; ++j) a[j] = na[j];
+      if (lane == 0) cw[t] = coff;
     }
-    // normalise
-    float m = NEG_INF;
-#pragma unroll
-    for (int j = 0; j < NS; ++j) m = fmaxf(m, a[j]);
-    m = warp_max(m);
-    if (m == NEG_INF) m = 0.f;  // dead lattice: stays -inf, nll becomes +inf below
-#pragma unroll
-    for (int j = 0; j < NS; ++j) a[j] -= m;
-    coff += static_cast<double>(m);
-    float4* dst = reinterpret_cast<float4*>(aw + static_cast<long long>(t) * SP + lane * NS);
-    if constexpr (NS % 4 == 0) {
-#pragma unroll
-      for (int j = 0; j < NS; j += 4) dst[j >> 2] = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < NS; ++j) aw[static_cast<long long>(t) * SP + lane * NS + j] = a[j];
-    }
-    if (lane == 0) cw[t] = coff;
+    __syncwarp();   // all lanes are done with this buffer before chunk c + 2 is copied into it
   }
   float e1 = NEG_INF, e2 = NEG_INF;
 #pragma unroll
@@ -146,18 +193,21 @@ ctc_alpha_kernel(const float* __restrict__ glog, const float* __restrict__ lse, 
 }
 
 // ------------------------------------------------------------------------------------------------ beta + grad
-// dG[b][t][c] = -gout[b] * occupancy(t, c);  rowscale[b][t] = gout[b] for valid frames of feasible utterances.
+// dG[b][t][c] = -gout[b] * occupancy(t, c) (dG arrives ZEROED: only reachable (t, c) are written);
+// rowscale[b][t] = gout[b] for valid frames of feasible utterances.
 // The dense part of d nll/d logits (softmax * rowscale) is regenerated by the vocab GEMM (mode 2).
+// smem: [2][CH][Lp] logits + [2][CH][SP] saved alpha + [2][CH] coff (double) + [2][CH] row LSE.
 template <int NS>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32)
 ctc_beta_grad_kernel(const float* __restrict__ glog, const float* __restrict__ lse, const long long* __restrict__ ys,
                      const long long* __restrict__ hlens, const long long* __restrict__ ylens, int B, int T, int Lp,
-                     int ys_ld, const float* __restrict__ alpha_ws, const double* __restrict__ coff_ws,
+                     int ys_ld, int CH, const float* __restrict__ alpha_ws, const double* __restrict__ coff_ws,
                      const double* __restrict__ nll_raw, const float* __restrict__ gout, float* __restrict__ dG,
                      float* __restrict__ rowscale) {
+  extern __shared__ __align__(16) unsigned char ctc_smem[];
   constexpr int SP = 32 * NS;
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int b = blockIdx.x;
   if (b >= B) return;
   int Tb = static_cast<int>(hlens[b]);
   Tb = Tb < 0 ? 0 : (Tb > T ? T : Tb);
@@ -170,11 +220,6 @@ ctc_beta_grad_kernel(const float* __restrict__ glog, const float* __restrict__ l
   float* rs = rowscale + static_cast<long long>(b) * T;
   for (int t = lane; t < T; t += 32) rs[t] = (feasible && t < Tb) ? go : 0.f;
   float* dg = dG + static_cast<long long>(b) * T * Lp;
-  // zero everything this utterance does not write below
-  for (long long i = lane; i < static_cast<long long>(T) * Lp; i += 32) {
-    const int t = static_cast<int>(i / Lp), c = static_cast<int>(i - static_cast<long long>(t) * Lp);
-    if (!feasible || t >= Tb || c > L) dg[i] = 0.f;
-  }
   if (!feasible) return;
 
   int col[NS];
@@ -190,69 +235,100 @@ ctc_beta_grad_kernel(const float* __restrict__ glog, const float* __restrict__ l
   const float* ls = lse + static_cast<long long>(b) * T;
   const float* aw = alpha_ws + static_cast<long long>(b) * T * SP;
   const double* cw = coff_ws + static_cast<long long>(b) * T;
+  double* sc = reinterpret_cast<double*>(ctc_smem);            // [2][CH]
+  float* sg = reinterpret_cast<float*>(sc + 2 * CH);           // [2][CH][Lp]
+  float* sa = sg + 2 * CH * Lp;                                // [2][CH][SP]
+  float* sl = sa + 2 * CH * SP;                                // [2][CH]
+
+  const int nchunk = (Tb + CH - 1) / CH;
+  auto issue = [&](int c) {      // chunk c covers frames [c*CH, c*CH + n); chunks are consumed from the last one down
+    if (c >= 0) {
+      const int t0 = c * CH;
+      const int n = min(CH, Tb - t0);
+      const int buf = c & 1;
+      float* dst = sg + buf * CH * Lp;
+      const float* src = g + static_cast<long long>(t0) * Lp;
+      for (int i = lane; i < n * (Lp >> 2); i += 32) cp_async16(dst + i * 4, src + i * 4);
+      float* dsta = sa + buf * CH * SP;
+      const float* srca = aw + static_cast<long long>(t0) * SP;
+      for (int i = lane; i < n * (SP >> 2); i += 32) cp_async16(dsta + i * 4, srca + i * 4);
+      for (int i = lane; i < n; i += 32) {
+        cp_async4(sl + buf * CH + i, ls + t0 + i);
+        cp_async8(sc + buf * CH + i, cw + t0 + i);
+      }
+    }
+    cp_async_commit();
+  };
 
   float bt[NS];
-  float lp[NS], nxt[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) bt[j] = NEG_INF;
   double boff = 0.0;
-  {
-    const float l0 = ls[Tb - 1];
-    const float* gr = g + static_cast<long long>(Tb - 1) * Lp;
+  issue(nchunk - 1);
+  for (int c = nchunk - 1; c >= 0; --c) {
+    issue(c - 1);
+    cp_async_wait<1>();
+    __syncwarp();
+    const int buf = c & 1;
+    const float* cg = sg + buf * CH * Lp;
+    const float* ca = sa + buf * CH * SP;
+    const float* cl = sl + buf * CH;
+    const double* cc = sc + buf * CH;
+    const int t0 = c * CH;
+    const int n = min(CH, Tb - t0);
+    for (int f = n - 1; f >= 0; --f) {
+      const int t = t0 + f;
+      float lp[NS];
+      const float l = cl[f];
 #pragma unroll
-    for (int j = 0; j < NS; ++j) nxt[j] = ok[j] ? gr[col[j]] - l0 : NEG_INF;
-  }
-  for (int t = Tb - 1; t >= 0; --t) {
+      for (int j = 0; j < NS; ++j) lp[j] = ok[j] ? cg[f * Lp + col[j]] - l : NEG_INF;
+      if (t == Tb - 1) {
 #pragma unroll
-    for (int j = 0; j < NS; ++j) lp[j] = nxt[j];
-    if (t > 0) {
-      const float l1 = ls[t - 1];
-      const float* gr = g + static_cast<long long>(t - 1) * Lp;
+        for (int j = 0; j < NS; ++j) {
+          const int s = lane * NS + j;
+          bt[j] = (ok[j] && (s == S - 1 || s == S - 2)) ? lp[j] : NEG_INF;
+        }
+      } else {
+        float np1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
+        float np2 = __shfl_down_sync(0xffffffffu, bt[1], 1);
+        if (lane == 31) { np1 = NEG_INF; np2 = NEG_INF; }
+        float nb[NS];
 #pragma unroll
-      for (int j = 0; j < NS; ++j) nxt[j] = ok[j] ? gr[col[j]] - l1 : NEG_INF;
-    }
-    if (t == Tb - 1) {
+        for (int j = 0; j < NS; ++j) {
+          const float s1 = j + 1 < NS ? bt[j + 1 < NS ? j + 1 : 0] : np1;
+          const float s2 = j + 2 < NS ? bt[j + 2 < NS ? j + 2 : 0] : (j + 2 == NS ? np1 : np2);
+          nb[j] = lp[j] + lse3(bt[j], s1, skip[j] ? s2 : NEG_INF);   // lp = -inf for states past the lattice
+        }
+#pragma unroll
+        for (int j = 0; j < NS; ++j) bt[j] = nb[j];
+      }
+      float m = NEG_INF;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) m = fmaxf(m, bt[j]);
+      m = warp_max_redux(m);
+      if (m == NEG_INF) m = 0.f;
+#pragma unroll
+      for (int j = 0; j < NS; ++j) bt[j] -= m;
+      boff += static_cast<double>(m);
+      // occupancy: exp(alpha + beta - lp + nll) with the three O(|nll|) offsets combined in double
+      const float shift = static_cast<float>(cc[f] + boff + nll);
+      const float* ar = ca + f * SP + lane * NS;
+      float blank_occ = 0.f;
+      float* dgr = dg + static_cast<long long>(t) * Lp;
 #pragma unroll
       for (int j = 0; j < NS; ++j) {
-        const int s = lane * NS + j;
-        bt[j] = (ok[j] && (s == S - 1 || s == S - 2)) ? lp[j] : NEG_INF;
+        // unreachable states have alpha or beta = -inf -> e = -inf -> occupancy 0 (lp is finite wherever ok[j])
+        const float e = ar[j] + bt[j] - (ok[j] ? lp[j] : 0.f) + shift;
+        const float occ = ex2_approx(e * 1.4426950408889634f);
+        if (ok[j]) {
+          if (col[j] == 0) blank_occ += occ;
+          else dgr[col[j]] = -go * occ;
+        }
       }
-    } else {
-      float np1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
-      float np2 = __shfl_down_sync(0xffffffffu, bt[1], 1);
-      if (lane == 31) { np1 = NEG_INF; np2 = NEG_INF; }
-      float nb[NS];
-#pragma unroll
-      for (int j = 0; j < NS; ++j) {
-        const float s1 = j + 1 < NS ? bt[j + 1 < NS ? j + 1 : 0] : np1;
-        const float s2 = j + 2 < NS ? bt[j + 2 < NS ? j + 2 : 0] : (j + 2 == NS ? np1 : np2);
-        nb[j] = ok[j] ? lp[j] + lse3(bt[j], s1, skip[j] ? s2 : NEG_INF) : NEG_INF;
-      }
-#pragma unroll
-      for (int j = 0; j < NS; ++j) bt[j] = nb[j];
+      blank_occ = warp_sum(blank_occ);
+      if (lane == 0) dgr[0] = -go * blank_occ;
     }
-    float m = NEG_INF;
-#pragma unroll
-    for (int j = 0; j < NS; ++j) m = fmaxf(m, bt[j]);
-    m = warp_max(m);
-    if (m == NEG_INF) m = 0.f;
-#pragma unroll
-    for (int j = 0; j < NS; ++j) bt[j] -= m;
-    boff += static_cast<double>(m);
-    // occupancy: exp(alpha + beta - lp + nll) with the three O(|nll|) offsets combined in double
-    const float shift = static_cast<float>(cw[t] + boff + nll);
-    const float* ar = aw + static_cast<long long>(t) * SP + lane * NS;
-    float blank_occ = 0.f;
-    float* dgr = dg + static_cast<long long>(t) * Lp;
-#pragma unroll
-    for (int j = 0; j < NS; ++j) {
-      if (ok[j]) {
-        const float e = ar[j] + bt[j] - lp[j] + shift;
-        const float occ = (ar[j] == NEG_INF || bt[j] == NEG_INF) ? 0.f : expf(e);
-        if (col[j] == 0) blank_occ += occ;
-        else dgr[col[j]] = -go * occ;
-      }
-    }
-    blank_occ = warp_sum(blank_occ);
-    if (lane == 0) dgr[0] = -go * blank_occ;
+    __syncwarp();
   }
 }
 
@@ -486,6 +562,15 @@ static int pick_ns(int max_states) {
 
 using namespace mtasr;
 
+// frames per shared-memory chunk of the alpha / beta kernels: two buffers within the 48 KB static-opt-in-free limit,
+// a multiple of 2, at most 32
+static int ctc_chunk_frames(int frame_bytes) {
+  int ch = 22000 / frame_bytes;
+  ch = ch > 32 ? 32 : ch;
+  ch &= ~1;
+  return ch < 2 ? 2 : ch;
+}
+
 extern "C" int mtasr_ctc_state_pad(int32_t max_label_len) {
   const int ns = pick_ns(2 * max_label_len + 1);
   return ns < 0 ? -1 : 32 * ns;
@@ -500,17 +585,20 @@ extern "C" int mtasr_ctc_alpha_fwd(const float* glog, const float* lse, const in
   MTASR_CHECK_ARG(B > 0 && T > 0 && Lp >= max_label_len + 1, "ctc_alpha_fwd: bad sizes B=%d T=%d Lp=%d Lmax=%d", B, T, Lp, max_label_len);
   const int ns = pick_ns(2 * max_label_len + 1);
   if (ns < 0) return set_error(MTASR_ERR_UNSUPPORTED, "ctc_alpha_fwd: label length %d > 255 not supported", max_label_len);
-  const int wpb = 4;
-  dim3 grid((B + wpb - 1) / wpb), block(32 * wpb);
+  MTASR_CHECK_ARG(Lp % 4 == 0 && (reinterpret_cast<uintptr_t>(glog) & 15) == 0, "ctc_alpha_fwd: Lp %% 4 and 16-byte aligned glog required");
+  const int frame_bytes = Lp * 4 + 4;
+  const int CH = ctc_chunk_frames(frame_bytes);
+  const size_t smem = 2 * static_cast<size_t>(CH) * frame_bytes;
+  dim3 grid(B), block(32);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long* y = reinterpret_cast<const long long*>(ys);
   const long long* hl = reinterpret_cast<const long long*>(hlens);
   const long long* yl = reinterpret_cast<const long long*>(ylens);
   switch (ns) {
-    case 2: ctc_alpha_kernel<2><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_out, nll_raw); break;
-    case 4: ctc_alpha_kernel<4><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_out, nll_raw); break;
-    case 8: ctc_alpha_kernel<8><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_out, nll_raw); break;
-    default: ctc_alpha_kernel<16><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_out, nll_raw); break;
+    case 2: ctc_alpha_kernel<2><<<grid, block, smem, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, CH, alpha_ws, coff_ws, nll_out, nll_raw); break;
+    case 4: ctc_alpha_kernel<4><<<grid, block, smem, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, CH, alpha_ws, coff_ws, nll_out, nll_raw); break;
+    case 8: ctc_alpha_kernel<8><<<grid, block, smem, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, CH, alpha_ws, coff_ws, nll_out, nll_raw); break;
+    default: ctc_alpha_kernel<16><<<grid, block, smem, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, CH, alpha_ws, coff_ws, nll_out, nll_raw); break;
   }
   g_launches.fetch_add(1);
   MTASR_CHECK_LAUNCH("ctc_alpha_fwd");
@@ -525,17 +613,21 @@ extern "C" int mtasr_ctc_beta_bwd(const float* glog, const float* lse, const int
   MTASR_CHECK_ARG(B > 0 && T > 0 && Lp >= max_label_len + 1, "ctc_beta_bwd: bad sizes");
   const int ns = pick_ns(2 * max_label_len + 1);
   if (ns < 0) return set_error(MTASR_ERR_UNSUPPORTED, "ctc_beta_bwd: label length %d > 255 not supported", max_label_len);
-  const int wpb = 4;
-  dim3 grid((B + wpb - 1) / wpb), block(32 * wpb);
+  MTASR_CHECK_ARG(Lp % 4 == 0 && (reinterpret_cast<uintptr_t>(glog) & 15) == 0 && (reinterpret_cast<uintptr_t>(alpha_ws) & 15) == 0,
+                  "ctc_beta_bwd: Lp %% 4 and 16-byte aligned glog / alpha_ws required");
+  const int frame_bytes = Lp * 4 + 32 * ns * 4 + 4 + 8;
+  const int CH = ctc_chunk_frames(frame_bytes);
+  const size_t smem = 2 * static_cast<size_t>(CH) * frame_bytes;
+  dim3 grid(B), block(32);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long* y = reinterpret_cast<const long long*>(ys);
   const long long* hl = reinterpret_cast<const long long*>(hlens);
   const long long* yl = reinterpret_cast<const long long*>(ylens);
   switch (ns) {
-    case 2: ctc_beta_grad_kernel<2><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_raw, gout, dG, rowscale); break;
-    case 4: ctc_beta_grad_kernel<4><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_raw, gout, dG, rowscale); break;
-    case 8: ctc_beta_grad_kernel<8><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_raw, gout, dG, rowscale); break;
-    default: ctc_beta_grad_kernel<16><<<grid, block, 0, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, alpha_ws, coff_ws, nll_raw, gout, dG, rowscale); break;
+    case 2: ctc_beta_grad_kernel<2><<<grid, block, smem, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, CH, alpha_ws, coff_ws, nll_raw, gout, dG, rowscale); break;
+    case 4: ctc_beta_grad_kernel<4><<<grid, block, smem, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, CH, alpha_ws, coff_ws, nll_raw, gout, dG, rowscale); break;
+    case 8: ctc_beta_grad_kernel<8><<<grid, block, smem, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, CH, alpha_ws, coff_ws, nll_raw, gout, dG, rowscale); break;
+    default: ctc_beta_grad_kernel<16><<<grid, block, smem, st>>>(glog, lse, y, hl, yl, B, T, Lp, ys_ld, CH, alpha_ws, coff_ws, nll_raw, gout, dG, rowscale); break;
   }
   g_launches.fetch_add(1);
   MTASR_CHECK_LAUNCH("ctc_beta_bwd");

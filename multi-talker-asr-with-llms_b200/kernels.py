@@ -350,7 +350,7 @@ def ctc_alpha_fwd(glog, lse, ys, hlens, ylens, max_label_len):
 
 def ctc_beta_bwd(glog, lse, ys, hlens, ylens, max_label_len, alpha, coff, nll_raw, gout):
     B, T, Lp = glog.shape
-    dG = torch.empty(B, T, Lp, device=glog.device, dtype=torch.float32)
+    dG = torch.zeros(B, T, Lp, device=glog.device, dtype=torch.float32)     # the kernel writes reachable (t, column) only
     rowscale = torch.empty(B, T, device=glog.device, dtype=torch.float32)
     ys_ld = ys.stride(0) if ys.numel() else 0
     check(_lib.load().mtasr_ctc_beta_bwd(_p(glog), _p(lse), _p(ys) if ys.numel() else None, _p(hlens), _p(ylens), B, T, Lp,
