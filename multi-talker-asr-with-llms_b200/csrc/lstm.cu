@@ -301,6 +301,11 @@ __device__ __forceinline__ void group_arrive(unsigned int* bar) {
   }
 }
 
+// Gate non-linearities on the SFU (one MUFU.EX2 + one MUFU.RCP each, |abs err| ~1e-7): libm expf/tanhf cost ~40
+// instructions with range-reduction branches apiece, five times per step on the critical path of the recurrence.
+__device__ __forceinline__ float sigmoid_sfu(float x) { return rcp_approx(1.f + ex2_approx(x * -1.4426950408889634f)); }
+__device__ __forceinline__ float tanh_sfu(float x) { return fmaf(2.f, sigmoid_sfu(2.f * x), -1.f); }
+
 struct LstmBsP {
   const float* xg;            // (B,T,4Hs)   fwd
   const __nv_bfloat16* whh;   // (4Hs, ldw)
@@ -315,6 +320,7 @@ struct LstmBsP {
   int dbg;                    // timing experiments only (MTASR_LSTM_DBG): 1 skip MMA, 2 skip exchange load, 4 skip barrier
 };
 
+template <int KPER>
 __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_bs_kernel(const LstmBsP p) {
   extern __shared__ __align__(16) uint8_t lsm[];
   const int Hs = p.Hs, T = p.T, U = p.U, G = p.G;
@@ -374,18 +380,43 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_bs_kernel(const LstmBsP 
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[mi][q] = 0.f;
-      for (int ks = (p.dbg & 1) ? k_hi : k_lo; ks < k_hi; ++ks) {
-        const int k0 = ks * 16;
-        uint32_t hb0, hb1;
-        ldsm_x2(smem_addr(Hsm + (lane & 7) * rs + k0 + ((lane >> 3) & 1) * 8), hb0, hb1);
+      if constexpr (KPER > 0) {
+        // fixed trip count (Hs = 64 KPER): fully unrolled so that the ldmatrix of later k-steps are issued ahead of the
+        // dependent MMA chain instead of ldmatrix -> mma -> ldmatrix ... serialisation (1.5 us of a 5 us step before)
+        uint32_t hb[KPER][2];
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi) {
-          const int mt = mt_lo + mi;
-          if (mi < mt_half && mt < m_tiles) {
-            const int row = min(mt * 16 + (lane & 15), M - 1);
-            uint32_t a0, a1, a2, a3;
-            ldsm_x4(smem_addr(Ws + row * rs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
-            mma16816(acc[mi], a0, a1, a2, a3, hb0, hb1);
+        for (int i = 0; i < KPER; ++i)
+          ldsm_x2(smem_addr(Hsm + (lane & 7) * rs + (k_lo + i) * 16 + ((lane >> 3) & 1) * 8), hb[i][0], hb[i][1]);
+        if (!(p.dbg & 1)) {
+#pragma unroll
+          for (int i = 0; i < KPER; ++i) {
+            const int k0 = (k_lo + i) * 16;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+              const int mt = mt_lo + mi;
+              if (mi < mt_half && mt < m_tiles) {
+                const int row = min(mt * 16 + (lane & 15), M - 1);
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4(smem_addr(Ws + row * rs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+                mma16816(acc[mi], a0, a1, a2, a3, hb[i][0], hb[i][1]);
+              }
+            }
+          }
+        }
+      } else {
+      for (int ks = (p.dbg & 1) ? k_hi : k_lo; ks < k_hi; ++ks) {
+          const int k0 = ks * 16;
+          uint32_t hb0, hb1;
+          ldsm_x2(smem_addr(Hsm + (lane & 7) * rs + k0 + ((lane >> 3) & 1) * 8), hb0, hb1);
+  #pragma unroll
+          for (int mi = 0; mi < 4; ++mi) {
+            const int mt = mt_lo + mi;
+            if (mi < mt_half && mt < m_tiles) {
+              const int row = min(mt * 16 + (lane & 15), M - 1);
+              uint32_t a0, a1, a2, a3;
+              ldsm_x4(smem_addr(Ws + row * rs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+              mma16816(acc[mi], a0, a1, a2, a3, hb0, hb1);
+            }
           }
         }
       }
@@ -413,11 +444,11 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_bs_kernel(const LstmBsP 
     }
     if (has_pair) {
       const float ai = xv[0] + gsum[0], af = xv[1] + gsum[1], ag = xv[2] + gsum[2], ao = xv[3] + gsum[3];
-      const float ig = 1.f / (1.f + expf(-ai)), fg = 1.f / (1.f + expf(-af));
-      const float gg = tanhf(ag), og = 1.f / (1.f + expf(-ao));
+      const float ig = sigmoid_sfu(ai), fg = sigmoid_sfu(af);
+      const float gg = tanh_sfu(ag), og = sigmoid_sfu(ao);
       const float c = fg * creg + ig * gg;
       creg = c;
-      const float h = og * tanhf(c);
+      const float h = og * tanh_sfu(c);
       const long long o = (static_cast<long long>(b0 + pb) * T + t) * Hs + u0 + pu;
       p.h_bf16[o] = f2bf(h);                       // the exchange store: published by the arrive below
       sv_h = h; sv_c = c; sv_i = ig; sv_f = fg; sv_g = gg; sv_o = og;
@@ -433,6 +464,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_bs_kernel(const LstmBsP 
   }
 }
 
+template <int KPER>
 __global__ void __launch_bounds__(LTHREADS, 1) lstm_bwd_bs_kernel(const LstmBsP p) {
   extern __shared__ __align__(16) uint8_t lsm[];
   const int Hs = p.Hs, T = p.T, U = p.U, G = p.G;
@@ -511,20 +543,41 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_bwd_bs_kernel(const LstmBsP 
           }
         }
         __syncthreads();
-        for (int ks = k_lo; ks < k_hi; ks += 2) {
+        if constexpr (KPER > 0) {
+          // fixed trip count (Hs = 128 KPER): unrolled, B fragments of the whole chunk loaded ahead of the MMA chain
+          uint32_t db[KPER][2];
 #pragma unroll
-          for (int par = 0; par < 2; ++par) {     // two independent accumulator sets halve the dependent MMA chain
-            if (ks + par < k_hi) {
-              const int k0 = (ks + par) * 16;
-              uint32_t d0, d1;
-              ldsm_x2(smem_addr(Asm + (lane & 7) * ars + k0 + ((lane >> 3) & 1) * 8), d0, d1);
+          for (int i = 0; i < KPER; ++i)
+            ldsm_x2(smem_addr(Asm + (lane & 7) * ars + (k_lo + i) * 16 + ((lane >> 3) & 1) * 8), db[i][0], db[i][1]);
 #pragma unroll
-              for (int mt = 0; mt < 2; ++mt) {
-                if (mt < m_tiles) {
-                  const int row = min(mt * 16 + (lane & 15), U - 1);
-                  uint32_t a0, a1, a2, a3;
-                  ldsm_x4(smem_addr(Wt + row * wrs + g * Hs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
-                  mma16816(acc[mt][par], a0, a1, a2, a3, d0, d1);
+          for (int i = 0; i < KPER; ++i) {
+            const int k0 = (k_lo + i) * 16;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              if (mt < m_tiles) {
+                const int row = min(mt * 16 + (lane & 15), U - 1);
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4(smem_addr(Wt + row * wrs + g * Hs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+                mma16816(acc[mt][i & 1], a0, a1, a2, a3, db[i][0], db[i][1]);
+              }
+            }
+          }
+        } else {
+          for (int ks = k_lo; ks < k_hi; ks += 2) {
+#pragma unroll
+            for (int par = 0; par < 2; ++par) {     // two independent accumulator sets halve the dependent MMA chain
+              if (ks + par < k_hi) {
+                const int k0 = (ks + par) * 16;
+                uint32_t d0, d1;
+                ldsm_x2(smem_addr(Asm + (lane & 7) * ars + k0 + ((lane >> 3) & 1) * 8), d0, d1);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                  if (mt < m_tiles) {
+                    const int row = min(mt * 16 + (lane & 15), U - 1);
+                    uint32_t a0, a1, a2, a3;
+                    ldsm_x4(smem_addr(Wt + row * wrs + g * Hs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+                    mma16816(acc[mt][par], a0, a1, a2, a3, d0, d1);
+                  }
                 }
               }
             }
@@ -627,11 +680,13 @@ extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw
       q.h_f32 = h_f32; q.c_all = c_all; q.gates = gates; q.bar = barrier;
       q.B = B; q.T = T; q.Hs = Hs; q.ldw = ldw; q.G = G; q.U = Hs / G;
       q.dbg = getenv("MTASR_LSTM_DBG") ? atoi(getenv("MTASR_LSTM_DBG")) : 0;
-      if (cudaFuncSetAttribute(lstm_fwd_bs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bs)) != cudaSuccess)
+      // unrolled instantiation when every warp owns exactly Hs/64 k-steps (Hs = 896 -> 14), generic loop otherwise
+      void (*kern)(const LstmBsP) = (Hs == 896) ? lstm_fwd_bs_kernel<14> : lstm_fwd_bs_kernel<0>;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bs)) != cudaSuccess)
         return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: cannot set smem attribute");
       if (cudaMemsetAsync(barrier, 0, sizeof(uint32_t) * S, st0) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: memset failed");
       void* args[] = {&q};
-      cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_fwd_bs_kernel), dim3(S * G), dim3(LTHREADS), args, smem_bs, st0);
+      cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(S * G), dim3(LTHREADS), args, smem_bs, st0);
       MTASR_COUNT_LAUNCH();
       if (e != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: cooperative launch failed: %s", cudaGetErrorString(e));
       return MTASR_OK;
@@ -668,11 +723,12 @@ extern "C" int mtasr_lstm_bwd(const float* dh_out, const float* gates, const flo
       q.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16); q.c_all = const_cast<float*>(c_all); q.gates = const_cast<float*>(gates);
       q.dh_out = dh_out; q.dgates = reinterpret_cast<__nv_bfloat16*>(dgates_bf16); q.bar = barrier;
       q.B = B; q.T = T; q.Hs = Hs; q.ldw = ldw; q.G = G; q.U = Hs / G;
-      if (cudaFuncSetAttribute(lstm_bwd_bs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bs)) != cudaSuccess)
+      void (*kern)(const LstmBsP) = (Hs == 896) ? lstm_bwd_bs_kernel<7> : lstm_bwd_bs_kernel<0>;   // Hs/128 k-steps per warp and chunk
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bs)) != cudaSuccess)
         return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: cannot set smem attribute");
       if (cudaMemsetAsync(barrier, 0, sizeof(uint32_t) * S, st0) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: memset failed");
       void* args[] = {&q};
-      cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_bwd_bs_kernel), dim3(S * G), dim3(LTHREADS), args, smem_bs, st0);
+      cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(S * G), dim3(LTHREADS), args, smem_bs, st0);
       MTASR_COUNT_LAUNCH();
       if (e != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: cooperative launch failed: %s", cudaGetErrorString(e));
       return MTASR_OK;
