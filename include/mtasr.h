@@ -31,6 +31,7 @@ extern "C" {
 
 #define MTASR_DT_BF16 0
 #define MTASR_DT_F32 1
+#define MTASR_DT_F16 2 /* only as the optional logits output of mtasr_gemm_bf16 mode 1 and the input of mtasr_softmax_from_logits */
 
 int mtasr_version(void);
 const char* mtasr_last_error_string(void);
@@ -67,8 +68,11 @@ int mtasr_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launche
  * the pre-activation); v = act(v); v += residual[..]; if accumulate: v += C_old; C = v.
  *  act 3 / act 4 are the backward forms: v *= gelu'(residual) / v *= (residual > 0), with `residual` holding the
  *  saved pre-activation (GELU) or activation output (ReLU) instead of being added.
- *  mode 1 (LSE partials, ref:models/ctc.py:53 log_softmax fused): nothing is written to C; for every row and
- *    N-tile writes {max, sum exp(v-max), argmax index} to lse_part[(b*M+m)*n_tiles + n_tile] (float4, .w unused).
+ *  mode 1 (LSE partials, ref:models/ctc.py:53 log_softmax fused): for every row and N-tile writes
+ *    {max, sum exp(v-max), argmax index} to lse_part[(b*M+m)*n_tiles + n_tile] (float4, .w unused).  C is optional:
+ *    NULL = no tensor output (inference); otherwise c_dtype must be MTASR_DT_F16 and the logits tile v is also written
+ *    as fp16 (the training forward keeps it so that the backward turns it into softmax * upstream with one streaming
+ *    pass, mtasr_softmax_from_logits, instead of repeating the vocabulary GEMM).
  *  mode 2 (softmax regeneration for the backward): C = exp(v - row_vec[b*M+m]) * row_scale[b*M+m].
  */
 typedef struct mtasr_gemm_desc {
@@ -175,6 +179,10 @@ int mtasr_cast_f32_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
  * tensor core's accumulation truncates).  terms 6: three-way split x = x1 + x2 + x3, A side [a3|a2|a1|a2|a1|a1],
  * B side [b1|b2|b3|b1|b2|b1] (all products down to 2^-24). */
 int mtasr_split_bf16(const float* x, int64_t n, int32_t c, int32_t order, int32_t terms, void* y_bf16, void* stream);
+/* P[r][v] (bf16, row stride ld) = exp(logits[r][v] - lse[r]) * rowscale[r] for v < V; logits fp16 (row stride ld, written by
+ * mtasr_gemm_bf16 mode 1), ld % 8 == 0.  The dense term of d nll / d logits of the CTC head (ref:models/ctc.py:53-54). */
+int mtasr_softmax_from_logits(const void* logits_f16, const float* lse, const float* rowscale, int64_t rows, int32_t V,
+                              int64_t ld, void* P_bf16, void* stream);
 /* out[n] = sum_m x[m][n] (bias gradients) */
 int mtasr_colsum(const void* x, int32_t dtype, int64_t M, int32_t N, int64_t ld, float* out, void* stream);
 /* gru_rel_pos gate of hf:167-176 for every (b, t, head), head_dim 64: wab (128) = [sum of weight rows 0..3 | rows 4..7]

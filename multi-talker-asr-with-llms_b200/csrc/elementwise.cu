@@ -1,6 +1,8 @@
 // HBM-bound row kernels of the hot path: LayerNorm fwd/bwd (+GELU), casts, column sums, attention softmax with
 // the gated relative-position bias folded in (fwd/bwd), padding copies, GLU.  All use 128-bit accesses, one warp
 // per row, grid-stride over rows with grids sized to a multiple of the SM count.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mtasr {
@@ -251,6 +253,39 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, long long n8, int
     } else {
       st8_bf16(o, p1); st8_bf16(o + cs, p2); st8_bf16(o + 2 * cs, p3);
       st8_bf16(o + 3 * cs, p1); st8_bf16(o + 4 * cs, p2); st8_bf16(o + 5 * cs, p1);
+    }
+  }
+}
+
+// P = exp(logit - lse[row]) * rowscale[row]: fp16 logits (vocab GEMM mode 1) -> bf16 softmax * upstream gradient.
+// One CTA per row, 128-bit loads / stores; pure streaming (2 B read + 2 B written per element).
+__global__ void __launch_bounds__(256)
+softmax_from_logits_kernel(const __half* __restrict__ lg, const float* __restrict__ lse, const float* __restrict__ rowscale,
+                           long long rows, int V, long long ld, __nv_bfloat16* __restrict__ P) {
+  const int V8 = (V + 7) >> 3;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float nl = -lse[row] * 1.4426950408889634f;
+    const float rsc = rowscale[row];
+    const uint4* src = reinterpret_cast<const uint4*>(lg + row * ld);
+    uint4* dst = reinterpret_cast<uint4*>(P + row * ld);
+    if (rsc == 0.f) {   // padded frames / infeasible utterances: no need to read the logits
+      for (int i = threadIdx.x; i < V8; i += blockDim.x) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+    for (int i = threadIdx.x; i < V8; i += blockDim.x) {
+      const uint4 u = src[i];
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        const int col = i * 8 + j * 2;
+        const float p0 = col < V ? ex2_approx(fmaf(f.x, 1.4426950408889634f, nl)) * rsc : 0.f;       // tail columns inside ld: 0
+        const float p1 = col + 1 < V ? ex2_approx(fmaf(f.y, 1.4426950408889634f, nl)) * rsc : 0.f;
+        ow[j] = pack_bf16x2(p0, p1);
+      }
+      dst[i] = o;
     }
   }
 }
@@ -708,6 +743,19 @@ extern "C" int mtasr_cast_f32_bf16(const float* x, void* y, int64_t n, void* str
     MTASR_COUNT_LAUNCH();
   }
   MTASR_CHECK_LAUNCH("cast_f32_bf16");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_softmax_from_logits(const void* logits_f16, const float* lse, const float* rowscale, int64_t rows, int32_t V,
+                                         int64_t ld, void* P_bf16, void* stream) {
+  MTASR_CHECK_ARG(logits_f16 && lse && rowscale && P_bf16 && rows > 0 && V > 0 && ld >= V && ld % 8 == 0, "softmax_from_logits: bad arguments");
+  MTASR_CHECK_ARG((reinterpret_cast<uintptr_t>(logits_f16) & 15) == 0 && (reinterpret_cast<uintptr_t>(P_bf16) & 15) == 0,
+                  "softmax_from_logits: unaligned pointer");
+  const long long grid = rows < static_cast<long long>(num_sms()) * 8 ? rows : static_cast<long long>(num_sms()) * 8;
+  softmax_from_logits_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(logits_f16), lse, rowscale, rows, V, ld, reinterpret_cast<__nv_bfloat16*>(P_bf16));
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("softmax_from_logits");
   return MTASR_OK;
 }
 

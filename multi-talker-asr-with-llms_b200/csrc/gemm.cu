@@ -19,6 +19,8 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -127,8 +129,18 @@ __device__ __forceinline__ uint32_t swz(uint32_t off) { return off ^ (((off >> 7
 
 // Boxes whose rows are 128 bytes (64 bf16 / 32 fp32 columns) use SWIZZLE_128B; the narrow 64-byte rows (bf16 tensors in
 // a 32-column group, i.e. a bf16 tensor next to an fp32 one) are plain row-major (SWIZZLE_NONE).
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
 __device__ __forceinline__ void stg_store8(uint8_t* buf, int dtype, int row, int gw, int c8, const float (&v)[8]) {
-  if (dtype == MTASR_DT_BF16) {
+  if (dtype == MTASR_DT_F16) {
+    uint4 u;
+    u.x = pack_f16x2(v[0], v[1]); u.y = pack_f16x2(v[2], v[3]);
+    u.z = pack_f16x2(v[4], v[5]); u.w = pack_f16x2(v[6], v[7]);
+    const uint32_t off = static_cast<uint32_t>(row * gw * 2 + c8 * 16);
+    *reinterpret_cast<uint4*>(buf + (gw == 64 ? swz(off) : off)) = u;
+  } else if (dtype == MTASR_DT_BF16) {
     uint4 u;
     u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
     u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
@@ -192,7 +204,9 @@ struct Epi {
   static constexpr bool GEN = (CFG & CFG_GENERIC) != 0;
   __device__ __forceinline__ static int mode(const GemmKP& p) { return GEN ? p.mode : (CFG & 3); }
   __device__ __forceinline__ static int act(const GemmKP& p) { return GEN ? p.act : ((CFG >> 2) & 7); }
-  __device__ __forceinline__ static bool aux(const GemmKP& p) { return GEN ? (p.aux != nullptr) : ((CFG & 32) != 0); }
+  __device__ __forceinline__ static bool aux(const GemmKP& p) { return GEN ? (p.aux != nullptr) : ((CFG & 32) != 0 && (CFG & 3) != 1); }
+  // mode 1 + the aux bit: the logits tile is ALSO written (fp16) next to the LSE partials (CTC head forward for training)
+  __device__ __forceinline__ static bool store1(const GemmKP& p) { return GEN ? (p.mode == 1 && p.c != nullptr) : ((CFG & 3) == 1 && (CFG & 32) != 0); }
   __device__ __forceinline__ static bool res(const GemmKP& p) { return GEN ? (p.residual != nullptr) : ((CFG & 64) != 0); }
   __device__ __forceinline__ static bool tma(const GemmKP& p) { return GEN ? (p.tma_epi != 0) : true; }
   __device__ __forceinline__ static bool res_tma(const GemmKP& p) { return GEN ? (p.tma_epi && p.stg_res >= 0) : ((CFG & 64) != 0); }
@@ -209,12 +223,14 @@ __device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMa
   using E = Epi<CFG>;
   const int mode = E::mode(p), act = E::act(p);
   const bool has_aux = E::aux(p), has_res = E::res(p), tma = E::tma(p), res_tma = E::res_tma(p);
+  const bool store1 = E::store1(p);
+  const bool tma_out = tma && (mode != 1 || store1);
   const int col0 = t.n_tile * p.block_n + g * GW;
   const int row0 = t.m_tile * BM + q * 32;
   uint8_t* stg_c = stg;
   uint8_t* stg_aux = stg + (p.stg_aux > 0 ? p.stg_aux : 0) * STG_BYTES;
   uint8_t* stg_r = stg + (p.stg_res > 0 ? p.stg_res : 0) * STG_BYTES;
-  if (tma && mode != 1) {
+  if (tma_out) {
     // the previous group's bulk stores must have finished READING the staging buffers before they are rewritten
     if (lane == 0) bulk_wait_read<0>();
     if (res_tma) fence_proxy_async();   // this warp's generic reads of the residual box precede its async overwrite
@@ -263,6 +279,7 @@ __device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMa
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
+      if (store1) stg_store8(stg_c, MTASR_DT_F16, lane, GW, c8, v);   // columns >= N are clipped by the TMA store
       float cm = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -280,12 +297,13 @@ __device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMa
 #pragma unroll
       for (int j = 0; j < 8; ++j) run_sum += ex2_approx(fmaf(v[j], 1.4426950408889634f, nm));
     }
-    return;
+    if (!store1) return;
   }
 
   const float nrv = -rvec * 1.4426950408889634f;
 #pragma unroll
   for (int c8 = 0; c8 < GW / 8; ++c8) {
+    if (mode == 1) break;
     const int col = col0 + c8 * 8;
     if (col >= p.N) break;   // warp-uniform
     const int nv = min(8, p.N - col);
@@ -346,7 +364,7 @@ __device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMa
     if (tma) stg_store8(stg_c, p.c_dtype, lane, GW, c8, v);
     else if (row_ok) store8(p.c, p.c_dtype, c_off + col, nv, v);
   }
-  if (tma) {
+  if (tma_out) {
     fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
     __syncwarp();
     if (lane == 0) {
@@ -618,7 +636,8 @@ static const KernelEntry kKernels[] = {
     MTASR_GEMM_CFG(0, 2, true, false),   // ReLU + tap: separator projections
     MTASR_GEMM_CFG(0, 3, false, true),   // GELU backward: FFN2 dgrad
     MTASR_GEMM_CFG(0, 4, false, true),   // ReLU backward
-    MTASR_GEMM_CFG(1, 0, false, false),  // row LSE / argmax partials: CTC head forward, greedy argmax
+    MTASR_GEMM_CFG(1, 0, false, false),  // row LSE / argmax partials: greedy argmax, CTC head forward without autograd
+    MTASR_GEMM_CFG(1, 0, true, false),   // row LSE partials + fp16 logits tile: CTC head forward for training
     MTASR_GEMM_CFG(2, 0, false, false),  // softmax regeneration: CTC head backward
     {CFG_GENERIC, gemm_bf16_kernel<CFG_GENERIC, 1>, gemm_bf16_kernel<CFG_GENERIC, 2>},
 };
@@ -730,6 +749,9 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   MTASR_CHECK_ARG(d->a && d->b, "gemm: null operand");
   MTASR_CHECK_ARG(d->mode >= 0 && d->mode <= 2, "gemm: bad mode %d", d->mode);
   MTASR_CHECK_ARG(d->mode == 1 ? d->lse_part != nullptr : d->c != nullptr, "gemm: missing output buffer");
+  MTASR_CHECK_ARG(d->mode == 1 ? (d->c == nullptr || d->c_dtype == MTASR_DT_F16) : (d->c_dtype == MTASR_DT_BF16 || d->c_dtype == MTASR_DT_F32),
+                  "gemm: C must be bf16 / f32 (mode 0, 2) or f16 (optional logits output of mode 1), got dtype %d", d->c_dtype);
+  MTASR_CHECK_ARG(d->mode != 1 || d->c == nullptr || (!d->accumulate && !d->aux && !d->residual), "gemm: mode 1 takes no aux / residual / accumulate");
   MTASR_CHECK_ARG(d->mode != 2 || d->row_vec != nullptr, "gemm: mode 2 needs row_vec");
 
   GemmKP p;
@@ -823,8 +845,9 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   const bool any_f32 = (d->mode != 1 && d->c_dtype == MTASR_DT_F32) || (d->residual && d->res_dtype == MTASR_DT_F32);
   p.gw = any_f32 ? 32 : 64;
   if (bn < p.gw) p.gw = bn;
-  if (d->mode != 1 && !d->accumulate && getenv("MTASR_GEMM_DIRECT_EPILOGUE") == nullptr) {
-    bool ok = encode_out_map(&mc, d->c, d->c_dtype, d->M, d->N, d->batch0, d->batch1, d->c_ld, d->c_sb0, d->c_sb1, p.gw) == 0;
+  const bool store1 = d->mode == 1 && d->c != nullptr;
+  if (store1 || (d->mode != 1 && !d->accumulate && getenv("MTASR_GEMM_DIRECT_EPILOGUE") == nullptr)) {
+    bool ok = encode_out_map(&mc, d->c, store1 ? MTASR_DT_BF16 /* 2-byte elements */ : d->c_dtype, d->M, d->N, d->batch0, d->batch1, d->c_ld, d->c_sb0, d->c_sb1, p.gw) == 0;
     int n = 1;
     if (ok && d->aux) {
       ok = encode_out_map(&maux, d->aux, MTASR_DT_BF16, d->M, d->N, d->batch0, d->batch1, d->c_ld, d->c_sb0, d->c_sb1, p.gw) == 0;
@@ -841,6 +864,7 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
       p.n_stg = n;
     } else {
       p.stg_aux = p.stg_res = -1;
+      if (store1) return set_error(MTASR_ERR_INVALID_ARG, "gemm: the mode-1 logits output needs a 16-byte aligned C with c_ld %% 8 == 0");
     }
   }
   // split-K: an un-batched plain fp32 GEMM that would leave more than half of the SMs idle (the K = B*T weight-gradient
@@ -897,7 +921,7 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   const bool special_ok = getenv("MTASR_GEMM_GENERIC") == nullptr && !d->accumulate &&
                           (d->mode == 1 || (p.tma_epi && (!d->residual || p.stg_res >= 0)));
   if (special_ok) {
-    const int want = make_cfg(d->mode, d->mode == 0 ? d->act : 0, d->mode == 0 && d->aux != nullptr,
+    const int want = make_cfg(d->mode, d->mode == 0 ? d->act : 0, (d->mode == 0 && d->aux != nullptr) || store1,
                               d->mode == 0 && d->residual != nullptr);
     for (const KernelEntry& k : kKernels)
       if (k.cfg == want) entry = &k;

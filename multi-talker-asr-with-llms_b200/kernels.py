@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import GemmDesc, check
 
-BF16, F32 = 0, 1
+BF16, F32, F16 = 0, 1, 2
 ACT_NONE, ACT_GELU, ACT_RELU, ACT_GELU_BWD, ACT_RELU_BWD = 0, 1, 2, 3, 4
 
 
@@ -22,6 +22,8 @@ def _dt(t: torch.Tensor) -> int:
         return BF16
     if t.dtype == torch.float32:
         return F32
+    if t.dtype == torch.float16:
+        return F16
     raise TypeError(f"unsupported dtype {t.dtype}")
 
 
@@ -233,6 +235,15 @@ def attn_softmax_fwd_split(S, gate, table, klen, B, H, T, Tp, scale, terms):
     check(_lib.load().mtasr_attn_softmax_fwd_split(_p(S), _p(gate), _p(table), _p(klen), B, H, T, Tp, scale, terms, _p(Ps), _stream()),
           "mtasr_attn_softmax_fwd_split")
     return Ps
+
+
+def softmax_from_logits(logits16: torch.Tensor, lse: torch.Tensor, rowscale: torch.Tensor, V: int) -> torch.Tensor:
+    """(rows, ld) fp16 logits -> (rows, ld) bf16 exp(logit - lse[row]) * rowscale[row] (columns >= V unspecified)."""
+    rows, ld = logits16.shape
+    P = torch.empty(rows, ld, device=logits16.device, dtype=torch.bfloat16)
+    check(_lib.load().mtasr_softmax_from_logits(_p(logits16), _p(lse), _p(rowscale), rows, V, ld, _p(P), _stream()),
+          "mtasr_softmax_from_logits")
+    return P
 
 
 def colsum(x: torch.Tensor) -> torch.Tensor:

@@ -20,6 +20,9 @@ F32 = torch.float32
 
 _bf16_cache = {}
 _UNFUSED_ATTN = os.environ.get("MTASR_UNFUSED_ATTN", "") not in ("", "0")   # debugging / A-B switch: materialise S and P
+# CTC head: keep the fp16 logits of the forward vocabulary GEMM for the backward (2 B x B*T x V per head, 4.1 GB at cfg2)
+# instead of regenerating the softmax with a second vocabulary GEMM.  "0" = memory-lean recompute path.
+_CTC_KEEP_LOGITS = os.environ.get("MTASR_CTC_KEEP_LOGITS", "1") not in ("", "0")
 
 
 def bf16_of(p: torch.Tensor) -> torch.Tensor:
@@ -448,7 +451,10 @@ class CTCHeadFn(Function):
         bf = bias.detach().float()
         nt = K.gemm_n_tiles(V)
         part = torch.empty(B * T, nt, 4, device=hs.device, dtype=F32)
-        K.gemm(K.Operand(hb, D), K.Operand(wb, D), B * T, V, D, None, bias=bf, mode=1, lse_part=part)
+        Vp = (V + 7) // 8 * 8
+        keep = _CTC_KEEP_LOGITS and any(ctx.needs_input_grad[:3])
+        logits16 = torch.empty(B * T, Vp, device=hs.device, dtype=torch.float16) if keep else None
+        K.gemm(K.Operand(hb, D), K.Operand(wb, D), B * T, V, D, K.Out(logits16, Vp) if keep else None, bias=bf, mode=1, lse_part=part)
         lse, _ = K.lse_finalize(part, B * T, nt)
         del part
         Lmax = int(ys.shape[1]) if ys.numel() else 0
@@ -464,20 +470,23 @@ class CTCHeadFn(Function):
         nll, nll_raw, alpha, coff = K.ctc_alpha_fwd(glog, lse, ys, hlens, ylens, Lmax)
         ctx.dims = (B, T, D, V, Lp, Lmax, blank)
         ctx.hs_dtype = hs.dtype
-        ctx.save_for_backward(hb, wb, bf, wg, glog, lse, alpha, coff, nll_raw, hlens, ys, ylens)
+        ctx.save_for_backward(hb, wb, bf, wg, glog, lse, alpha, coff, nll_raw, hlens, ys, ylens, logits16)
         return nll
 
     @staticmethod
     def backward(ctx, gout):
-        hb, wb, bf, wg, glog, lse, alpha, coff, nll_raw, hlens, ys, ylens = ctx.saved_tensors
+        hb, wb, bf, wg, glog, lse, alpha, coff, nll_raw, hlens, ys, ylens, logits16 = ctx.saved_tensors
         B, T, D, V, Lp, Lmax, blank = ctx.dims
         dev = gout.device
         dG, rowscale = K.ctc_beta_bwd(glog, lse, ys, hlens, ylens, Lmax, alpha, coff, nll_raw, gout.contiguous().float())
         dGb = K.cast_bf16(dG)
         Vp = (V + 7) // 8 * 8
-        P = torch.empty(B * T, Vp, device=dev, dtype=BF)                       # softmax * upstream, regenerated
-        K.gemm(K.Operand(hb, D), K.Operand(wb, D), B * T, V, D, K.Out(P, Vp), bias=bf, mode=2, row_vec=lse.view(-1),
-               row_scale=rowscale.view(-1))
+        if logits16 is not None:                                               # softmax * upstream from the kept logits
+            P = K.softmax_from_logits(logits16, lse.view(-1), rowscale.view(-1), V)
+        else:                                                                  # ... or regenerated by a second vocab GEMM
+            P = torch.empty(B * T, Vp, device=dev, dtype=BF)
+            K.gemm(K.Operand(hb, D), K.Operand(wb, D), B * T, V, D, K.Out(P, Vp), bias=bf, mode=2, row_vec=lse.view(-1),
+                   row_scale=rowscale.view(-1))
         dh = dw = db = None
         if ctx.needs_input_grad[0]:
             dhf = torch.empty(B * T, D, device=dev, dtype=F32)

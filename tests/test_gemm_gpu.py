@@ -166,6 +166,19 @@ def test_lse_and_exp_modes(cuda, V):
     Kn.gemm(Kn.Operand(h, K), Kn.Operand(w, K), M, V, K, Kn.Out(Pm, Pm.stride(0)), bias=bias, mode=2, row_vec=lse, row_scale=scale)
     ref = torch.softmax(logits, -1) * scale[:, None]
     assert _rel(Pm[:, :V], ref) < 5e-3
+    # mode 1 with the optional fp16 logits output, and the streaming softmax built from it (same LSE partials as without)
+    Vp = (V + 7) // 8 * 8
+    lg16 = torch.full((M, Vp), float("nan"), device=cuda, dtype=torch.float16)
+    part2 = torch.empty(M, nt, 4, device=cuda)
+    Kn.gemm(Kn.Operand(h, K), Kn.Operand(w, K), M, V, K, Kn.Out(lg16, Vp), bias=bias, mode=1, lse_part=part2)
+    lse2, am2 = Kn.lse_finalize(part2, M, nt, want_argmax=True)
+    assert torch.equal(lse2, lse) and torch.equal(am2, am)
+    assert (lg16[:, :V].float() - logits).abs().max() < 2e-3 * logits.abs().max()
+    scale[5] = 0.0
+    P2 = Kn.softmax_from_logits(lg16, lse, scale, V)
+    ref = torch.softmax(logits, -1) * scale[:, None]
+    assert _rel(P2[:, :V], ref) < 5e-3
+    assert P2[5].abs().max().item() == 0.0 and (Vp == V or P2[:, V:].abs().max().item() == 0.0)
 
 
 @pytest.mark.parametrize("M,N,K", [(1024, 1024, 15968), (896, 128, 4000), (256, 192, 7000)])
