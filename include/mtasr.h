@@ -180,9 +180,16 @@ int mtasr_cast_f32_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
  * B side [b1|b2|b3|b1|b2|b1] (all products down to 2^-24). */
 int mtasr_split_bf16(const float* x, int64_t n, int32_t c, int32_t order, int32_t terms, void* y_bf16, void* stream);
 /* P[r][v] (bf16, row stride ld) = exp(logits[r][v] - lse[r]) * rowscale[r] for v < V; logits fp16 (row stride ld, written by
- * mtasr_gemm_bf16 mode 1), ld % 8 == 0.  The dense term of d nll / d logits of the CTC head (ref:models/ctc.py:53-54). */
+ * mtasr_gemm_bf16 mode 1), ld % 8 == 0.  The dense term of d nll / d logits of the CTC head (ref:models/ctc.py:53-54).
+ * colsum (V) f32, optional: column sums of P (the dense part of the bias gradient) are ACCUMULATED into it (zero it first). */
 int mtasr_softmax_from_logits(const void* logits_f16, const float* lse, const float* rowscale, int64_t rows, int32_t V,
-                              int64_t ld, void* P_bf16, void* stream);
+                              int64_t ld, void* P_bf16, float* colsum, void* stream);
+/* weight_norm over the last dim (torch.nn.utils.parametrizations.weight_norm(conv, dim=2), hf:48-66): v (R, Kt) f32 with
+ * R = all leading dims flattened, g (Kt); w = g v / ||v[:, c]||.  sumsq (Kt) and dot (Kt) are ACCUMULATED scratch (zero them
+ * first); sumsq from the forward is an input of the backward.  dv (R, Kt), dg (Kt) written.  Kt must divide 256. */
+int mtasr_weightnorm_fwd(const float* v, const float* g, int64_t R, int32_t Kt, float* w, float* sumsq, void* stream);
+int mtasr_weightnorm_bwd(const float* dw, const float* v, const float* g, const float* sumsq, int64_t R, int32_t Kt, float* dv,
+                         float* dg, float* dot, void* stream);
 /* out[n] = sum_m x[m][n] (bias gradients) */
 int mtasr_colsum(const void* x, int32_t dtype, int64_t M, int32_t N, int64_t ld, float* out, void* stream);
 /* gru_rel_pos gate of hf:167-176 for every (b, t, head), head_dim 64: wab (128) = [sum of weight rows 0..3 | rows 4..7]

@@ -257,37 +257,85 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, long long n8, int
   }
 }
 
-// P = exp(logit - lse[row]) * rowscale[row]: fp16 logits (vocab GEMM mode 1) -> bf16 softmax * upstream gradient.
-// One CTA per row, 128-bit loads / stores; pure streaming (2 B read + 2 B written per element).
+// P = exp(logit - lse[row]) * rowscale[row]: fp16 logits (vocab GEMM mode 1) -> bf16 softmax * upstream gradient, plus
+// (optionally) its column sums = the bias gradient, so that P is not re-read by a separate reduction.  Pure streaming
+// (2 B read + 2 B written per element): CTA (x, y) owns 2048 columns (one 128-bit piece per thread and row) of row group
+// y; the 8 column sums of a thread live in registers over its rows and leave with one atomic per column at the end.
 __global__ void __launch_bounds__(256)
 softmax_from_logits_kernel(const __half* __restrict__ lg, const float* __restrict__ lse, const float* __restrict__ rowscale,
-                           long long rows, int V, long long ld, __nv_bfloat16* __restrict__ P) {
-  const int V8 = (V + 7) >> 3;
-  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
-    const float nl = -lse[row] * 1.4426950408889634f;
+                           long long rows, int V, long long ld, long long rows_per_group, __nv_bfloat16* __restrict__ P,
+                           float* __restrict__ colsum) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;     // 8-column piece
+  if (i * 8 >= V) return;
+  const long long r0 = blockIdx.y * rows_per_group;
+  const long long r1 = r0 + rows_per_group < rows ? r0 + rows_per_group : rows;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long row = r0; row < r1; ++row) {
     const float rsc = rowscale[row];
-    const uint4* src = reinterpret_cast<const uint4*>(lg + row * ld);
-    uint4* dst = reinterpret_cast<uint4*>(P + row * ld);
+    uint4* dst = reinterpret_cast<uint4*>(P + row * ld) + i;
     if (rsc == 0.f) {   // padded frames / infeasible utterances: no need to read the logits
-      for (int i = threadIdx.x; i < V8; i += blockDim.x) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+      *dst = make_uint4(0u, 0u, 0u, 0u);
       continue;
     }
-    for (int i = threadIdx.x; i < V8; i += blockDim.x) {
-      const uint4 u = src[i];
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
-      uint4 o;
-      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+    const float nl = -lse[row] * 1.4426950408889634f;
+    const uint4 u = reinterpret_cast<const uint4*>(lg + row * ld)[i];
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h[j]);
-        const int col = i * 8 + j * 2;
-        const float p0 = col < V ? ex2_approx(fmaf(f.x, 1.4426950408889634f, nl)) * rsc : 0.f;       // tail columns inside ld: 0
-        const float p1 = col + 1 < V ? ex2_approx(fmaf(f.y, 1.4426950408889634f, nl)) * rsc : 0.f;
-        ow[j] = pack_bf16x2(p0, p1);
-      }
-      dst[i] = o;
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      const int col = i * 8 + j * 2;
+      const float p0 = col < V ? ex2_approx(fmaf(f.x, 1.4426950408889634f, nl)) * rsc : 0.f;       // tail columns inside ld: 0
+      const float p1 = col + 1 < V ? ex2_approx(fmaf(f.y, 1.4426950408889634f, nl)) * rsc : 0.f;
+      ow[j] = pack_bf16x2(p0, p1);
+      acc[j * 2] += p0;
+      acc[j * 2 + 1] += p1;
     }
+    *dst = o;
   }
+  if (colsum) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (i * 8 + j < V) atomicAdd(colsum + i * 8 + j, acc[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ weight norm (last dim)
+// torch.nn.utils.parametrizations.weight_norm(conv, dim=2) of the positional conv (hf:48-66): w[r][c] = g[c] v[r][c] / ||v[:, c]||
+// with the norm over all rows r = (out, in) of tap c.  Column reductions over the (R, Kt) matrix + one elementwise pass.
+template <bool DOT>
+__global__ void __launch_bounds__(256)
+wn_colreduce_kernel(const float* __restrict__ a, const float* __restrict__ b, long long R, int Kt, float* __restrict__ out) {
+  __shared__ float red[256];
+  const int c = threadIdx.x % Kt, lr = threadIdx.x / Kt, nr = blockDim.x / Kt;
+  float acc = 0.f;
+  for (long long r = static_cast<long long>(blockIdx.x) * nr + lr; r < R; r += static_cast<long long>(gridDim.x) * nr) {
+    const float x = a[r * Kt + c];
+    acc = fmaf(x, DOT ? b[r * Kt + c] : x, acc);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (lr == 0) {
+    for (int i = 1; i < nr; ++i) acc += red[i * Kt + c];
+    atomicAdd(out + c, acc);
+  }
+}
+// fwd: w = v * g / sqrt(sumsq);  bwd: dv = (g / n) (dw - v dot / n^2), n = sqrt(sumsq), dot = sum_r dw v
+__global__ void wn_apply_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ sumsq,
+                                const float* __restrict__ dw, const float* __restrict__ dot, long long n, int Kt,
+                                float* __restrict__ out) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Kt);
+    const float inv = rsqrtf(sumsq[c]);
+    if (dw == nullptr) out[i] = v[i] * g[c] * inv;
+    else out[i] = g[c] * inv * (dw[i] - v[i] * dot[c] * inv * inv);
+  }
+}
+__global__ void wn_dg_kernel(const float* __restrict__ dot, const float* __restrict__ sumsq, int Kt, float* __restrict__ dg) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < Kt) dg[c] = dot[c] * rsqrtf(sumsq[c]);
 }
 
 // out[n] += sum_m x[m][n]  (bias gradients).  Vector path (N % 8 == 0, 16-byte aligned rows): each thread owns 8
@@ -747,15 +795,45 @@ extern "C" int mtasr_cast_f32_bf16(const float* x, void* y, int64_t n, void* str
 }
 
 extern "C" int mtasr_softmax_from_logits(const void* logits_f16, const float* lse, const float* rowscale, int64_t rows, int32_t V,
-                                         int64_t ld, void* P_bf16, void* stream) {
+                                         int64_t ld, void* P_bf16, float* colsum, void* stream) {
   MTASR_CHECK_ARG(logits_f16 && lse && rowscale && P_bf16 && rows > 0 && V > 0 && ld >= V && ld % 8 == 0, "softmax_from_logits: bad arguments");
   MTASR_CHECK_ARG((reinterpret_cast<uintptr_t>(logits_f16) & 15) == 0 && (reinterpret_cast<uintptr_t>(P_bf16) & 15) == 0,
                   "softmax_from_logits: unaligned pointer");
-  const long long grid = rows < static_cast<long long>(num_sms()) * 8 ? rows : static_cast<long long>(num_sms()) * 8;
-  softmax_from_logits_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half*>(logits_f16), lse, rowscale, rows, V, ld, reinterpret_cast<__nv_bfloat16*>(P_bf16));
+  const int col_blocks = ((V + 7) / 8 + 255) / 256;
+  long long groups = (static_cast<long long>(num_sms()) * 8 + col_blocks - 1) / col_blocks;
+  if (groups > rows) groups = rows;
+  if (groups > 65535) groups = 65535;
+  const long long rpg = (rows + groups - 1) / groups;
+  groups = (rows + rpg - 1) / rpg;
+  softmax_from_logits_kernel<<<dim3(col_blocks, static_cast<unsigned>(groups)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(logits_f16), lse, rowscale, rows, V, ld, rpg, reinterpret_cast<__nv_bfloat16*>(P_bf16), colsum);
   MTASR_COUNT_LAUNCH();
   MTASR_CHECK_LAUNCH("softmax_from_logits");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_weightnorm_fwd(const float* v, const float* g, int64_t R, int32_t Kt, float* w, float* sumsq, void* stream) {
+  MTASR_CHECK_ARG(v && g && w && sumsq && R > 0 && Kt > 0 && Kt <= 256 && 256 % Kt == 0, "weightnorm_fwd: need Kt | 256 (Kt=%d)", Kt);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  wn_colreduce_kernel<false><<<num_sms(), 256, 0, st>>>(v, nullptr, R, Kt, sumsq);
+  MTASR_COUNT_LAUNCH();
+  wn_apply_kernel<<<grid_for(R * Kt, 256), 256, 0, st>>>(v, g, sumsq, nullptr, nullptr, R * Kt, Kt, w);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("weightnorm_fwd");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_weightnorm_bwd(const float* dw, const float* v, const float* g, const float* sumsq, int64_t R, int32_t Kt,
+                                    float* dv, float* dg, float* dot, void* stream) {
+  MTASR_CHECK_ARG(dw && v && g && sumsq && dv && dg && dot && R > 0 && Kt > 0 && Kt <= 256 && 256 % Kt == 0, "weightnorm_bwd: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  wn_colreduce_kernel<true><<<num_sms(), 256, 0, st>>>(dw, v, R, Kt, dot);
+  MTASR_COUNT_LAUNCH();
+  wn_apply_kernel<<<grid_for(R * Kt, 256), 256, 0, st>>>(v, g, sumsq, dw, dot, R * Kt, Kt, dv);
+  MTASR_COUNT_LAUNCH();
+  wn_dg_kernel<<<(Kt + 127) / 128, 128, 0, st>>>(dot, sumsq, Kt, dg);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("weightnorm_bwd");
   return MTASR_OK;
 }
 

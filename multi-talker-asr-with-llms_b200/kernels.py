@@ -201,8 +201,8 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: t
     dy = dy.contiguous()
     dxf = torch.empty(x.shape, device=x.device, dtype=torch.float32) if want_f32 else None
     dxb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
-    dg = torch.zeros(D, device=x.device, dtype=torch.float32) if want_param_grads else None
-    db = torch.zeros(D, device=x.device, dtype=torch.float32) if want_param_grads else None
+    dgb = torch.zeros(2, D, device=x.device, dtype=torch.float32) if want_param_grads else None   # one fill for both
+    dg, db = (dgb[0], dgb[1]) if want_param_grads else (None, None)
     check(_lib.load().mtasr_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma), _p(dres), rows, D,
                                           _p(dxf), _p(dxb), _p(dg), _p(db), _stream()), "mtasr_layernorm_bwd")
     return dxf, dxb, dg, db
@@ -237,13 +237,36 @@ def attn_softmax_fwd_split(S, gate, table, klen, B, H, T, Tp, scale, terms):
     return Ps
 
 
-def softmax_from_logits(logits16: torch.Tensor, lse: torch.Tensor, rowscale: torch.Tensor, V: int) -> torch.Tensor:
-    """(rows, ld) fp16 logits -> (rows, ld) bf16 exp(logit - lse[row]) * rowscale[row] (columns >= V unspecified)."""
+def softmax_from_logits(logits16: torch.Tensor, lse: torch.Tensor, rowscale: torch.Tensor, V: int, want_colsum: bool = False):
+    """(rows, ld) fp16 logits -> (rows, ld) bf16 exp(logit - lse[row]) * rowscale[row] (columns >= V zero), and optionally
+    the (V,) fp32 column sums of it."""
     rows, ld = logits16.shape
     P = torch.empty(rows, ld, device=logits16.device, dtype=torch.bfloat16)
-    check(_lib.load().mtasr_softmax_from_logits(_p(logits16), _p(lse), _p(rowscale), rows, V, ld, _p(P), _stream()),
+    cs = torch.zeros(V, device=logits16.device, dtype=torch.float32) if want_colsum else None
+    check(_lib.load().mtasr_softmax_from_logits(_p(logits16), _p(lse), _p(rowscale), rows, V, ld, _p(P), _p(cs), _stream()),
           "mtasr_softmax_from_logits")
-    return P
+    return (P, cs) if want_colsum else P
+
+
+def weightnorm_fwd(v: torch.Tensor, g: torch.Tensor):
+    """v (..., Kt) f32, g (Kt) -> (w like v, sumsq (Kt))."""
+    v = v.contiguous()
+    Kt = v.shape[-1]
+    w = torch.empty_like(v)
+    sumsq = torch.zeros(Kt, device=v.device, dtype=torch.float32)
+    check(_lib.load().mtasr_weightnorm_fwd(_p(v), _p(g), v.numel() // Kt, Kt, _p(w), _p(sumsq), _stream()), "mtasr_weightnorm_fwd")
+    return w, sumsq
+
+
+def weightnorm_bwd(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor, sumsq: torch.Tensor):
+    dw, v = dw.contiguous(), v.contiguous()
+    Kt = v.shape[-1]
+    dv = torch.empty_like(v)
+    dg = torch.empty(Kt, device=v.device, dtype=torch.float32)
+    dot = torch.zeros(Kt, device=v.device, dtype=torch.float32)
+    check(_lib.load().mtasr_weightnorm_bwd(_p(dw), _p(v), _p(g), _p(sumsq), v.numel() // Kt, Kt, _p(dv), _p(dg), _p(dot), _stream()),
+          "mtasr_weightnorm_bwd")
+    return dv, dg
 
 
 def colsum(x: torch.Tensor) -> torch.Tensor:
@@ -262,9 +285,8 @@ def relpos_gate_fwd(x, wab, bab, cst, B, T, H):
 
 def relpos_gate_bwd(x, wab, bab, cst, dgate, B, T, H):
     dx = torch.empty(B, T, H * 64, device=x.device, dtype=torch.float32)
-    dwab = torch.zeros(128, device=x.device, dtype=torch.float32)
-    dbab = torch.zeros(2, device=x.device, dtype=torch.float32)
-    dcst = torch.zeros(H, device=x.device, dtype=torch.float32)
+    acc = torch.zeros(128 + 4 + H, device=x.device, dtype=torch.float32)                            # one fill for the three
+    dwab, dbab, dcst = acc[:128], acc[128:130], acc[132:132 + H]
     check(_lib.load().mtasr_relpos_gate_bwd(_p(x), _dt(x), _p(wab), _p(bab), _p(cst), _p(dgate), B, T, H, _p(dx), _p(dwab),
                                             _p(dbab), _p(dcst), _stream()), "mtasr_relpos_gate_bwd")
     return dx, dwab, dbab, dcst
@@ -286,8 +308,9 @@ def attn_bwd(qkv, out, dout, lse, gate, table, klen, B, H, T, scale):
     dqkv = torch.empty(B * T, 3 * D, device=dev, dtype=torch.bfloat16)
     dq32 = torch.zeros(B * T, D, device=dev, dtype=torch.float32)
     delta = torch.empty(B, H, T, device=dev, dtype=torch.float32)
-    dgate = torch.zeros(B, H, T, device=dev, dtype=torch.float32)
-    dtable = torch.zeros(H, 2 * T - 1, device=dev, dtype=torch.float32)
+    n_g = (B * H * T + 3) // 4 * 4
+    acc = torch.zeros(n_g + H * (2 * T - 1), device=dev, dtype=torch.float32)                       # one fill for both
+    dgate, dtable = acc[:B * H * T].view(B, H, T), acc[n_g:].view(H, 2 * T - 1)
     check(_lib.load().mtasr_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(gate), _p(table), _p(klen), B, H, T, scale, _p(dqkv),
                                      _p(dq32), _p(delta), _p(dgate), _p(dtable), _stream()), "mtasr_attn_bwd")
     return dqkv, dgate, dtable

@@ -359,7 +359,7 @@ class WavLMModel(WavLMPreTrainedModel):
             hidden = hidden * fmask.unsqueeze(-1).to(hidden.dtype)       # hf:476-479 zero padded frames
             klen = fmask.sum(1).to(torch.int32).contiguous()
         conv = enc.pos_conv_embed.conv
-        hidden = ops.PosConvFn.apply(hidden.contiguous(), conv.weight, conv.bias, conv.groups, None)
+        hidden = ops.PosConvFn.apply(hidden.contiguous(), ops.pos_conv_weight(conv), conv.bias, conv.groups, None)
         if not self.config.do_stable_layer_norm:
             hidden = ops.layer_norm(hidden, enc.layer_norm.weight, enc.layer_norm.bias, enc.layer_norm.eps, F32)
         table = self._relpos_table(T, hidden.device)
@@ -439,7 +439,7 @@ class WavLMModel(WavLMPreTrainedModel):
                 hidden = hidden * fmask.unsqueeze(-1).to(hidden.dtype)
                 klen = fmask.sum(1).to(torch.int32).contiguous()
             conv = enc.pos_conv_embed.conv
-            hidden = precise.pos_conv(hidden.contiguous(), conv.weight, conv.bias, conv.groups)
+            hidden = precise.pos_conv(hidden.contiguous(), ops.pos_conv_weight(conv), conv.bias, conv.groups)
             if not cfg.do_stable_layer_norm:
                 hidden = precise.layer_norm(hidden, enc.layer_norm)
             table = self._relpos_table(T, hidden.device)

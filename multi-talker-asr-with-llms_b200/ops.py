@@ -304,6 +304,38 @@ def _group_pad(x_bf16: torch.Tensor, G: int, cgp: int) -> torch.Tensor:
     return out
 
 
+class WeightNormFn(Function):
+    """w = g * v / ||v|| with the norm over every dim but the last (torch weight_norm(dim=2) of the positional conv,
+    hf:48-66): v = parametrizations.weight.original1 (out, in/groups, k), g = original0 (1, 1, k)."""
+
+    @staticmethod
+    def forward(ctx, v, g):
+        vf, gf = v.detach().float().contiguous(), g.detach().float().reshape(-1).contiguous()
+        w, sumsq = K.weightnorm_fwd(vf, gf)
+        ctx.save_for_backward(vf, gf, sumsq)
+        ctx.g_shape = g.shape
+        return w
+
+    @staticmethod
+    def backward(ctx, dw):
+        vf, gf, sumsq = ctx.saved_tensors
+        dv, dg = K.weightnorm_bwd(dw.float(), vf, gf, sumsq)
+        return (dv if ctx.needs_input_grad[0] else None), (dg.view(ctx.g_shape) if ctx.needs_input_grad[1] else None)
+
+
+def pos_conv_weight(conv) -> torch.Tensor:
+    """The (weight-normalised) kernel of the positional conv.  With the stock torch parametrization (weight_norm over the
+    last dim, 256 % k == 0) the normalisation runs in our kernels; any other set-up reads `conv.weight` (torch computes it)."""
+    pz = getattr(conv, "parametrizations", None)
+    plist = getattr(pz, "weight", None) if pz is not None else None
+    if plist is not None and len(plist) == 1 and type(plist[0]).__name__ == "_WeightNorm" and hasattr(plist, "original0"):
+        v, g = plist.original1, plist.original0
+        dim = plist[0].dim
+        if v.is_cuda and v.dim() == 3 and dim in (2, -1) and g.numel() == v.shape[2] and 256 % v.shape[2] == 0:
+            return WeightNormFn.apply(v, g)
+    return conv.weight
+
+
 class PosConvFn(Function):
     """x + GELU(grouped_conv1d(x, w, bias, k, pad=k//2)[:T])   (hf:48-90 + hf:403/481; `w` is the already
     weight-normalised kernel g*v/||v||, computed by torch so autograd carries the gradient to original0/original1).
@@ -481,8 +513,10 @@ class CTCHeadFn(Function):
         dG, rowscale = K.ctc_beta_bwd(glog, lse, ys, hlens, ylens, Lmax, alpha, coff, nll_raw, gout.contiguous().float())
         dGb = K.cast_bf16(dG)
         Vp = (V + 7) // 8 * 8
+        need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        db_dense = None
         if logits16 is not None:                                               # softmax * upstream from the kept logits
-            P = K.softmax_from_logits(logits16, lse.view(-1), rowscale.view(-1), V)
+            P, db_dense = K.softmax_from_logits(logits16, lse.view(-1), rowscale.view(-1), V, want_colsum=True)
         else:                                                                  # ... or regenerated by a second vocab GEMM
             P = torch.empty(B * T, Vp, device=dev, dtype=BF)
             K.gemm(K.Operand(hb, D), K.Operand(wb, D), B * T, V, D, K.Out(P, Vp), bias=bf, mode=2, row_vec=lse.view(-1),
@@ -494,14 +528,13 @@ class CTCHeadFn(Function):
             K.gemm(K.Operand(dGb, Lp, sb0=T * Lp), K.Operand(wg, D, major=1, sb0=Lp * D), T, D, Lp, K.Out(dhf, D, sb0=T * D),
                    batch=(B, 1), accumulate=True)
             dh = dhf.view(B, T, D).to(ctx.hs_dtype)
-        need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         if need_w or need_b:
             dw = torch.empty(V, D, device=dev, dtype=F32)
             K.gemm(K.Operand(P, Vp, major=1), K.Operand(hb, D, major=1), V, D, B * T, K.Out(dw, D))
             dwg = torch.empty(B, Lp, D, device=dev, dtype=F32)
             K.gemm(K.Operand(dGb, Lp, major=1, sb0=T * Lp, rows=T), K.Operand(hb, D, major=1, sb0=T * D, rows=T), Lp, D, T,
                    K.Out(dwg, D, sb0=Lp * D), batch=(B, 1))
-            db = K.colsum(P)[:V].contiguous()
+            db = db_dense if db_dense is not None else K.colsum(P)[:V].contiguous()
             K.ctc_scatter_rows(dwg, dG.sum(1).contiguous(), ys, ylens, blank, dw, db)
             if not need_w:
                 dw = None

@@ -175,9 +175,10 @@ def test_lse_and_exp_modes(cuda, V):
     assert torch.equal(lse2, lse) and torch.equal(am2, am)
     assert (lg16[:, :V].float() - logits).abs().max() < 2e-3 * logits.abs().max()
     scale[5] = 0.0
-    P2 = Kn.softmax_from_logits(lg16, lse, scale, V)
+    P2, cs = Kn.softmax_from_logits(lg16, lse, scale, V, want_colsum=True)
     ref = torch.softmax(logits, -1) * scale[:, None]
     assert _rel(P2[:, :V], ref) < 5e-3
+    assert _rel(cs, ref.sum(0)) < 2e-3
     assert P2[5].abs().max().item() == 0.0 and (Vp == V or P2[:, V:].abs().max().item() == 0.0)
 
 

@@ -157,3 +157,20 @@ def test_split_bf16_bit_exact_and_gemm_accuracy(cuda, order, terms):
                 M, N, terms * Kd, Kn.Out(out, N))
         ref = (a.double() @ b.double().t()).float()
         assert _rel(out, ref) < (1e-5 if terms == 3 else 1e-6), _rel(out, ref)
+
+
+def test_weightnorm_fwd_bwd(cuda):
+    """WeightNormFn (pos-conv weight_norm over the last dim, hf:48-66) vs torch._weight_norm and its autograd."""
+    from mtasr_b200 import ops
+    torch.manual_seed(3)
+    v = torch.randn(96, 8, 128, device=cuda)
+    g = torch.rand(1, 1, 128, device=cuda) + 0.5
+    v1, g1 = v.clone().requires_grad_(True), g.clone().requires_grad_(True)
+    v2, g2 = v.clone().requires_grad_(True), g.clone().requires_grad_(True)
+    w1 = ops.WeightNormFn.apply(v1, g1)
+    w2 = torch._weight_norm(v2, g2, 2)
+    assert _rel(w1, w2) < 1e-6
+    up = torch.randn_like(w2)
+    d1 = torch.autograd.grad((w1 * up).sum(), [v1, g1])
+    d2 = torch.autograd.grad((w2 * up).sum(), [v2, g2])
+    assert _rel(d1[0], d2[0]) < 1e-5 and _rel(d1[1], d2[1]) < 1e-5
