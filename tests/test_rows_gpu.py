@@ -174,3 +174,19 @@ def test_weightnorm_fwd_bwd(cuda):
     d1 = torch.autograd.grad((w1 * up).sum(), [v1, g1])
     d2 = torch.autograd.grad((w2 * up).sum(), [v2, g2])
     assert _rel(d1[0], d2[0]) < 1e-5 and _rel(d1[1], d2[1]) < 1e-5
+
+
+def test_host_prefetcher_and_scalar_reader(cuda):
+    """mtasr_b200.io: staged copies arrive intact on the compute stream; pipelined scalar read-back returns each value."""
+    from mtasr_b200.io import HostPrefetcher, ScalarReader
+    pre, rd = HostPrefetcher(cuda), ScalarReader(depth=2)
+    host = [torch.randn(4, 1000).pin_memory(), torch.arange(4000, dtype=torch.int64).view(4, 1000).pin_memory()]
+    pend = []
+    for i in range(5):
+        st = pre.stage([t + i for t in host])
+        a, b = pre.take(st)
+        assert torch.equal(a.cpu(), host[0] + i) and torch.equal(b.cpu(), host[1] + i)
+        pend.append(rd.submit(a.sum() * 0 + i))
+        if len(pend) == 2:
+            assert pend.pop(0).result() == float(i - 1)
+    assert pend.pop(0).result() == 4.0
