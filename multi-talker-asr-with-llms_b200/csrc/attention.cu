@@ -570,7 +570,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const bool ok = q_ok && (kb + e < kl);
-              const float t = trel[kb + e];
+              // masked keys may index past the 2T-1 table entries (uninitialised shared memory): 0 * NaN would poison dg
+              const float t = ok ? trel[kb + e] : 0.f;
               const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, fmaf(g, t, nlse2))) : 0.f;
               const float dz = pv * (__uint_as_float(dv[e]) - delta);
               dg = fmaf(dz, t, dg);

@@ -40,6 +40,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                : "memory");
 }
 // Bounded wait: a protocol bug must trap (launch failure surfaced to the host) instead of hanging the GPU.
+// try_wait carries a suspend-time hint, so a waiting warp is parked by the hardware until the phase completes (or the
+// hint expires) instead of polling: in the warp-specialised kernels half of all issued instructions used to be these
+// polling loops, taken from the issue slots of the warps doing the work on the same scheduler (ncu, attn_bwd_kernel).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
@@ -48,13 +51,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (true) {
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(0x989680u)
         : "memory");
     if (done) break;
-    if ((++spins & 0x3ff) == 0) {
+    if ((++spins & 0x3f) == 0) {
       long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz

@@ -23,6 +23,12 @@ def _ref(qkv, gate, table, klen, B, H, T, scale):
     return o, torch.logsumexp(z, -1), (q, k, v, z, p)
 
 
+def _poison(cuda):
+    """Fill recycled allocator blocks with NaN so that any read of an unwritten output / scratch element shows up."""
+    junk = torch.full((32 * 1024 * 1024,), float("nan"), device=cuda)
+    del junk
+
+
 def _inputs(B, H, T, cuda, seed=0, ragged=True):
     g = torch.Generator(device=cuda).manual_seed(seed)
     qkv = (torch.randn(B * T, 3 * H * 64, device=cuda, generator=g) * 0.8).to(torch.bfloat16)
@@ -38,6 +44,7 @@ def _inputs(B, H, T, cuda, seed=0, ragged=True):
 def test_attn_fwd(cuda, B, H, T):
     from mtasr_b200 import kernels as Kn
     qkv, gate, table, klen = _inputs(B, H, T, cuda)
+    _poison(cuda)
     out, lse = Kn.attn_fwd(qkv, gate, table, klen, B, H, T, 0.125)
     ref, ref_lse, _ = _ref(qkv, gate, table, klen.long(), B, H, T, 0.125)
     assert _rel(out, ref) < 6e-3, _rel(out, ref)
@@ -56,6 +63,7 @@ def test_attn_bwd(cuda, B, H, T):
     out, lse = Kn.attn_fwd(qkv, gate, table, klen, B, H, T, 0.125)
     g = torch.Generator(device=cuda).manual_seed(5)
     dout = (torch.randn(B * T, D, device=cuda, generator=g) * 0.5).to(torch.bfloat16)
+    _poison(cuda)
     dqkv, dgate, dtable = Kn.attn_bwd(qkv, out, dout, lse, gate, table, klen, B, H, T, 0.125)
     qr = qkv.float().requires_grad_(True)
     gr = gate.clone().requires_grad_(True)

@@ -178,7 +178,7 @@ def test_lse_and_exp_modes(cuda, V):
     P2, cs = Kn.softmax_from_logits(lg16, lse, scale, V, want_colsum=True)
     ref = torch.softmax(logits, -1) * scale[:, None]
     assert _rel(P2[:, :V], ref) < 5e-3
-    assert _rel(cs, ref.sum(0)) < 2e-3
+    assert _rel(cs, ref.sum(0)) < 4e-3          # fp16 logits: 2^-11 relative on |logit| ~ 5 in the exponent
     assert P2[5].abs().max().item() == 0.0 and (Vp == V or P2[:, V:].abs().max().item() == 0.0)
 
 
