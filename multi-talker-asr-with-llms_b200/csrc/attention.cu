@@ -360,7 +360,7 @@ struct AttnBwdP {
   float* dq32;             // (B*T, H*64) fp32, zero-initialised, receives dQ partial sums
   float* dgate;            // (B,H,T) zero-initialised (atomics)
   float* dtable;           // (H,2T-1) zero-initialised (atomics)
-  int dbg;                 // timing experiments only (MTASR_ATTN_DBG): 1 skip table-gradient diagonals, 2 skip dQ reductions
+  int dbg;                 // timing experiments only (MTASR_ATTN_DBG): 1 skip table-gradient diagonals, 2 skip dQ reductions, 4 skip softmax math
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -522,13 +522,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       const int kl = p.klen ? min(p.klen[b], p.T) : p.T;
       const int k0 = jt * AT_BK + grp * 64;
       const long long bh = static_cast<long long>(b) * p.H + h;
+      // per-row scalars of query tile i + 1 are requested while tile i is processed (three dependent L2 round trips
+      // per tile otherwise sit between the S / dP MMAs and the first exponential)
+      float g_n, lse_n, delta_n;
+      {
+        const int qc0 = min(r, p.T - 1);
+        g_n = p.gate[bh * p.T + qc0]; lse_n = p.lse[bh * p.T + qc0]; delta_n = p.delta[bh * p.T + qc0];
+      }
       for (int i = 0; i < nq; ++i) {
         const int q = i * AT_BQ + r;
         const bool q_ok = q < p.T;
         const int qc = q_ok ? q : p.T - 1;
-        const float g = p.gate[bh * p.T + qc];
-        const float nlse2 = -p.lse[bh * p.T + qc] * LOG2E;
-        const float delta = p.delta[bh * p.T + qc];
+        const float g = g_n;
+        const float nlse2 = -lse_n * LOG2E;
+        const float delta = delta_n;
+        if (i + 1 < nq) {
+          const int qn = min((i + 1) * AT_BQ + r, p.T - 1);
+          g_n = p.gate[bh * p.T + qn]; lse_n = p.lse[bh * p.T + qn]; delta_n = p.delta[bh * p.T + qn];
+        }
         const float* trel = tbl_s + (p.T - 1 - qc);
         float dg = 0.f;
         mbar_wait(sdp_full, sdp_ph);
@@ -536,16 +547,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         tc_fence_after();
         uint8_t* pc = p_s + grp * 16384;
         uint8_t* dc = ds_s + db * AT_P_BYTES + grp * 16384;
+        uint32_t svb[2][16], dvb[2][16];
+        tmem_ld16(tm_s + lane_off + grp * 64, svb[0]);
+        tmem_ld16(tm_dp + lane_off + grp * 64, dvb[0]);
+        tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t sv[16], dv[16];
-          tmem_ld16(tm_s + lane_off + grp * 64 + c * 16, sv);
-          tmem_ld16(tm_dp + lane_off + grp * 64 + c * 16, dv);
-          tmem_ld_wait();
-          if (c == 3) {   // all TMEM reads of this tile are in registers: the next S / dP may be issued
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(sdp_empty);
+          uint32_t(&sv)[16] = svb[c & 1];
+          uint32_t(&dv)[16] = dvb[c & 1];
+          if (c + 1 < 4) {   // next chunk's TMEM loads fly while this chunk is processed
+            tmem_ld16(tm_s + lane_off + grp * 64 + (c + 1) * 16, svb[(c + 1) & 1]);
+            tmem_ld16(tm_dp + lane_off + grp * 64 + (c + 1) * 16, dvb[(c + 1) & 1]);
           }
           if (c == 0) {   // P of the previous tile (MMA 3) and dS / gate of two tiles ago (MMA 4/5 + reducers) consumed
             mbar_wait(p_empty, pe_ph ^ 1);
@@ -556,7 +568,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           }
           const int kb = k0 + c * 16;
           float pe[16], de[16];
-          if (q_ok && kb + 16 <= kl) {
+          if (p.dbg & 4) {   // timing experiment: no per-element math
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { pe[e] = __uint_as_float(sv[e]); de[e] = __uint_as_float(dv[e]); }
+          } else if (q_ok && kb + 16 <= kl) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
               const float t = trel[kb + e];
@@ -589,6 +604,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             u.x = pack_bf16x2(de[g16 * 8 + 0], de[g16 * 8 + 1]); u.y = pack_bf16x2(de[g16 * 8 + 2], de[g16 * 8 + 3]);
             u.z = pack_bf16x2(de[g16 * 8 + 4], de[g16 * 8 + 5]); u.w = pack_bf16x2(de[g16 * 8 + 6], de[g16 * 8 + 7]);
             *reinterpret_cast<uint4*>(dc + off) = u;
+          }
+          if (c + 1 < 4) tmem_ld_wait();
+          if (c == 2) {   // all TMEM reads of this tile are in registers: the next S / dP may be issued
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sdp_empty);
           }
         }
         fence_proxy_async();

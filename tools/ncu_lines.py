@@ -3,6 +3,9 @@ usage: python tools/ncu_lines.py report.ncu-rep object.o kernel_substring [top]"
 import csv, io, re, subprocess, sys, collections, os, tempfile
 rep, obj, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+callsite = len(sys.argv) > 5 and sys.argv[5] == "callsite"
+main_file = re.sub(r"(_v\d+)?\.o$", ".cu", os.path.basename(obj))
+last_main = None
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, data = rows[1], rows[2:]
@@ -27,7 +30,10 @@ for l in dis.splitlines():
         continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", l)
     if m and cur_line:
-        line_of[int(m.group(1), 16)] = cur_line
+        # inlined helpers (ptx.cuh, common.cuh, CUDA headers) are charged to the last line of the kernel's own file
+        if cur_line[0] == main_file:
+            last_main = cur_line
+        line_of[int(m.group(1), 16)] = cur_line if (cur_line[0] == main_file or last_main is None or not callsite) else (last_main[0], last_main[1])
 stalls = [k for k in hdr if k.startswith("stall_") and "Not Issued" not in k]
 agg = collections.defaultdict(lambda: [0, 0, collections.Counter()])
 tot = 0
