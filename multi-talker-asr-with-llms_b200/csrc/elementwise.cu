@@ -270,29 +270,42 @@ softmax_from_logits_kernel(const __half* __restrict__ lg, const float* __restric
   const long long r0 = blockIdx.y * rows_per_group;
   const long long r1 = r0 + rows_per_group < rows ? r0 + rows_per_group : rows;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long long row = r0; row < r1; ++row) {
-    const float rsc = rowscale[row];
-    uint4* dst = reinterpret_cast<uint4*>(P + row * ld) + i;
-    if (rsc == 0.f) {   // padded frames / infeasible utterances: no need to read the logits
-      *dst = make_uint4(0u, 0u, 0u, 0u);
-      continue;
-    }
-    const float nl = -lse[row] * 1.4426950408889634f;
-    const uint4 u = reinterpret_cast<const uint4*>(lg + row * ld)[i];
-    const __half2* h = reinterpret_cast<const __half2*>(&u);
-    uint4 o;
-    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+  constexpr int RU = 4;   // rows in flight per thread: the loads of RU rows are issued before any of them is consumed
+  for (long long rb = r0; rb < r1; rb += RU) {
+    float rsc[RU], nl[RU];
+    uint4 u[RU];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(h[j]);
-      const int col = i * 8 + j * 2;
-      const float p0 = col < V ? ex2_approx(fmaf(f.x, 1.4426950408889634f, nl)) * rsc : 0.f;       // tail columns inside ld: 0
-      const float p1 = col + 1 < V ? ex2_approx(fmaf(f.y, 1.4426950408889634f, nl)) * rsc : 0.f;
-      ow[j] = pack_bf16x2(p0, p1);
-      acc[j * 2] += p0;
-      acc[j * 2 + 1] += p1;
+    for (int k = 0; k < RU; ++k) {
+      const long long row = rb + k;
+      rsc[k] = row < r1 ? rowscale[row] : 0.f;
+      nl[k] = row < r1 ? -lse[row] * 1.4426950408889634f : 0.f;
     }
-    *dst = o;
+#pragma unroll
+    for (int k = 0; k < RU; ++k) {
+      const long long row = rb + k;
+      u[k] = (row < r1 && rsc[k] != 0.f) ? reinterpret_cast<const uint4*>(lg + row * ld)[i] : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < RU; ++k) {
+      const long long row = rb + k;
+      if (row >= r1) break;
+      uint4 o = make_uint4(0u, 0u, 0u, 0u);   // padded frames / infeasible utterances (rowscale 0): zeros, logits not read
+      if (rsc[k] != 0.f) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          const int col = i * 8 + j * 2;
+          const float p0 = col < V ? ex2_approx(fmaf(f.x, 1.4426950408889634f, nl[k])) * rsc[k] : 0.f;   // tail columns inside ld: 0
+          const float p1 = col + 1 < V ? ex2_approx(fmaf(f.y, 1.4426950408889634f, nl[k])) * rsc[k] : 0.f;
+          ow[j] = pack_bf16x2(p0, p1);
+          acc[j * 2] += p0;
+          acc[j * 2 + 1] += p1;
+        }
+      }
+      reinterpret_cast<uint4*>(P + row * ld)[i] = o;
+    }
   }
   if (colsum) {
 #pragma unroll

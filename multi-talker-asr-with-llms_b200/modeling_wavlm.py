@@ -334,7 +334,14 @@ class WavLMModel(WavLMPreTrainedModel):
         at, ff = layer.attention, layer.feed_forward
         H = at.num_heads
         eps = layer.layer_norm.eps
-        if self.config.do_stable_layer_norm:   # hf:355-366
+        if self.config.do_stable_layer_norm and at.head_dim == 64 and not ops._UNFUSED_ATTN and ops._FUSED_LAYERS:   # hf:355-366
+            gl = at.gru_rel_pos_linear
+            x = ops.PreLNAttentionFn.apply(x, layer.layer_norm.weight, layer.layer_norm.bias, eps, at.q_proj.weight, at.q_proj.bias,
+                                           at.k_proj.weight, at.k_proj.bias, at.v_proj.weight, at.v_proj.bias, at.out_proj.weight,
+                                           at.out_proj.bias, gl.weight, gl.bias, at.gru_rel_pos_const, table, klen, H)
+            x = ops.PreLNFFNFn.apply(x, layer.final_layer_norm.weight, layer.final_layer_norm.bias, eps, ff.intermediate_dense.weight,
+                                     ff.intermediate_dense.bias, ff.output_dense.weight, ff.output_dense.bias)
+        elif self.config.do_stable_layer_norm:
             h1 = ops.layer_norm(x, layer.layer_norm.weight, layer.layer_norm.bias, eps, BF)
             x = ops.AttentionFn.apply(h1, x, at.q_proj.weight, at.q_proj.bias, at.k_proj.weight, at.k_proj.bias, at.v_proj.weight,
                                       at.v_proj.bias, at.out_proj.weight, at.out_proj.bias, self._gate(h1, at), table, klen, H)

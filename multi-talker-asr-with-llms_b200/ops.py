@@ -20,6 +20,9 @@ F32 = torch.float32
 
 _bf16_cache = {}
 _UNFUSED_ATTN = os.environ.get("MTASR_UNFUSED_ATTN", "") not in ("", "0")   # debugging / A-B switch: materialise S and P
+# one autograd node per half encoder layer (PreLNAttentionFn / PreLNFFNFn); "0" = the separate LayerNorm / gate / attention /
+# FFN nodes (A-B switch; identical kernels)
+_FUSED_LAYERS = os.environ.get("MTASR_FUSED_LAYERS", "1") not in ("", "0")
 # CTC head: keep the fp16 logits of the forward vocabulary GEMM for the backward (2 B x B*T x V per head, 4.1 GB at cfg2)
 # instead of regenerating the softmax with a second vocabulary GEMM.  "0" = memory-lean recompute path.
 _CTC_KEEP_LOGITS = os.environ.get("MTASR_CTC_KEEP_LOGITS", "1") not in ("", "0")
@@ -287,6 +290,121 @@ class AttentionFn(Function):
             dbq, dbk, dbv = dbqkv[:D], dbqkv[D:2 * D], dbqkv[2 * D:]
         return (dh, dy if need[1] else None, dwq, dbq, dwk, dbk, dwv, dbv, dwo, dbo,
                 dgate if need[10] else None, dtable if need[11] else None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------------ fused pre-LN blocks
+def _gate_params(weight, bias, const, H):
+    """4-row sums of gru_rel_pos_linear (8,64) / its bias, and gru_rel_pos_const as (H,) -- see RelPosGateFn."""
+    w = weight.detach().float()
+    b = bias.detach().float()
+    wab = torch.cat([w[:4].sum(0), w[4:].sum(0)]).contiguous()
+    bab = torch.stack([b[:4].sum(), b[4:].sum()]).contiguous()
+    return wab, bab, const.detach().float().reshape(H).contiguous()
+
+
+class PreLNAttentionFn(Function):
+    """x + out_proj(attention(LN(x)))  -- the first half of a stable-layer-norm (WavLM-Large) encoder layer, hf:355-362,
+    as ONE autograd node: LayerNorm, gru_rel_pos gate, fused QKV GEMM, fused attention, out-proj (+ residual epilogue).
+
+    Same kernels as LayerNormFn -> RelPosGateFn -> AttentionFn; what the fusion removes is autograd's own arithmetic
+    between them: the three gradient contributions to LN(x) (QKV dgrad, gate) are combined in the dgrad GEMM's residual
+    epilogue and the residual-stream gradient is added inside the LayerNorm backward kernel (`dres`), instead of three
+    65 MB elementwise adds / casts per layer launched by the autograd engine."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, eps, wq, bq, wk, bk, wv, bv, wo, bo, gw, gb, gconst, table, klen, H):
+        B, T, D = x.shape
+        d = D // H
+        if d != 64 or gw.shape != (8, 64):
+            raise NotImplementedError("mtasr_b200: the fused pre-LN attention block needs head_dim 64")
+        xf = x.contiguous()
+        gamma = ln_w.detach().float()
+        h1, _, mean, rstd = K.layernorm_fwd(xf, gamma, ln_b.detach().float(), eps, out_bf16=True, out_f32=False)
+        wab, bab, cst = _gate_params(gw, gb, gconst, H)
+        gate = K.relpos_gate_fwd(h1, wab, bab, cst, B, T, H)
+        wqkv = cat_cached((wq, wk, wv), BF)
+        bqkv = cat_cached((bq, bk, bv), F32)
+        wob = bf16_of(wo)
+        h2d = h1.view(B * T, D)
+        qkv = K.linear_fwd(h2d, wqkv, bqkv)
+        scale = float(d) ** -0.5
+        tab = table.detach().contiguous().float()
+        O, lse = K.attn_fwd(qkv, gate, tab, klen, B, H, T, scale)
+        y = K.linear_fwd(O, wob, bo.detach().float(), residual=xf.view(B * T, D), out_dtype=F32)
+        ctx.dims = (B, T, D, H, scale)
+        ctx.const_shape = gconst.shape
+        ctx.save_for_backward(xf, gamma, mean, rstd, h1, qkv, lse, O, wqkv, wob, gate, tab, klen, wab, bab, cst)
+        return y.view(B, T, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xf, gamma, mean, rstd, h1, qkv, lse, O, wqkv, wob, gate, tab, klen, wab, bab, cst = ctx.saved_tensors
+        B, T, D, H, scale = ctx.dims
+        need = ctx.needs_input_grad
+        dy = dy.contiguous()
+        dyb = K.cast_bf16(dy.view(B * T, D))
+        dO = K.linear_dgrad(dyb, wob)
+        dwo = K.linear_wgrad(dyb, O) if need[10] else None
+        dbo = K.colsum(dyb) if need[11] else None
+        dqkv, dgate, dtable = K.attn_bwd(qkv, O, dO, lse, gate, tab, klen, B, H, T, scale)
+        dxg, dwab, dbab, dcst = K.relpos_gate_bwd(h1, wab, bab, cst, dgate, B, T, H)           # gate path into LN(x), fp32
+        dx = dlnw = dlnb = None
+        if need[0] or need[1] or need[2]:
+            dh1 = K.linear_dgrad(dqkv, wqkv, residual=dxg.view(B * T, D))                      # QKV dgrad + gate path, one epilogue
+            dxf, _, dlnw, dlnb = K.layernorm_bwd(dh1.view(B, T, D), xf, mean, rstd, gamma, dres=dy, want_f32=True,
+                                                 want_param_grads=need[1] or need[2])
+            dx = dxf if need[0] else None
+        dwq = dwk = dwv = dbq = dbk = dbv = None
+        if need[4] or need[6] or need[8]:
+            dwqkv = K.linear_wgrad(dqkv, h1.view(B * T, D))
+            dwq, dwk, dwv = dwqkv[:D], dwqkv[D:2 * D], dwqkv[2 * D:]
+        if need[5] or need[7] or need[9]:
+            dbqkv = K.colsum(dqkv)
+            dbq, dbk, dbv = dbqkv[:D], dbqkv[D:2 * D], dbqkv[2 * D:]
+        dgw = torch.cat([dwab[:64].expand(4, 64), dwab[64:].expand(4, 64)], 0) if need[12] else None
+        dgb = torch.cat([dbab[0:1].expand(4), dbab[1:2].expand(4)]) if need[13] else None
+        dgc = dcst.view(ctx.const_shape) if need[14] else None
+        return (dx, dlnw, dlnb, None, dwq, dbq, dwk, dbk, dwv, dbv, dwo, dbo, dgw, dgb, dgc,
+                dtable if need[15] else None, None, None)
+
+
+class PreLNFFNFn(Function):
+    """x + W2 GELU(W1 LN(x) + b1) + b2  -- the second half of a stable-layer-norm encoder layer (hf:363-366) as one
+    autograd node (LayerNormFn -> FFNFn with the residual-stream gradient added inside the LayerNorm backward)."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, eps, w1, b1, w2, b2):
+        shp = x.shape
+        D = shp[-1]
+        xf = x.contiguous()
+        gamma = ln_w.detach().float()
+        hb, _, mean, rstd = K.layernorm_fwd(xf, gamma, ln_b.detach().float(), eps, out_bf16=True, out_f32=False)
+        w1b, w2b = bf16_of(w1), bf16_of(w2)
+        h2d = hb.view(-1, D)
+        a, u = K.linear_fwd(h2d, w1b, b1.detach().float(), act=K.ACT_GELU, want_aux=True)
+        y = K.linear_fwd(a, w2b, b2.detach().float(), residual=xf.view(-1, D), out_dtype=F32)
+        ctx.save_for_backward(xf, gamma, mean, rstd, hb, u, a, w1b, w2b)
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xf, gamma, mean, rstd, hb, u, a, w1b, w2b = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        D = xf.shape[-1]
+        dy = dy.contiguous()
+        dyb = K.cast_bf16(dy.view(-1, D))
+        du = K.linear_dgrad(dyb, w2b, act=K.ACT_GELU_BWD, act_src=u)
+        dx = dlnw = dlnb = None
+        if need[0] or need[1] or need[2]:
+            dh = K.linear_dgrad(du, w1b)
+            dxf, _, dlnw, dlnb = K.layernorm_bwd(dh.view(xf.shape), xf, mean, rstd, gamma, dres=dy, want_f32=True,
+                                                 want_param_grads=need[1] or need[2])
+            dx = dxf if need[0] else None
+        dw1 = K.linear_wgrad(du, hb.view(-1, D)) if need[4] else None
+        db1 = K.colsum(du) if need[5] else None
+        dw2 = K.linear_wgrad(dyb, a) if need[6] else None
+        db2 = K.colsum(dyb) if need[7] else None
+        return dx, dlnw, dlnb, None, dw1, db1, dw2, db2
 
 
 # ------------------------------------------------------------------------------------------------------ pos conv
