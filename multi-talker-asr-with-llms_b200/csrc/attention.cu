@@ -25,7 +25,7 @@ static constexpr int AT_BK = 128;        // keys per inner tile
 static constexpr int AT_TILE = 128 * 64 * 2;   // one 128 x 64 bf16 operand tile = 16 KB
 static constexpr int AT_KV_SLOTS = 4;
 static constexpr int AT_P_BYTES = 128 * 128 * 2;   // P tile: two 64-key chunks of 128 rows x 128 B
-static constexpr int AT_THREADS = 384;         // 4 control warps + 2 softmax warpgroups
+static constexpr int AT_THREADS = 640;         // 4 control warps + 4 softmax warpgroups (2 S/P buffers x 2 column halves)
 static constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnFwdP {
@@ -63,8 +63,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
   uint8_t* p_s = kv_s + AT_KV_SLOTS * AT_TILE;           // 2 x 32 KB
   float* tbl_s = reinterpret_cast<float*>(p_s + 2 * AT_P_BYTES);   // 2T-1 floats
   // (+256 floats of slack: masked lanes of the last key tile may form addresses up to 128 entries past the table)
-  float* xch_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tbl_s) + attn_table_bytes(p.T));   // 2 x 128 floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xch_s + 256);
+  float* xch_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tbl_s) + attn_table_bytes(p.T));   // 4 x 128 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xch_s + 512);
   uint64_t* q_full = bars;
   uint64_t* q_empty = bars + 1;
   uint64_t* kv_full = bars + 2;                  // [4]
@@ -86,11 +86,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
       mbar_init(q_empty, 1);
       for (int i = 0; i < AT_KV_SLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4);
-        mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
+        mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
+        mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
       }
       mbar_init(o_full, 1);
-      mbar_init(o_empty, 8);
+      mbar_init(o_empty, 16);
       fence_barrier_init();
     }
   } else if (warp == 2) {
@@ -179,25 +179,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
       }
     }
   } else if (warp >= 4) {
-    // ---------------------------------------------------------------- softmax warps: thread = query row.
-    // Two warpgroups (warps 4-7 and 8-11) own the two S / P buffers: group g processes every key tile that lands in
-    // buffer g, so consecutive tiles are exponentiated concurrently; the partial row max / row sum of the two groups
-    // are combined through shared memory.
+    // ---------------------------------------------------------------- softmax warps: thread = (query row, 64-key half).
+    // Four warpgroups: group (grp, sub) owns key columns [64 sub, 64 sub + 64) of every key tile that lands in S / P buffer
+    // grp, so consecutive tiles are exponentiated concurrently and every scheduler holds four softmax warps (the per-element
+    // chain LDS -> FFMA -> MUFU -> pack is latency-bound: with two warps per scheduler the kernel ran at ~0.1 IPC per
+    // warp).  The partial row max / row sum of the four groups are combined through shared memory.
     const int wq = warp & 3;
-    const int grp = (warp - 4) >> 2;
+    const int grp = ((warp - 4) >> 2) & 1;
+    const int sub = (warp - 4) >> 3;
+    const int gid = sub * 2 + grp;                 // 0..3
     const int r = wq * 32 + lane;
-    const int st = threadIdx.x - 128;              // 0..255 over both groups
+    const int st = threadIdx.x - 128;              // 0..511 over the four groups
     uint32_t sph = 0, pph = 0, oph = 0;            // phases of this group's S / P buffer and of the O accumulator
     int cur_h = -1;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int qt = item % p.nq, h = (item / p.nq) % p.H, b = item / (p.nq * p.H);
-      named_bar_sync(1, 256);                      // every softmax thread is done with the previous item's table / xch
+      named_bar_sync(1, 512);                      // every softmax thread is done with the previous item's table / xch
       if (h != cur_h) {
         const float* trow = p.table + static_cast<long long>(h) * (2 * p.T - 1);
-        for (int i = st; i < 2 * p.T - 1; i += 256) tbl_s[i] = trow[i] * LOG2E;
+        for (int i = st; i < 2 * p.T - 1; i += 512) tbl_s[i] = trow[i] * LOG2E;
         cur_h = h;
       }
-      named_bar_sync(1, 256);
+      named_bar_sync(1, 512);
       const int q = qt * AT_BQ + r;
       const bool q_ok = q < p.T;
       const int qc = q_ok ? q : p.T - 1;
@@ -205,23 +208,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
       const float g = p.gate[(static_cast<long long>(b) * p.H + h) * p.T + qc];
       const float* trel = tbl_s + (p.T - 1 - qc);   // trel[k] = log2e * table[h, k - q + T - 1]
       const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+      const uint32_t tm_mine = tm_s[grp] + lane_off + sub * 64;
 
-      // pass A: exact row maximum of z (log2 units) over this group's tiles (tile j lives in buffer j & 1)
+      // pass A: exact row maximum of z (log2 units) over this group's half tiles (tile j lives in buffer j & 1)
       float m = -INFINITY;
       for (int j = grp; j < nk; j += 2) {
         mbar_wait(&s_full[grp], sph);
         sph ^= 1;
         tc_fence_after();
-        const int k0 = j * AT_BK;
-        // 32-column chunks, software-pipelined: the TMEM load of chunk c+1 is in flight while chunk c is reduced
+        const int k0 = j * AT_BK + sub * 64;
         uint32_t va[32], vb[32];
-        tmem_ld32(tm_s[grp] + lane_off, va);
+        tmem_ld32(tm_mine, va);
+        tmem_ld32(tm_mine + 32, vb);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[grp]);   // both chunks are in registers: the buffer may be overwritten
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t(&cur)[32] = (c & 1) ? vb : va;
-          uint32_t(&nxt)[32] = (c & 1) ? va : vb;
-          if (c + 1 < 4) tmem_ld32(tm_s[grp] + lane_off + (c + 1) * 32, nxt);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t(&cur)[32] = c ? vb : va;
           const int kb = k0 + c * 32;
           if (kb + 32 <= kl) {
 #pragma unroll
@@ -231,17 +236,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
             for (int i = 0; i < 32; ++i)
               if (kb + i < kl) m = fmaxf(m, fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]));
           }
-          if (c + 1 < 4) tmem_ld_wait();
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[grp]);
       }
-      xch_s[grp * 128 + r] = m;
-      named_bar_sync(1, 256);
-      m = fmaxf(m, xch_s[(grp ^ 1) * 128 + r]);
+      xch_s[gid * 128 + r] = m;
+      named_bar_sync(1, 512);
+      m = fmaxf(fmaxf(xch_s[r], xch_s[128 + r]), fmaxf(xch_s[256 + r], xch_s[384 + r]));
       const float mm = m == -INFINITY ? 0.f : m;
-      named_bar_sync(1, 256);                      // both groups have read the maxima before xch is reused for the sums
+      named_bar_sync(1, 512);                      // all groups have read the maxima before xch is reused for the sums
 
       // pass B: P = exp2(z - m) -> bf16 smem tile, l = partial row sum (pass-B tile j lives in buffer (nk + j) & 1)
       float l = 0.f;
@@ -251,69 +252,62 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
         mbar_wait(&p_empty[grp], pph ^ 1);
         pph ^= 1;
         tc_fence_after();
-        const int k0 = j * AT_BK;
-        uint8_t* pt = p_s + grp * AT_P_BYTES;
+        const int k0 = j * AT_BK + sub * 64;
+        uint8_t* chunk = p_s + grp * AT_P_BYTES + sub * 16384;   // this group's 64-key swizzle chunk of the P tile
         uint32_t va[32], vb[32];
-        tmem_ld32(tm_s[grp] + lane_off, va);
+        tmem_ld32(tm_mine, va);
+        tmem_ld32(tm_mine + 32, vb);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[grp]);   // the next QK^T may overwrite this S buffer
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t(&cur)[32] = (c & 1) ? vb : va;
-          uint32_t(&nxt)[32] = (c & 1) ? va : vb;
-          if (c + 1 < 4) tmem_ld32(tm_s[grp] + lane_off + (c + 1) * 32, nxt);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t(&cur)[32] = c ? vb : va;
           const int kb = k0 + c * 32;
           float e[32];
           if (kb + 32 <= kl) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              e[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]) - mm);
+              e[i] = ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, fmaf(g, trel[kb + i], -mm)));
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              e[i] = kb + i < kl ? ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]) - mm) : 0.f;
+              e[i] = kb + i < kl ? ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, fmaf(g, trel[kb + i], -mm))) : 0.f;
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) l += e[i];
-          uint8_t* chunk = pt + (c >> 1) * 16384;
 #pragma unroll
           for (int g16 = 0; g16 < 4; ++g16) {
             uint4 u;
             u.x = pack_bf16x2(e[g16 * 8 + 0], e[g16 * 8 + 1]); u.y = pack_bf16x2(e[g16 * 8 + 2], e[g16 * 8 + 3]);
             u.z = pack_bf16x2(e[g16 * 8 + 4], e[g16 * 8 + 5]); u.w = pack_bf16x2(e[g16 * 8 + 6], e[g16 * 8 + 7]);
-            *reinterpret_cast<uint4*>(chunk + swz128(static_cast<uint32_t>(r * 128 + (c & 1) * 64 + g16 * 16))) = u;
-          }
-          if (c + 1 < 4) {
-            tmem_ld_wait();
-          }
-          if (c == 2) {   // the last chunk is in registers: the next QK^T may overwrite this S buffer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[grp]);
+            *reinterpret_cast<uint4*>(chunk + swz128(static_cast<uint32_t>(r * 128 + c * 64 + g16 * 16))) = u;
           }
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[grp]);
       }
-      xch_s[grp * 128 + r] = l;
-      named_bar_sync(1, 256);
-      l += xch_s[(grp ^ 1) * 128 + r];
+      xch_s[gid * 128 + r] = l;
+      named_bar_sync(1, 512);
+      l = (xch_s[r] + xch_s[128 + r]) + (xch_s[256 + r] + xch_s[384 + r]);
 
-      // epilogue: O / l -> bf16 (group g stores head-dim columns 32g..32g+31), LSE
+      // epilogue: O / l -> bf16 (group gid stores head-dim columns 16 gid .. 16 gid + 15), LSE
       mbar_wait(o_full, oph);
       oph ^= 1;
       tc_fence_after();
-      uint32_t o0[32];
-      tmem_ld32(tm_o + lane_off + grp * 32, o0);
+      uint32_t o0[16];
+      tmem_ld16(tm_o + lane_off + gid * 16, o0);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(o_empty);
       if (q_ok) {
         const float inv = l > 0.f ? 1.f / l : 0.f;
-        __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.T + q) * (p.H * AT_D) + h * AT_D + grp * 32;
+        __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.T + q) * (p.H * AT_D) + h * AT_D + gid * 16;
 #pragma unroll
-        for (int g16 = 0; g16 < 4; ++g16) {
+        for (int g16 = 0; g16 < 2; ++g16) {
           uint4 u;
           u.x = pack_bf16x2(__uint_as_float(o0[g16 * 8 + 0]) * inv, __uint_as_float(o0[g16 * 8 + 1]) * inv);
           u.y = pack_bf16x2(__uint_as_float(o0[g16 * 8 + 2]) * inv, __uint_as_float(o0[g16 * 8 + 3]) * inv);
@@ -322,7 +316,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
           reinterpret_cast<uint4*>(orow)[g16] = u;
         }
         // natural-log LSE of the biased scores: z_log2 = z * log2e  =>  lse = (m + log2(l)) / log2e
-        if (grp == 0)
+        if (gid == 0)
           p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l > 0.f ? (mm + log2f(l)) * 0.6931471805599453f : -INFINITY;
       }
     }
@@ -836,7 +830,7 @@ extern "C" int mtasr_attn_fwd(const void* qkv, const float* gate, const float* t
   p.gate = gate; p.table = table; p.klen = klen;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse;
-  const int smem = AT_TILE + AT_KV_SLOTS * AT_TILE + 2 * AT_P_BYTES + attn_table_bytes(T) + 1024 + 256;
+  const int smem = AT_TILE + AT_KV_SLOTS * AT_TILE + 2 * AT_P_BYTES + attn_table_bytes(T) + 2048 + 256;
   MTASR_CHECK_ARG(smem <= 232448, "attn_fwd: T=%d needs %d bytes of shared memory", T, smem);
   if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return set_error(MTASR_ERR_LAUNCH, "attn_fwd: cannot set the shared-memory attribute");
