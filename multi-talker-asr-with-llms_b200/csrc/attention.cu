@@ -7,11 +7,15 @@
 // repo wrote S (fp32) and P (bf16).  Here nothing of size T x T ever reaches HBM: one CTA owns a 128-query tile of one
 // (utterance, head); S tiles live in TMEM, P tiles in swizzled shared memory, O accumulates in TMEM.
 //
-// Forward, warp-specialised (256 threads): warp 0 TMA producer (Q once, then K/V tiles through a 4-slot ring),
-// warp 1 single-thread tcgen05.mma issuer, warp 2 TMEM allocator, warps 4..7 softmax (thread = query row).
-// Exact two-pass softmax: pass A runs QK^T only and reduces the row maximum (no exponentials), pass B recomputes the
-// S tiles, forms P = exp(z - max) once, accumulates the row sum in registers and O += P V in TMEM -- no accumulator
-// rescaling, no second exponential; the extra QK^T pass is cheap because the kernel is SFU(exp)-bound, not MMA-bound.
+// Forward, warp-specialised (640 threads): warp 0 TMA producer (Q, then K/V tiles through a 4-slot ring), warp 1
+// single-thread tcgen05.mma issuer, warp 2 TMEM allocator, warps 4..19 softmax (thread = query row x 64-key half; four
+// warpgroups = 2 S/P buffers x 2 column halves).
+//   * attn_fwd_sp_kernel (T <= 512, the headline shape): single pass -- every key tile has its own O accumulator in TMEM
+//     and its own tile-local row maximum; the epilogue combines the (<= 4) partial results exactly.
+//   * attn_fwd_kernel (any T): exact two-pass softmax -- pass A runs QK^T only and reduces the row maximum, pass B
+//     recomputes the S tiles, forms P = exp(z - max) once and accumulates O += P V in TMEM without rescaling.
+// Both are bound by the shared-memory pipe (one table look-up per score + P staging + MMA operand reads), not by MUFU or
+// the tensor pipe: ncu line profiles under profiles/.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -318,6 +322,299 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
         // natural-log LSE of the biased scores: z_log2 = z * log2e  =>  lse = (m + log2(l)) / log2e
         if (gid == 0)
           p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l > 0.f ? (mm + log2f(l)) * 0.6931471805599453f : -INFINITY;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ forward, single pass
+// T <= 512 (at most four 128-key tiles per row -- the 10 s utterances of the headline configuration): every key tile gets
+// its OWN 64-column O accumulator in TMEM (2 S buffers + 4 accumulators = all 512 columns) and is exponentiated against
+// its own tile-local row maximum m_j, so there is neither the max-only first pass of attn_fwd_kernel (a second QK^T per
+// tile and twice the MMA <-> softmax hand-offs, which is what that kernel's time is made of) nor an online rescale of a
+// running accumulator.  The epilogue combines exactly:  O = sum_j 2^(m_j - m) O_j / l,  l = sum_j 2^(m_j - m) l_j.
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* q_s = smem;                                   // 2 x 16 KB: the next item's Q tile is prefetched
+  uint8_t* kv_s = q_s + 2 * AT_TILE;                     // 4 x 16 KB
+  uint8_t* p_s = kv_s + AT_KV_SLOTS * AT_TILE;           // 2 x 32 KB
+  float* tbl_s = reinterpret_cast<float*>(p_s + 2 * AT_P_BYTES);   // 2T-1 floats (+ slack, see attn_table_bytes)
+  float* xm_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(tbl_s) + attn_table_bytes(p.T));   // [2 sets][2 grp][2 sub][128]
+  float* tm_sm = xm_s + 1024;                            // [2 item parities][4 tiles][128]  tile-local row maxima
+  float* tl_sm = tm_sm + 1024;                           // [2 item parities][4 tiles][2 halves][128]  partial row sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tl_sm + 2048);
+  uint64_t* q_full = bars;                       // [2]
+  uint64_t* q_empty = bars + 2;                  // [2]
+  uint64_t* kv_full = bars + 4;                  // [4]
+  uint64_t* kv_empty = kv_full + AT_KV_SLOTS;    // [4]
+  uint64_t* s_full = kv_empty + AT_KV_SLOTS;     // [2]
+  uint64_t* s_empty = s_full + 2;                // [2]
+  uint64_t* p_full = s_empty + 2;                // [2]
+  uint64_t* p_empty = p_full + 2;                // [2]
+  uint64_t* o_full = p_empty + 2;
+  uint64_t* o_empty = o_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    if (elect_one()) prefetch_tmap(&tmap_qkv);
+  } else if (warp == 1) {
+    if (elect_one()) {
+      for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+      for (int i = 0; i < AT_KV_SLOTS; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8);
+        mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1);
+      }
+      mbar_init(o_full, 1);
+      mbar_init(o_empty, 16);
+      fence_barrier_init();
+    }
+  } else if (warp == 2) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_s[2] = {tmem_base, tmem_base + 128};
+  const uint32_t tm_o = tmem_base + 256;         // accumulator of key tile j: tm_o + 64 j
+  const int nk = p.nk;                           // <= 4
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      int slot = 0, qb = 0;
+      uint32_t ph = 0, qph[2] = {0, 0};
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int qt = item % p.nq, h = (item / p.nq) % p.H, b = item / (p.nq * p.H);
+        mbar_wait(&q_empty[qb], qph[qb] ^ 1);
+        qph[qb] ^= 1;
+        mbar_arrive_expect_tx(&q_full[qb], AT_TILE);
+        tma_load_4d(q_s + qb * AT_TILE, &tmap_qkv, &q_full[qb], 0, qt * AT_BQ, h, b);
+        qb ^= 1;
+        auto load = [&](int row0, int slice) {
+          mbar_wait(&kv_empty[slot], ph ^ 1);
+          mbar_arrive_expect_tx(&kv_full[slot], AT_TILE);
+          tma_load_4d(kv_s + slot * AT_TILE, &tmap_qkv, &kv_full[slot], 0, row0, slice, b);
+          if (++slot == AT_KV_SLOTS) { slot = 0; ph ^= 1; }
+        };
+        load(0, p.H + h);                                                // K_0, then K_{j+1}, V_j
+        for (int j = 0; j < nk; ++j) {
+          if (j + 1 < nk) load((j + 1) * AT_BK, p.H + h);
+          load(j * AT_BK, 2 * p.H + h);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);          // S = Q K^T: both K-major
+      const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);           // O_j = P V: A K-major, B (V) MN-major
+      int slot = 0, qb = 0;
+      uint32_t ph = 0, qph[2] = {0, 0}, oph = 0;
+      uint32_t sph[2] = {0, 0}, pph[2] = {0, 0};
+      auto issue_s = [&](int buf) {
+        mbar_wait(&kv_full[slot], ph);
+        mbar_wait(&s_empty[buf], sph[buf] ^ 1);
+        sph[buf] ^= 1;
+        tc_fence_after();
+        const uint32_t qa = smem_u32(q_s + qb * AT_TILE), ka = smem_u32(kv_s + slot * AT_TILE);
+#pragma unroll
+        for (int ks = 0; ks < AT_D / 16; ++ks) umma_f16(tm_s[buf], desc_kmajor(qa, ks), desc_kmajor(ka, ks), idesc_s, ks != 0);
+        umma_commit(&kv_empty[slot]);
+        umma_commit(&s_full[buf]);
+        if (++slot == AT_KV_SLOTS) { slot = 0; ph ^= 1; }
+      };
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        mbar_wait(&q_full[qb], qph[qb]);
+        qph[qb] ^= 1;
+        issue_s(0);                                                      // key tile j always uses S / P buffer j & 1
+        for (int j = 0; j < nk; ++j) {
+          const int pb = j & 1;
+          if (j + 1 < nk) issue_s(pb ^ 1);
+          mbar_wait(&p_full[pb], pph[pb]);
+          pph[pb] ^= 1;
+          mbar_wait(&kv_full[slot], ph);
+          if (j == 0) { mbar_wait(o_empty, oph ^ 1); oph ^= 1; }
+          tc_fence_after();
+          const uint32_t pa = smem_u32(p_s + pb * AT_P_BYTES), va = smem_u32(kv_s + slot * AT_TILE);
+#pragma unroll
+          for (int ks = 0; ks < AT_BK / 16; ++ks)
+            umma_f16(tm_o + 64 * j, make_smem_desc(pa + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024), desc_mnmajor(va, ks, 8192),
+                     idesc_o, ks != 0);
+          umma_commit(&kv_empty[slot]);
+          umma_commit(&p_empty[pb]);
+          if (++slot == AT_KV_SLOTS) { slot = 0; ph ^= 1; }
+        }
+        umma_commit(o_full);
+        umma_commit(&q_empty[qb]);
+        qb ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- softmax warps: thread = (query row, 64-key half)
+    const int wq = warp & 3;
+    const int grp = ((warp - 4) >> 2) & 1;         // S / P buffer = key-tile parity
+    const int sub = (warp - 4) >> 3;               // key columns [64 sub, 64 sub + 64) of the tile
+    const int gid = sub * 2 + grp;                 // 0..3
+    const int r = wq * 32 + lane;
+    const int st = threadIdx.x - 128;              // 0..511
+    uint32_t sph = 0, pph = 0, oph = 0;
+    int xset = 0;                                  // exchange-slot set, alternating per tile of this buffer
+    int cur_h = -1;
+    int ipar = 0;                                  // item parity: the combine arrays are double-buffered, so the only
+                                                   // CTA-wide barrier per item is the one in front of the combination
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int qt = item % p.nq, h = (item / p.nq) % p.H, b = item / (p.nq * p.H);
+      if (h != cur_h) {                            // uniform over the CTA: the table changes once per head
+        named_bar_sync(1, 512);                    // every softmax thread is done with the previous head's table
+        const float* trow = p.table + static_cast<long long>(h) * (2 * p.T - 1);
+        for (int i = st; i < 2 * p.T - 1; i += 512) tbl_s[i] = trow[i] * LOG2E;
+        cur_h = h;
+        named_bar_sync(1, 512);
+      }
+      float* tmx = tm_sm + ipar * 512;
+      float* tlx = tl_sm + ipar * 1024;
+      ipar ^= 1;
+      const int q = qt * AT_BQ + r;
+      const bool q_ok = q < p.T;
+      const int qc = q_ok ? q : p.T - 1;
+      const int kl = p.klen ? min(p.klen[b], p.T) : p.T;
+      const float g = p.gate[(static_cast<long long>(b) * p.H + h) * p.T + qc];
+      const float* trel = tbl_s + (p.T - 1 - qc);   // trel[k] = log2e * table[h, k - q + T - 1]
+      const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+      const uint32_t tm_mine = tm_s[grp] + lane_off + sub * 64;
+
+      for (int j = grp; j < nk; j += 2) {
+        mbar_wait(&s_full[grp], sph);
+        sph ^= 1;
+        tc_fence_after();
+        const int k0 = j * AT_BK + sub * 64;
+        uint32_t va[32], vb[32];
+        tmem_ld32(tm_mine, va);
+        tmem_ld32(tm_mine + 32, vb);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[grp]);   // S is in registers: the buffer may take tile j + 2
+        // z (log2 units) in place, masked keys -> -inf; tile-local max of this half
+        float mh = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t(&cur)[32] = c ? vb : va;
+          const int kb = k0 + c * 32;
+          if (kb + 32 <= kl) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float z = fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]);
+              cur[i] = __float_as_uint(z);
+              mh = fmaxf(mh, z);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              float z = -INFINITY;
+              if (kb + i < kl) z = fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]);
+              cur[i] = __float_as_uint(z);
+              mh = fmaxf(mh, z);
+            }
+          }
+        }
+        // the two halves of a tile share one maximum (one scale per row of P V): exchange through shared memory
+        float* xs = xm_s + xset * 512 + grp * 256;
+        xs[sub * 128 + r] = mh;
+        named_bar_sync(2 + grp, 256);
+        const float mj = fmaxf(mh, xs[(sub ^ 1) * 128 + r]);
+        xset ^= 1;
+        const float mm = mj == -INFINITY ? 0.f : mj;
+        mbar_wait(&p_empty[grp], pph ^ 1);
+        pph ^= 1;
+        uint8_t* chunk = p_s + grp * AT_P_BYTES + sub * 16384;   // this group's 64-key swizzle chunk of the P tile
+        float lh = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t(&cur)[32] = c ? vb : va;
+          float e[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) e[i] = ex2_approx(__uint_as_float(cur[i]) - mm);   // exp2(-inf) = 0 for masked keys
+#pragma unroll
+          for (int i = 0; i < 32; ++i) lh += e[i];
+#pragma unroll
+          for (int g16 = 0; g16 < 4; ++g16) {
+            uint4 u;
+            u.x = pack_bf16x2(e[g16 * 8 + 0], e[g16 * 8 + 1]); u.y = pack_bf16x2(e[g16 * 8 + 2], e[g16 * 8 + 3]);
+            u.z = pack_bf16x2(e[g16 * 8 + 4], e[g16 * 8 + 5]); u.w = pack_bf16x2(e[g16 * 8 + 6], e[g16 * 8 + 7]);
+            *reinterpret_cast<uint4*>(chunk + swz128(static_cast<uint32_t>(r * 128 + c * 64 + g16 * 16))) = u;
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[grp]);
+        if (sub == 0) tmx[j * 128 + r] = mm;
+        tlx[(j * 2 + sub) * 128 + r] = lh;
+      }
+      named_bar_sync(1, 512);
+      // exact combination over the key tiles
+      float m = -INFINITY;
+      for (int j = 0; j < nk; ++j) {
+        const float lj = tlx[(j * 2) * 128 + r] + tlx[(j * 2 + 1) * 128 + r];
+        if (lj > 0.f) m = fmaxf(m, tmx[j * 128 + r]);
+      }
+      float f[4] = {0.f, 0.f, 0.f, 0.f};
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nk) {
+          const float lj = tlx[(j * 2) * 128 + r] + tlx[(j * 2 + 1) * 128 + r];
+          f[j] = lj > 0.f ? ex2_approx(tmx[j * 128 + r] - m) : 0.f;
+          l = fmaf(f[j], lj, l);
+        }
+      }
+      // epilogue: sum_j f_j O_j / l -> bf16 (group gid stores head-dim columns 16 gid .. 16 gid + 15), LSE
+      mbar_wait(o_full, oph);
+      oph ^= 1;
+      tc_fence_after();
+      float acc[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < nk) {
+          uint32_t o0[16];
+          tmem_ld16(tm_o + 64 * j + lane_off + gid * 16, o0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[i] = fmaf(f[j], __uint_as_float(o0[i]), acc[i]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      if (q_ok) {
+        const float inv = l > 0.f ? 1.f / l : 0.f;
+        __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.T + q) * (p.H * AT_D) + h * AT_D + gid * 16;
+#pragma unroll
+        for (int g16 = 0; g16 < 2; ++g16) {
+          uint4 u;
+          u.x = pack_bf16x2(acc[g16 * 8 + 0] * inv, acc[g16 * 8 + 1] * inv);
+          u.y = pack_bf16x2(acc[g16 * 8 + 2] * inv, acc[g16 * 8 + 3] * inv);
+          u.z = pack_bf16x2(acc[g16 * 8 + 4] * inv, acc[g16 * 8 + 5] * inv);
+          u.w = pack_bf16x2(acc[g16 * 8 + 6] * inv, acc[g16 * 8 + 7] * inv);
+          reinterpret_cast<uint4*>(orow)[g16] = u;
+        }
+        if (gid == 0)
+          p.lse[(static_cast<long long>(b) * p.H + h) * p.T + q] = l > 0.f ? (m + log2f(l)) * 0.6931471805599453f : -INFINITY;
       }
     }
   }
@@ -830,11 +1127,21 @@ extern "C" int mtasr_attn_fwd(const void* qkv, const float* gate, const float* t
   p.gate = gate; p.table = table; p.klen = klen;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse;
+  const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
+  if (p.nk <= 4 && getenv("MTASR_ATTN_TWO_PASS") == nullptr) {
+    // T <= 512: one O accumulator per key tile, no max-only pass (attn_fwd_sp_kernel)
+    const int smem = 2 * AT_TILE + AT_KV_SLOTS * AT_TILE + 2 * AT_P_BYTES + attn_table_bytes(T) + (1024 + 1024 + 2048) * 4 + 256;
+    if (cudaFuncSetAttribute(attn_fwd_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return set_error(MTASR_ERR_LAUNCH, "attn_fwd: cannot set the shared-memory attribute");
+    attn_fwd_sp_kernel<<<grid, AT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map, p);
+    MTASR_COUNT_LAUNCH();
+    MTASR_CHECK_LAUNCH("attn_fwd");
+    return MTASR_OK;
+  }
   const int smem = AT_TILE + AT_KV_SLOTS * AT_TILE + 2 * AT_P_BYTES + attn_table_bytes(T) + 2048 + 256;
   MTASR_CHECK_ARG(smem <= 232448, "attn_fwd: T=%d needs %d bytes of shared memory", T, smem);
   if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return set_error(MTASR_ERR_LAUNCH, "attn_fwd: cannot set the shared-memory attribute");
-  const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
   attn_fwd_kernel<<<grid, AT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map, p);
   MTASR_COUNT_LAUNCH();
   MTASR_CHECK_LAUNCH("attn_fwd");
