@@ -220,8 +220,16 @@ def main_ours(args):
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # SMs left to the NCCL all-reduce kernels during the backward (0 = none reserved).  The persistent GEMM / attention
+    # kernels own whole SMs, so without a reservation the collective only gets SMs in the gaps between kernels and the
+    # statically scheduled tiles of the kernel it displaces finish late.  Measured at 8 GPUs (cfg2, ms per step): no
+    # gradient exchange 102.0, in-place reducer without reservation 115.5, with 8 reserved SMs + NCCL_MAX_CTAS=8 106.6.
+    comm_sms = int(os.environ.get("MTASR_COMM_SMS", "8")) if world > 1 else 0
+    total_sms = torch.cuda.get_device_properties(dev).multi_processor_count
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if comm_sms:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(comm_sms))
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(1234)
@@ -235,9 +243,21 @@ def main_ours(args):
     model.eval()      # dropout 0 / SpecAugment off (RNG streams of the reference are not reproducible); gradients still flow
     n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
     net = model
-    if world > 1:
+    # Data parallel: one process per GPU, the only collective is the gradient all-reduce (mean).  Default: the in-place
+    # mtasr_b200.dp.GradGroupReducer (coalesced NCCL all-reduce of the gradient tensors where the backward kernels wrote
+    # them, launched per group as the backward produces them).  MTASR_DP=ddp selects torch DistributedDataParallel
+    # (flat buckets + pre-division: +3.4 ms of copies per step at cfg2), MTASR_DP=none no reduction at all (debug).
+    dp_mode = os.environ.get("MTASR_DP", "group") if world > 1 else "single"
+    reducer = None
+    if dp_mode == "ddp":
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
-                                                        bucket_cap_mb=100, broadcast_buffers=False)
+                                                        bucket_cap_mb=int(os.environ.get("MTASR_DDP_BUCKET_MB", "100")),
+                                                        broadcast_buffers=False)
+    elif dp_mode == "group":
+        from mtasr_b200.dp import GradGroupReducer
+        for p_ in model.parameters():                       # same start on every rank (what DDP's constructor does)
+            dist.broadcast(p_.data, src=0)
+        reducer = GradGroupReducer(model.parameters(), group_bytes=int(os.environ.get("MTASR_DP_GROUP_MB", "64")) << 20)
 
     wav, mask, labels, lens = synth_batch(B, S, args.speakers, V_LLAMA3_CTC, seed=1234 + rank)
     host = [wav.pin_memory(), mask.pin_memory()] + [y.pin_memory() for y in labels] + [l.pin_memory() for l in lens]
@@ -255,8 +275,18 @@ def main_ours(args):
             return ids.sum().float()
         for p in model.parameters():
             p.grad = None
+        if reducer is not None:
+            reducer.begin()
         loss = net(w, attention_mask=m, label_spks=ys, label_spks_lengths=yl)
-        loss.backward()
+        if comm_sms:
+            K.set_sm_budget(total_sms - comm_sms)           # the backward's persistent kernels leave `comm_sms` SMs to NCCL
+        try:
+            loss.backward()
+        finally:
+            if comm_sms:
+                K.set_sm_budget(0)
+        if reducer is not None:
+            reducer.finish()                                # the current stream waits for the gradient all-reduce
         return loss
 
     def barrier():

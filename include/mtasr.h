@@ -34,6 +34,10 @@ extern "C" {
 #define MTASR_DT_F16 2 /* only as the optional logits output of mtasr_gemm_bf16 mode 1 and the input of mtasr_softmax_from_logits */
 
 int mtasr_version(void);
+/* Cap the number of SMs the persistent kernels (GEMM, attention) size their grids for; 0 = all.  Returns the effective count.
+ * Data-parallel training leaves a few SMs to the NCCL gradient all-reduce during the backward: the persistent kernels
+ * otherwise occupy every SM back to back and the collective only runs once the backward has drained. */
+int mtasr_set_sm_budget(int32_t n_sms);
 const char* mtasr_last_error_string(void);
 /* Number of kernels this library has enqueued since load (process-wide; used by bench.py `gpu_launches`). */
 int64_t mtasr_launch_count(void);

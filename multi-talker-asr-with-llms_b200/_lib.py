@@ -47,6 +47,7 @@ class GemmDesc(C.Structure):
 _P, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SIGNATURES = {
     "mtasr_version": (C.c_int, []),
+    "mtasr_set_sm_budget": (C.c_int, [_I32]),
     "mtasr_last_error_string": (C.c_char_p, []),
     "mtasr_launch_count": (_I64, []),
     "mtasr_profile_begin": (C.c_int, []),

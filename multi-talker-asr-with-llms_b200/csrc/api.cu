@@ -19,6 +19,8 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+static std::atomic<int> g_sm_budget{0};
+
 int num_sms() {
   static int n = 0;
   static std::once_flag once;
@@ -28,10 +30,16 @@ int num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
   });
-  return n;
+  const int b = g_sm_budget.load(std::memory_order_relaxed);
+  return (b > 0 && b < n) ? b : n;
 }
 
 }  // namespace mtasr
 
 extern "C" int mtasr_version(void) { return 100; }
+extern "C" int mtasr_set_sm_budget(int32_t n_sms) {
+  if (n_sms < 0) return mtasr::set_error(MTASR_ERR_INVALID_ARG, "set_sm_budget: negative SM count");
+  mtasr::g_sm_budget.store(n_sms & ~1);   // even: CTA pairs
+  return mtasr::num_sms();
+}
 extern "C" const char* mtasr_last_error_string(void) { return mtasr::last_error_buf(); }

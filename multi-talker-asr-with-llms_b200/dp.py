@@ -86,3 +86,102 @@ class GradBucketReducer:
     def remove(self):
         for h in self._hooks:
             h.remove()
+
+
+class GradGroupReducer:
+    """In-place, copy-free variant: gradients stay where the backward kernels wrote them.
+
+    DistributedDataParallel (and `GradBucketReducer`) move every gradient into a flat bucket and pre-divide it: two extra
+    passes over the 2.4 GB of fp32 gradients of cfg2 plus ~500 small copy launches from autograd hooks, measured at
+    3.4 ms of a 100 ms step before a single byte crosses NVLink.  Here the parameters are only *grouped* (reverse
+    registration order, ~`group_bytes` each); when the last gradient of a group has landed, one coalesced NCCL call
+    (`ncclGroupStart/End` around per-tensor all-reduces, `ReduceOp.AVG`) reduces the tensors in place on a side stream
+    ordered after the producing kernels by an event.  `finish()` flushes groups that never completed (unused / frozen
+    parameters) and makes the current stream wait for the collectives.  Call `begin()` before each backward (with
+    `.grad = None`, as `optimizer.zero_grad(set_to_none=True)` leaves them)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group_bytes: int = 256 << 20, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.params = [p for p in params if p.requires_grad]
+        self.groups: List[List[torch.nn.Parameter]] = []
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):
+            nbytes = p.numel() * 4
+            if cur and cur_bytes + nbytes > group_bytes:
+                self.groups.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self.groups.append(cur)
+        self._gid = {}
+        for gi, g in enumerate(self.groups):
+            for p in g:
+                self._gid[p] = gi
+        self._cuda = bool(self.params) and self.params[0].is_cuda
+        self._stream = torch.cuda.Stream(device=self.params[0].device) if self._cuda else None
+        backend = dist.get_backend(group) if dist.is_initialized() else ""
+        self._avg = backend == "nccl"                 # gloo has no AVG: SUM, then divide
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._works: List = []
+        self.begin()
+
+    def begin(self):
+        self._pending = [len(g) for g in self.groups]
+        self._launched = [False] * len(self.groups)
+        self._works = []
+
+    def _reduce(self, tensors):
+        op = dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
+        cm = getattr(dist, "_coalescing_manager", None)
+        if self._avg and cm is not None and len(tensors) > 1:
+            with cm(group=self.group, device=tensors[0].device, async_ops=True) as work:
+                for t in tensors:
+                    dist.all_reduce(t, op=op, group=self.group)
+            self._works.append(work)
+        else:
+            for t in tensors:
+                self._works.append(dist.all_reduce(t, op=op, group=self.group, async_op=True))
+
+    def _launch(self, gi):
+        self._launched[gi] = True
+        if self.world == 1:
+            return
+        tensors = [p.grad for p in self.groups[gi] if p.grad is not None]
+        if not tensors:
+            return
+        if self._cuda:
+            ev = torch.cuda.Event()
+            ev.record()                               # the gradients of this group are complete on the current stream
+            self._stream.wait_event(ev)
+            with torch.cuda.stream(self._stream):
+                self._reduce(tensors)
+        else:
+            self._reduce(tensors)
+
+    def _on_grad(self, p):
+        gi = self._gid[p]
+        self._pending[gi] -= 1
+        if self._pending[gi] == 0 and not self._launched[gi]:
+            self._launch(gi)
+
+    def finish(self):
+        for gi in range(len(self.groups)):
+            if not self._launched[gi]:
+                self._launch(gi)
+        for w in self._works:
+            if w is not None:
+                w.wait()
+        if self._cuda:
+            torch.cuda.current_stream().wait_stream(self._stream)
+        if self.world > 1 and not self._avg:
+            for g in self.groups:
+                for p in g:
+                    if p.grad is not None:
+                        p.grad.div_(self.world)
+        self._works = []
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()

@@ -49,6 +49,11 @@ def empty_act(shape, dtype, device) -> torch.Tensor:
     return flat[:n].view(*shape)
 
 
+def set_sm_budget(n_sms: int) -> int:
+    """Cap the SM count the persistent kernels size their grids for (0 = all SMs); returns the effective count."""
+    return int(_lib.load().mtasr_set_sm_budget(int(n_sms)))
+
+
 def launch_count() -> int:
     return int(_lib.load().mtasr_launch_count())
 

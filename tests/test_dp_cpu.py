@@ -15,21 +15,30 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, kind="bucket"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from mtasr_b200.dp import GradBucketReducer
+    from mtasr_b200.dp import GradBucketReducer, GradGroupReducer
     torch.manual_seed(0)                                      # same weights on both ranks
     net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 8), torch.nn.Linear(8, 4))
     net[3].weight.requires_grad_(False)                       # frozen parameter
     unused = torch.nn.Parameter(torch.ones(5))                # trainable but never reached by the loss
     params = list(net.parameters()) + [unused]
-    red = GradBucketReducer(params, bucket_bytes=1024)        # tiny buckets -> several collectives
-    assert len(red.buckets) > 1
+    if kind == "bucket":
+        red = GradBucketReducer(params, bucket_bytes=1024)    # tiny buckets -> several collectives
+        assert len(red.buckets) > 1
+    else:
+        red = GradGroupReducer(params, group_bytes=1024)      # in-place, copy-free groups
+        assert len(red.groups) > 1
     for step in range(2):                                     # reuse across steps
         g = torch.Generator().manual_seed(100 + rank + 10 * step)
         x = torch.randn(6, 16, generator=g)                   # each rank draws its own utterances
-        red.zero_grad()
+        if kind == "bucket":
+            red.zero_grad()
+        else:
+            for p in params:
+                p.grad = None
+            red.begin()
         net(x).pow(2).mean().backward()
         red.finish()
     # single-process reference: mean of the two ranks' gradients of the last step
@@ -44,7 +53,7 @@ def _worker(rank, world, port, out):
                 ref[i] += next(it) / world
     ok = True
     for p, r_ in zip(params, ref):
-        if p.requires_grad:
+        if p.requires_grad and (kind == "bucket" or p is not unused):
             ok = ok and p.grad is not None and torch.allclose(p.grad, r_, atol=1e-6)
         else:
             ok = ok and p.grad is None
@@ -57,4 +66,12 @@ def test_bucketed_allreduce_world2_gloo():
     with mp.Manager() as m:
         out = m.dict()
         mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+        assert out[0] is True and out[1] is True
+
+
+def test_inplace_group_allreduce_world2_gloo():
+    mp.set_start_method("spawn", force=True)
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_worker, args=(2, _free_port(), out, "group"), nprocs=2, join=True)
         assert out[0] is True and out[1] is True
