@@ -381,8 +381,18 @@ def main_ours(args):
     alg_gemm = (fl["total"] - fl["attention_total"] - fl["lstm_recurrent_total"]) * B
     peak, peak_src = peaks()
     ms_step = ms / args.steps
+    # DRAM traffic of the kernel's launches of ONE step (sum over the launches, like `achieved`), from the committed ncu
+    # metrics pass of this workload (profiles/gemm_traffic_r1.json); only quoted for the configuration it was captured on
+    traffic = None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "gemm_traffic_r1.json")
+    if os.path.exists(tpath) and args.mode == "train" and args.speakers == 2 and args.seconds == 10.0 and B == 32 and not args.layers:
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("launches_per_step") == gemm_launches:
+            traffic = tj["dram_bytes"]
     roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05/TMEM/TMA)", "achieved": alg_gemm / (gemm_ms / 1e3) / 1e12,
-            "peak": peak, "unit": "TFLOP/s", "frac": alg_gemm / (gemm_ms / 1e3) / 1e12 / peak, "traffic": None,
+            "peak": peak, "unit": "TFLOP/s", "frac": alg_gemm / (gemm_ms / 1e3) / 1e12 / peak, "traffic": traffic,
+            "traffic_unit": "DRAM bytes (read + write) per step over the kernel's launches, ncu, profiles/gemm_traffic_r1.json",
             "algorithmic_tflop_per_step_in_kernel": alg_gemm / 1e12,
             "peak_source": peak_src, "launches_per_step": gemm_launches, "kernel_ms_per_step": gemm_ms,
             "kernel_share_of_step": gemm_ms / ms_step, "algorithmic_tflop_per_step": alg_step / 1e12,
