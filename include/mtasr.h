@@ -189,8 +189,10 @@ int mtasr_split_bf16(const float* x, int64_t n, int32_t c, int32_t order, int32_
 int mtasr_softmax_from_logits(const void* logits_f16, const float* lse, const float* rowscale, int64_t rows, int32_t V,
                               int64_t ld, void* P_bf16, float* colsum, void* stream);
 /* weight_norm over the last dim (torch.nn.utils.parametrizations.weight_norm(conv, dim=2), hf:48-66): v (R, Kt) f32 with
- * R = all leading dims flattened, g (Kt); w = g v / ||v[:, c]||.  sumsq (Kt) and dot (Kt) are ACCUMULATED scratch (zero them
- * first); sumsq from the forward is an input of the backward.  dv (R, Kt), dg (Kt) written.  Kt must divide 256. */
+ * R = all leading dims flattened, g (Kt); w = g v / ||v[:, c]||.  sumsq and dot are (1 + MTASR_WN_PARTS) * Kt floats: [0, Kt)
+ * receives the column reduction, the rest is scratch for per-CTA partials summed in a fixed order (deterministic: no
+ * atomics); sumsq[0, Kt) from the forward is an input of the backward.  dv (R, Kt), dg (Kt) written.  Kt must divide 256. */
+#define MTASR_WN_PARTS 128
 int mtasr_weightnorm_fwd(const float* v, const float* g, int64_t R, int32_t Kt, float* w, float* sumsq, void* stream);
 int mtasr_weightnorm_bwd(const float* dw, const float* v, const float* g, const float* sumsq, int64_t R, int32_t Kt, float* dv,
                          float* dg, float* dot, void* stream);

@@ -317,6 +317,7 @@ softmax_from_logits_kernel(const __half* __restrict__ lg, const float* __restric
 // ------------------------------------------------------------------------------------------------ weight norm (last dim)
 // torch.nn.utils.parametrizations.weight_norm(conv, dim=2) of the positional conv (hf:48-66): w[r][c] = g[c] v[r][c] / ||v[:, c]||
 // with the norm over all rows r = (out, in) of tap c.  Column reductions over the (R, Kt) matrix + one elementwise pass.
+static constexpr int WN_PARTS = 128;   // CTAs (= partial sums per column) of the weight-norm column reductions
 template <bool DOT>
 __global__ void __launch_bounds__(256)
 wn_colreduce_kernel(const float* __restrict__ a, const float* __restrict__ b, long long R, int Kt, float* __restrict__ out) {
@@ -331,8 +332,18 @@ wn_colreduce_kernel(const float* __restrict__ a, const float* __restrict__ b, lo
   __syncthreads();
   if (lr == 0) {
     for (int i = 1; i < nr; ++i) acc += red[i * Kt + c];
-    atomicAdd(out + c, acc);
+    out[static_cast<long long>(blockIdx.x) * Kt + c] = acc;   // per-CTA partial: summed in a fixed order below (deterministic)
   }
+}
+// out[c] = sum over the CTA partials, fixed order: the normalised weight must not change from call to call (an atomic
+// accumulation moved ||v|| by an ulp between calls, which flipped bf16 roundings of the kernel and made the forward
+// non-reproducible at the 1e-4 level).
+__global__ void wn_partial_sum_kernel(const float* __restrict__ part, int nparts, int Kt, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Kt) return;
+  float s = 0.f;
+  for (int i = 0; i < nparts; ++i) s += part[static_cast<long long>(i) * Kt + c];
+  out[c] = s;
 }
 // fwd: w = v * g / sqrt(sumsq);  bwd: dv = (g / n) (dw - v dot / n^2), n = sqrt(sumsq), dot = sum_r dw v
 __global__ void wn_apply_kernel(const float* __restrict__ v, const float* __restrict__ g, const float* __restrict__ sumsq,
@@ -828,7 +839,10 @@ extern "C" int mtasr_softmax_from_logits(const void* logits_f16, const float* ls
 extern "C" int mtasr_weightnorm_fwd(const float* v, const float* g, int64_t R, int32_t Kt, float* w, float* sumsq, void* stream) {
   MTASR_CHECK_ARG(v && g && w && sumsq && R > 0 && Kt > 0 && Kt <= 256 && 256 % Kt == 0, "weightnorm_fwd: need Kt | 256 (Kt=%d)", Kt);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  wn_colreduce_kernel<false><<<num_sms(), 256, 0, st>>>(v, nullptr, R, Kt, sumsq);
+  // sumsq: (1 + WN_PARTS) * Kt floats; [0, Kt) receives the result, the rest holds the per-CTA partials
+  wn_colreduce_kernel<false><<<WN_PARTS, 256, 0, st>>>(v, nullptr, R, Kt, sumsq + Kt);
+  MTASR_COUNT_LAUNCH();
+  wn_partial_sum_kernel<<<(Kt + 127) / 128, 128, 0, st>>>(sumsq + Kt, WN_PARTS, Kt, sumsq);
   MTASR_COUNT_LAUNCH();
   wn_apply_kernel<<<grid_for(R * Kt, 256), 256, 0, st>>>(v, g, sumsq, nullptr, nullptr, R * Kt, Kt, w);
   MTASR_COUNT_LAUNCH();
@@ -840,7 +854,9 @@ extern "C" int mtasr_weightnorm_bwd(const float* dw, const float* v, const float
                                     float* dv, float* dg, float* dot, void* stream) {
   MTASR_CHECK_ARG(dw && v && g && sumsq && dv && dg && dot && R > 0 && Kt > 0 && Kt <= 256 && 256 % Kt == 0, "weightnorm_bwd: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  wn_colreduce_kernel<true><<<num_sms(), 256, 0, st>>>(dw, v, R, Kt, dot);
+  wn_colreduce_kernel<true><<<WN_PARTS, 256, 0, st>>>(dw, v, R, Kt, dot + Kt);
+  MTASR_COUNT_LAUNCH();
+  wn_partial_sum_kernel<<<(Kt + 127) / 128, 128, 0, st>>>(dot + Kt, WN_PARTS, Kt, dot);
   MTASR_COUNT_LAUNCH();
   wn_apply_kernel<<<grid_for(R * Kt, 256), 256, 0, st>>>(v, g, sumsq, dw, dot, R * Kt, Kt, dv);
   MTASR_COUNT_LAUNCH();

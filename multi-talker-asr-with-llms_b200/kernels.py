@@ -253,12 +253,15 @@ def softmax_from_logits(logits16: torch.Tensor, lse: torch.Tensor, rowscale: tor
     return (P, cs) if want_colsum else P
 
 
+WN_PARTS = 128      # MTASR_WN_PARTS of include/mtasr.h
+
+
 def weightnorm_fwd(v: torch.Tensor, g: torch.Tensor):
     """v (..., Kt) f32, g (Kt) -> (w like v, sumsq (Kt))."""
     v = v.contiguous()
     Kt = v.shape[-1]
     w = torch.empty_like(v)
-    sumsq = torch.zeros(Kt, device=v.device, dtype=torch.float32)
+    sumsq = torch.empty((1 + WN_PARTS) * Kt, device=v.device, dtype=torch.float32)   # result + per-CTA partials
     check(_lib.load().mtasr_weightnorm_fwd(_p(v), _p(g), v.numel() // Kt, Kt, _p(w), _p(sumsq), _stream()), "mtasr_weightnorm_fwd")
     return w, sumsq
 
@@ -268,7 +271,7 @@ def weightnorm_bwd(dw: torch.Tensor, v: torch.Tensor, g: torch.Tensor, sumsq: to
     Kt = v.shape[-1]
     dv = torch.empty_like(v)
     dg = torch.empty(Kt, device=v.device, dtype=torch.float32)
-    dot = torch.zeros(Kt, device=v.device, dtype=torch.float32)
+    dot = torch.empty((1 + WN_PARTS) * Kt, device=v.device, dtype=torch.float32)
     check(_lib.load().mtasr_weightnorm_bwd(_p(dw), _p(v), _p(g), _p(sumsq), v.numel() // Kt, Kt, _p(dv), _p(dg), _p(dot), _stream()),
           "mtasr_weightnorm_bwd")
     return dv, dg

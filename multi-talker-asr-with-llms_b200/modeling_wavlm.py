@@ -21,6 +21,7 @@ from typing import Optional, Tuple, Union
 import numpy as np
 import torch
 import torch.nn.functional as F
+import torch.utils.checkpoint
 from torch import nn
 from transformers.models.wavlm.configuration_wavlm import WavLMConfig
 from transformers.models.wavlm.modeling_wavlm import (
@@ -371,10 +372,16 @@ class WavLMModel(WavLMPreTrainedModel):
             hidden = ops.layer_norm(hidden, enc.layer_norm.weight, enc.layer_norm.bias, enc.layer_norm.eps, F32)
         table = self._relpos_table(T, hidden.device)
         all_h = () if output_hidden_states else None
+        # `--gradient_checkpointing` (ref:run.sh:239 -> PreTrainedModel.gradient_checkpointing_enable sets the flag on the
+        # encoder; the reference's layers are GradientCheckpointingLayers, hf:298,339): recompute each layer in the backward
+        ckpt = bool(getattr(enc, "gradient_checkpointing", False)) and self.training and torch.is_grad_enabled()
         for layer in enc.layers:
             if output_hidden_states:
                 all_h = all_h + (hidden,)
-            hidden = self._encoder_layer(hidden, layer, table, klen)
+            if ckpt:
+                hidden = torch.utils.checkpoint.checkpoint(self._encoder_layer, hidden, layer, table, klen, use_reentrant=False)
+            else:
+                hidden = self._encoder_layer(hidden, layer, table, klen)
         if self.config.do_stable_layer_norm:
             hidden = ops.layer_norm(hidden, enc.layer_norm.weight, enc.layer_norm.bias, enc.layer_norm.eps, F32)
         if output_hidden_states:
