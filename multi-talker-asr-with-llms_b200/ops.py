@@ -293,6 +293,31 @@ class AttentionFn(Function):
 
 
 # ------------------------------------------------------------------------------------------------------ fused pre-LN blocks
+# The residual-stream gradient leaves one block's LayerNorm backward as fp32 and is immediately cast to bf16 by the next
+# block's backward (operand of its dgrad / wgrad GEMMs).  The LayerNorm backward kernel can write both precisions in one
+# pass, so the producer publishes the bf16 twin under the identity of the fp32 tensor it returns to autograd; the consumer
+# uses it only if it receives that very tensor object, unmodified (autograd hands a single-consumer gradient through
+# unchanged; anything else -- accumulation, hooks, checkpoint replays -- misses the registry and falls back to the cast).
+_bf16_twins = {}
+
+
+def _publish_twin(t32: torch.Tensor, tb: torch.Tensor) -> None:
+    if len(_bf16_twins) > 16:
+        _bf16_twins.clear()
+    try:
+        _bf16_twins[id(t32)] = (weakref.ref(t32), t32._version, tb)
+    except TypeError:
+        pass
+
+
+def _cast_or_twin(dy: torch.Tensor) -> torch.Tensor:
+    """bf16 (rows, D) operand copy of the fp32 gradient `dy`."""
+    hit = _bf16_twins.pop(id(dy), None)
+    if hit is not None and hit[0]() is dy and hit[1] == dy._version and hit[2].numel() == dy.numel():
+        return hit[2].view(-1, dy.shape[-1])
+    return K.cast_bf16(dy.view(-1, dy.shape[-1]))
+
+
 def _gate_params(weight, bias, const, H):
     """4-row sums of gru_rel_pos_linear (8,64) / its bias, and gru_rel_pos_const as (H,) -- see RelPosGateFn."""
     w = weight.detach().float()
@@ -342,7 +367,7 @@ class PreLNAttentionFn(Function):
         B, T, D, H, scale = ctx.dims
         need = ctx.needs_input_grad
         dy = dy.contiguous()
-        dyb = K.cast_bf16(dy.view(B * T, D))
+        dyb = _cast_or_twin(dy)
         dO = K.linear_dgrad(dyb, wob)
         dwo = K.linear_wgrad(dyb, O) if need[10] else None
         dbo = K.colsum(dyb) if need[11] else None
@@ -351,9 +376,11 @@ class PreLNAttentionFn(Function):
         dx = dlnw = dlnb = None
         if need[0] or need[1] or need[2]:
             dh1 = K.linear_dgrad(dqkv, wqkv, residual=dxg.view(B * T, D))                      # QKV dgrad + gate path, one epilogue
-            dxf, _, dlnw, dlnb = K.layernorm_bwd(dh1.view(B, T, D), xf, mean, rstd, gamma, dres=dy, want_f32=True,
-                                                 want_param_grads=need[1] or need[2])
+            dxf, dxb, dlnw, dlnb = K.layernorm_bwd(dh1.view(B, T, D), xf, mean, rstd, gamma, dres=dy, want_f32=True,
+                                                   want_bf16=need[0], want_param_grads=need[1] or need[2])
             dx = dxf if need[0] else None
+            if dx is not None:
+                _publish_twin(dx, dxb)
         dwq = dwk = dwv = dbq = dbk = dbv = None
         if need[4] or need[6] or need[8]:
             dwqkv = K.linear_wgrad(dqkv, h1.view(B * T, D))
@@ -392,14 +419,16 @@ class PreLNFFNFn(Function):
         need = ctx.needs_input_grad
         D = xf.shape[-1]
         dy = dy.contiguous()
-        dyb = K.cast_bf16(dy.view(-1, D))
+        dyb = _cast_or_twin(dy)
         du = K.linear_dgrad(dyb, w2b, act=K.ACT_GELU_BWD, act_src=u)
         dx = dlnw = dlnb = None
         if need[0] or need[1] or need[2]:
             dh = K.linear_dgrad(du, w1b)
-            dxf, _, dlnw, dlnb = K.layernorm_bwd(dh.view(xf.shape), xf, mean, rstd, gamma, dres=dy, want_f32=True,
-                                                 want_param_grads=need[1] or need[2])
+            dxf, dxb, dlnw, dlnb = K.layernorm_bwd(dh.view(xf.shape), xf, mean, rstd, gamma, dres=dy, want_f32=True,
+                                                   want_bf16=need[0], want_param_grads=need[1] or need[2])
             dx = dxf if need[0] else None
+            if dx is not None:
+                _publish_twin(dx, dxb)
         dw1 = K.linear_wgrad(du, hb.view(-1, D)) if need[4] else None
         db1 = K.colsum(du) if need[5] else None
         dw2 = K.linear_wgrad(dyb, a) if need[6] else None
