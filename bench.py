@@ -230,6 +230,9 @@ def main_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if comm_sms:
             os.environ.setdefault("NCCL_MAX_CTAS", str(comm_sms))
+        # the reducer waits on every NCCL work itself (GradGroupReducer.finish): no record_stream bookkeeping on the
+        # gradient tensors, whose deferred frees otherwise churn the caching allocator when the host runs ahead
+        os.environ.setdefault("TORCH_NCCL_AVOID_RECORD_STREAMS", "1")
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(1234)

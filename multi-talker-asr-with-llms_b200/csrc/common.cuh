@@ -28,6 +28,7 @@ int set_error(int code, const char* fmt, ...);
   } while (0)
 
 int num_sms();
+int num_units(int ncta);   // CTAs or TPC-safe CTA pairs available to a persistent kernel (api.cu)
 extern std::atomic<long long> g_launches;
 #define MTASR_COUNT_LAUNCH() ::mtasr::g_launches.fetch_add(1)
 

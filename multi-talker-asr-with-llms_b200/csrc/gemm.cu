@@ -874,7 +874,7 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
       d->batch0 == 1 && d->batch1 == 1 && d->alpha == 1.0f && p.num_kb >= 16 && getenv("MTASR_GEMM_NO_SPLITK") == nullptr) {
     // choose the split that best fills whole waves of SMs (wave quantisation: e.g. 500 tiles on 148 SMs run as 4 waves at
     // 84 % occupancy, 2 x 500 half-K items as 7 waves at 97 %), keeping >= 32 k-blocks (K >= 2048) per item
-    const int sms = num_sms() / ncta;   // schedulable units: CTAs or CTA pairs
+    const int sms = num_units(ncta);   // schedulable units: CTAs or CTA pairs
     auto eff = [&](int sp) {
       const long long items = static_cast<long long>(p.num_tiles) * sp;
       const long long waves = (items + sms - 1) / sms;
@@ -928,7 +928,7 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   }
   GemmKernelFn kernel = ncta == 2 ? entry->fn2 : entry->fn;
 
-  const int units = num_sms() / ncta;
+  const int units = num_units(ncta);
   const int grid = (p.num_tiles < units ? p.num_tiles : units) * ncta;
   ProfRec rec{};
   bool prof = false;
