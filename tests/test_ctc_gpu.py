@@ -34,7 +34,10 @@ def test_ctc_golden(cuda, golden_dir):
     assert nll[5].item() == 0.0 and dl[5].abs().max().item() == 0.0      # infeasible row: zero_infinity
 
 
-@pytest.mark.parametrize("B,T,V,Lmax,seed", [(4, 50, 30, 12, 0), (3, 200, 500, 60, 1), (2, 300, 64, 120, 2), (2, 20, 11, 0, 3)])
+@pytest.mark.parametrize("B,T,V,Lmax,seed", [(4, 50, 30, 12, 0), (3, 200, 500, 60, 1), (2, 300, 64, 120, 2), (2, 20, 11, 0, 3),
+                                              (2, 560, 300, 255, 4),      # maximum label length (16 states per lane)
+                                              (3, 1, 9, 1, 5), (3, 3, 9, 2, 6),   # fewer frames than one ring chunk
+                                              (2, 67, 40, 30, 7)])        # frame count not a multiple of the chunk
 def test_ctc_vs_fp64_oracle(cuda, B, T, V, Lmax, seed):
     from mtasr_b200 import kernels as Kn
     from oracle import ctc_ref
