@@ -40,7 +40,9 @@ def _inputs(B, H, T, cuda, seed=0, ragged=True):
     return qkv, gate, table, klen
 
 
-@pytest.mark.parametrize("B,H,T", [(2, 2, 64), (2, 3, 197), (1, 2, 499), (3, 16, 499), (1, 2, 1100), (2, 1, 128), (1, 1, 129)])
+@pytest.mark.parametrize("B,H,T", [(2, 2, 64), (2, 3, 197), (1, 2, 499), (3, 16, 499), (1, 2, 1100), (2, 1, 128), (1, 1, 129),
+                                   (4, 16, 300),     # three key tiles (odd): S/P buffer parity restarts per item, several items per CTA
+                                   (2, 16, 512), (2, 4, 385), (2, 16, 513)])   # full last tile / one key in the last tile / first two-pass length
 def test_attn_fwd(cuda, B, H, T):
     from mtasr_b200 import kernels as Kn
     qkv, gate, table, klen = _inputs(B, H, T, cuda)
@@ -54,7 +56,7 @@ def test_attn_fwd(cuda, B, H, T):
     assert _rel(out2, ref2) < 6e-3
 
 
-@pytest.mark.parametrize("B,H,T", [(2, 2, 64), (2, 3, 197), (2, 16, 499), (1, 2, 749), (1, 1, 129)])
+@pytest.mark.parametrize("B,H,T", [(2, 2, 64), (2, 3, 197), (2, 16, 499), (1, 2, 749), (1, 1, 129), (4, 16, 300), (2, 4, 385)])
 def test_attn_bwd(cuda, B, H, T):
     """dq/dk/dv, dgate and the Toeplitz table gradient vs torch autograd through the fp32 restatement."""
     from mtasr_b200 import kernels as Kn
