@@ -69,3 +69,26 @@ def test_product_path_fails_loudly_without_cuda():
         K.cast_bf16(torch.zeros(8))
     with pytest.raises((MtasrError, RuntimeError)):
         K.ctc_collapse(torch.zeros(2, 4, dtype=torch.int64), 1, 0)
+
+
+def test_sm_budget_precision_switch_and_new_entry_argument_checks():
+    """Host-only behaviour of the later additions: SM budget (data-parallel backward), fp32 parity-mode switch, and the
+    argument checks of the entry points that need no device to reject bad input."""
+    from mtasr_b200 import _lib, precise
+    lib = _lib.load()
+    total = lib.mtasr_set_sm_budget(0)
+    assert total > 0
+    assert lib.mtasr_set_sm_budget(total - 8) == total - 8
+    assert lib.mtasr_set_sm_budget(total + 100) == total          # a budget above the device is "all SMs"
+    assert lib.mtasr_set_sm_budget(-1) < 0
+    assert lib.mtasr_set_sm_budget(0) == total
+    assert precise.get_precision() == "bf16"
+    with precise.precision("fp32"):
+        assert precise.get_precision() == "fp32"
+    assert precise.get_precision() == "bf16"
+    with pytest.raises(ValueError):
+        precise.set_precision("fp16")
+    assert lib.mtasr_split_bf16(None, 8, 8, 0, 3, None, None) < 0
+    assert lib.mtasr_softmax_from_logits(None, None, None, 1, 8, 8, None, None, None) < 0
+    assert lib.mtasr_weightnorm_fwd(None, None, 1, 128, None, None, None) < 0
+    assert lib.mtasr_attn_softmax_fwd_split(None, None, None, None, 1, 1, 8, 8, 1.0, 3, None, None) < 0
