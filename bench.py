@@ -29,6 +29,13 @@ METRIC = "encoder+serialized-CTC fwd+bwd audio-sec/s"
 UNIT = "audio-s/s"
 
 
+# BASELINE.json configs: cfg2 = the headline; cfg3 = 3-mix 15 s training step; cfg5 = 30 s forward + greedy collapse (B = 64
+# over 8 GPUs = 8 per GPU)
+PRESETS = {"cfg2": dict(speakers=2, seconds=10.0, batch=32, mode="train"),
+           "cfg3": dict(speakers=3, seconds=15.0, batch=32, mode="train"),
+           "cfg5": dict(speakers=3, seconds=30.0, batch=8, mode="infer")}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -45,7 +52,14 @@ def parse():
                     help="train: fwd+bwd of the serialized-CTC loss (the headline metric); infer: encoder + separator + greedy "
                          "CTC argmax + collapse (BASELINE config 5 shape), not the headline")
     ap.add_argument("--profile-run", action="store_true", help="ncu helper: 1 warm-up + 1 step, no e2e/roofline/cpu legs")
-    return ap.parse_args()
+    ap.add_argument("--config", default=None, choices=sorted(PRESETS),
+                    help="BASELINE.json configuration preset (sets --speakers/--seconds/--batch/--mode); default = cfg2, the headline")
+    ap.add_argument("--no-stock-gpu", action="store_true", help="skip the stock-PyTorch-on-GPU leg (oracle modules on the same GPU)")
+    a = ap.parse_args()
+    if a.config:
+        for k, v in PRESETS[a.config].items():
+            setattr(a, k, v)
+    return a
 
 
 def synth_batch(B, S, n_spk, vocab, seed):
@@ -126,6 +140,20 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+def source_sha16():
+    """Hash of the sources that determine the kernels and the launch sequence: a committed ncu traffic figure is only quoted
+    for the build it was measured on."""
+    import hashlib
+    h = hashlib.sha256()
+    pkg = os.path.join(ROOT, "multi-talker-asr-with-llms_b200")
+    names = sorted(os.listdir(os.path.join(pkg, "csrc")))
+    for f in [os.path.join(pkg, "csrc", n) for n in names if n.endswith((".cu", ".cuh"))] + \
+            [os.path.join(pkg, n) for n in ("ops.py", "kernels.py", "modeling_wavlm.py", "separator.py", "ctc.py")]:
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -159,6 +187,13 @@ def run_cpu_reference(args, steps, warmup, budget_s):
     def step(Bc, seed):
         wav, mask, labels, lens = synth_batch(Bc, S, args.speakers, V_LLAMA3_CTC, seed)
         t0 = time.perf_counter()
+        if args.mode == "infer":                          # ref ...llama.py:873-900: argmax per head + python collapse
+            from oracle import host_ref
+            with torch.no_grad():
+                _, h, _, _ = enc(wav, mask.long())
+                for hd, x in zip(heads, sep(h)):
+                    host_ref.collapse(hd.argmax(x).tolist(), V_LLAMA3_CTC - 1, V_LLAMA3_CTC - 2)
+            return time.perf_counter() - t0
         _, h, _, _ = enc(wav, mask.long())
         sp = sep(h)
         fm = enc.frame_mask_x0(h.shape[1], mask.long())
@@ -178,8 +213,75 @@ def run_cpu_reference(args, steps, warmup, budget_s):
     ts = [step(Bc, 300 + i) for i in range(max(1, steps))]
     dt = sum(ts) / len(ts)
     return dict(value=Bc * args.seconds / dt, ms_per_step=dt * 1e3, cores=cores, batch=Bc, steps=len(ts),
-                sample=f"{Bc} utterance(s) x {args.seconds:g} s per step of the cfg2 workload (WavLM-Large, {args.speakers} heads, "
-                       f"V={V_LLAMA3_CTC}), {len(ts)} timed step(s), torch CPU fp32, {cores} threads")
+                sample=f"{Bc} utterance(s) x {args.seconds:g} s per step of the {workload_name(args).split(':')[0]} workload "
+                       f"(WavLM-Large, {args.speakers} heads, V={V_LLAMA3_CTC}, mode {args.mode}), {len(ts)} timed step(s), "
+                       f"torch CPU fp32, {cores} threads")
+
+
+def run_stock_torch_gpu(args, dev):
+    """SURVEY 8d "what you get today": the oracle's restatement of the reference modules (the transformers WavLM classes
+    the reference instantiates + its separator / CTC / loss wiring, i.e. stock PyTorch / cuBLAS / cuDNN kernels) on the SAME
+    GPU and workload, in fp32 (TF32 off: the reference's default precision, ref:slurm/template.slurm:99) and under
+    torch.autocast(bf16) (its --bf16 option), with the largest batch <= the benched one that fits.  A yardstick printed
+    beside `cpu_baseline`; nothing of the product path runs here."""
+    from oracle.model_ref import RefCTC, RefSeparator, RefWavLMModel, ref_hybrid_ctc
+    from mtasr_b200.configs import V_LLAMA3_CTC, wavlm_config
+    torch.manual_seed(0)
+    cfg = wavlm_config("large", **({"num_hidden_layers": args.layers} if args.layers else {}))
+    S = int(args.seconds * 16000)
+    enc = RefWavLMModel(cfg).to(dev).eval()
+    for p in list(enc.feature_extractor.parameters()) + list(enc.adapter.parameters()):
+        p.requires_grad_(False)
+    sep = RefSeparator(cfg.hidden_size, 896, args.speakers).to(dev).eval()
+    heads = torch.nn.ModuleList(RefCTC(V_LLAMA3_CTC, cfg.hidden_size) for _ in range(args.speakers)).to(dev)
+    params = [p for m in (enc, sep, heads) for p in m.parameters() if p.requires_grad]
+    prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    out = {}
+
+    def step(batch, autocast):
+        wav, mask, labels, lens = batch
+        if args.mode == "infer":
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                _, h, _, _ = enc(wav, mask)
+                return sum(hd.argmax(x.float()).sum() for hd, x in zip(heads, sep(h)))
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            _, h, _, _ = enc(wav, mask)
+            sp = sep(h)
+        fm = enc.frame_mask_x0(h.shape[1], mask)
+        loss, _ = ref_hybrid_ctc(heads, [x.float() for x in sp], fm, labels, lens)
+        torch.autograd.grad(loss, params, allow_unused=True)
+        return loss
+
+    try:
+        for name, autocast in (("fp32", False), ("bf16_autocast", True)):
+            Bc = args.batch
+            while Bc >= 1:
+                try:
+                    wav, mask, labels, lens = synth_batch(Bc, S, args.speakers, V_LLAMA3_CTC, 77)
+                    batch = (wav.to(dev), mask.to(dev).long(), [y.to(dev) for y in labels], [l.to(dev) for l in lens])
+                    step(batch, autocast)                  # warm-up (cuDNN autotune, allocator)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    n = 2
+                    e0.record()
+                    for _ in range(n):
+                        step(batch, autocast)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms = e0.elapsed_time(e1) / n
+                    out[name] = {"value": Bc * args.seconds / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "batch": Bc, "steps": n}
+                    break
+                except torch.OutOfMemoryError:
+                    del batch
+                    torch.cuda.empty_cache()
+                    Bc //= 2
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+    out["what"] = ("oracle modules (transformers WavLM + python-loop LSTM separator + nn.Linear/log_softmax/CTCLoss heads) with stock "
+                   "PyTorch kernels on this GPU, same workload; fp32 = TF32 off")
+    return out
 
 
 def main_reference(args):
@@ -197,9 +299,18 @@ def main_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def workload_name(args):
+    """Truthful description of what is being timed, derived from the arguments (not a fixed string)."""
+    if args.layers:
+        return f"DEBUG {args.layers}-layer encoder"
+    shape = (args.speakers, args.seconds, args.mode)
+    tag = {(2, 10.0, "train"): "cfg2", (3, 15.0, "train"): "cfg3", (3, 30.0, "infer"): "cfg5"}.get(shape, "custom")
+    what = "fwd+bwd, feature encoder frozen" if args.mode == "train" else "forward + greedy CTC argmax + collapse (no backward)"
+    return (f"{tag}: WavLM-Large + Separator(896) + serialized CTC ({args.speakers}mix), {args.seconds:g} s 16 kHz, {what}")
+
+
 def workload_config(args, batch, world):
-    return {"workload": "cfg2: WavLM-Large + Separator(896) + serialized CTC (2mix), 10 s 16 kHz, fwd+bwd, feature encoder frozen"
-            if not args.layers else f"DEBUG {args.layers}-layer encoder",
+    return {"workload": workload_name(args),
             "encoder": "wavlm-large-shaped (24L, D=1024, H=16, F=4096), random init", "speakers": args.speakers,
             "seconds": args.seconds, "batch_per_gpu": batch, "global_batch": batch * world, "vocab": 128259,
             "separator_hidden": 896, "parallelism": f"dp{world}", "spec_augment": "off", "dropout": 0.0,
@@ -387,15 +498,20 @@ def main_ours(args):
     # DRAM traffic of the kernel's launches of ONE step (sum over the launches, like `achieved`), from the committed ncu
     # metrics pass of this workload (profiles/gemm_traffic_r1.json); only quoted for the configuration it was captured on
     traffic = None
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "gemm_traffic_r1.json")
-    if os.path.exists(tpath) and args.mode == "train" and args.speakers == 2 and args.seconds == 10.0 and B == 32 and not args.layers:
+    traffic_src = "null: no ncu DRAM-bytes pass of THIS build / workload is committed (profiles/gemm_traffic_r2.json)"
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic_r2.json")
+    if os.path.exists(tpath) and not args.layers:
         with open(tpath) as f:
             tj = json.load(f)
-        if tj.get("launches_per_step") == gemm_launches:
+        # only quoted when the capture was taken on this very build (hash of the kernel + op sources) and workload
+        if (tj.get("source_sha16") == source_sha16() and tj.get("workload") == workload_name(args) and tj.get("batch") == B
+                and tj.get("launches_per_step") == gemm_launches):
             traffic = tj["dram_bytes"]
+            traffic_src = ("DRAM bytes (read + write) summed over the kernel's launches of one step, ncu dram__bytes_{read,write}.sum, "
+                           "profiles/gemm_traffic_r2.json (same source hash, workload and launch count as this run)")
     roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05/TMEM/TMA)", "achieved": alg_gemm / (gemm_ms / 1e3) / 1e12,
             "peak": peak, "unit": "TFLOP/s", "frac": alg_gemm / (gemm_ms / 1e3) / 1e12 / peak, "traffic": traffic,
-            "traffic_unit": "DRAM bytes (read + write) per step over the kernel's launches, ncu, profiles/gemm_traffic_r1.json",
+            "traffic_unit": traffic_src,
             "algorithmic_tflop_per_step_in_kernel": alg_gemm / 1e12,
             "peak_source": peak_src, "launches_per_step": gemm_launches, "kernel_ms_per_step": gemm_ms,
             "kernel_share_of_step": gemm_ms / ms_step, "algorithmic_tflop_per_step": alg_step / 1e12,
@@ -403,6 +519,16 @@ def main_ours(args):
             "step_achieved_tflops": alg_step / (ms_step / 1e3) / 1e12, "step_frac": alg_step / (ms_step / 1e3) / 1e12 / peak}
 
     cpu = None
+    stock = None
+    if rank == 0 and world == 1 and not args.no_stock_gpu:
+        del net, model
+        net = model = None
+        torch.cuda.empty_cache()
+        try:
+            stock = run_stock_torch_gpu(args, dev)
+        except Exception as ex:                             # a yardstick must never take the bench line down
+            stock = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del net, model
         torch.cuda.empty_cache()
@@ -413,7 +539,7 @@ def main_ours(args):
         line = {"metric": METRIC if args.mode == "train" else "encoder+greedy-CTC forward audio-sec/s", "value": world * B * args.seconds * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(args, B, world), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+                "config": workload_config(args, B, world), "roofline": roof, "cpu_baseline": cpu, "stock_torch_gpu": stock, "e2e": e2e,
                 "gpu_launches": int(launches), "clocks": clocks, "loss": loss0, "trainable_params": n_train,
                 "gflop_per_audio_s": fl["total"] / args.seconds / 1e9}
         print(json.dumps(line), flush=True)

@@ -157,11 +157,14 @@ int mtasr_ctc_gather_cols(const float* dense, const int64_t* ys, const int64_t* 
 int mtasr_ctc_scatter_cols(const float* src, const int64_t* ys, const int64_t* ylens, int32_t B, int32_t T, int32_t V,
                            int32_t Lp, int32_t ys_ld, int64_t blank, float* dense, void* stream);
 /* rows of the head weight (V,D) bf16 / bias (V) f32 touched by each lattice -> wg (B,Lp,D) bf16, bg (B,Lp) f32;
- * and the reverse scatter-add of their gradients (f32 atomics). */
+ * and the reverse scatter-add of their gradients (f32 atomics).  Label ids outside [0, V) (a -100 pad counted into ylens)
+ * gather a zero row / scatter nothing, and ylens is clamped to the label row: no access leaves the (V, D) matrix. */
 int mtasr_ctc_gather_rows(const void* w_bf16, const float* bias, const int64_t* ys, const int64_t* ylens, int32_t B,
-                          int32_t Lp, int32_t D, int32_t ys_ld, int64_t blank, void* wg_bf16, float* bg, void* stream);
+                          int32_t Lp, int32_t D, int32_t ys_ld, int64_t blank, int64_t V, void* wg_bf16, float* bg,
+                          void* stream);
 int mtasr_ctc_scatter_rows(const float* dwg, const float* dbg, const int64_t* ys, const int64_t* ylens, int32_t B,
-                           int32_t Lp, int32_t D, int32_t ys_ld, int64_t blank, float* dw, float* db, void* stream);
+                           int32_t Lp, int32_t D, int32_t ys_ld, int64_t blank, int64_t V, float* dw, float* db,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * HBM-bound row kernels (128-bit vectorised, one warp per row).

@@ -64,8 +64,8 @@ SIGNATURES = {
     "mtasr_segment_mean_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "mtasr_ctc_gather_cols": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I64, _P, _P]),
     "mtasr_ctc_scatter_cols": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I64, _P, _P]),
-    "mtasr_ctc_gather_rows": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _P, _P, _P]),
-    "mtasr_ctc_scatter_rows": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _P, _P, _P]),
+    "mtasr_ctc_gather_rows": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, _P]),
+    "mtasr_ctc_scatter_rows": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, _P]),
     "mtasr_layernorm_fwd": (C.c_int, [_P, _I32, _P, _P, _F, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
     "mtasr_layernorm_bwd": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
     "mtasr_cast_f32_bf16": (C.c_int, [_P, _P, _I64, _P]),

@@ -17,6 +17,13 @@ namespace mtasr {
 
 static constexpr float NEG_INF = -INFINITY;
 
+// Label length of utterance b as the kernels may use it: never past the label row (ys_ld entries) nor past the Lp - 1 label
+// columns of the compact lattice, whatever the caller put into ylens.
+__device__ __forceinline__ int clamp_label_len(long long L, int Lp, int ys_ld) {
+  const long long hi = ys_ld < Lp - 1 ? ys_ld : Lp - 1;
+  return static_cast<int>(L < 0 ? 0 : (L > hi ? hi : L));
+}
+
 // log(exp a + exp b + exp c) on the SFU (ex2 / lg2 approximations, ~1e-7 relative): the recursion is one dependent chain
 // per time step, so the instruction count of this function IS the latency of the kernel.  Branch-free on purpose: with
 // a branch per call the NS calls of one step become NS serialised BSSY/BSYNC regions and their MUFU latencies add up
@@ -77,7 +84,7 @@ ctc_alpha_kernel(const float* __restrict__ glog, const float* __restrict__ lse, 
   if (b >= B) return;
   int Tb = static_cast<int>(hlens[b]);
   Tb = Tb < 0 ? 0 : (Tb > T ? T : Tb);
-  const int L = static_cast<int>(ylens[b]);
+  const int L = clamp_label_len(ylens[b], Lp, ys_ld);   // never walk past the label row / the lattice columns
   const int S = 2 * L + 1;
   const long long* y = ys + static_cast<long long>(b) * ys_ld;
 
@@ -211,7 +218,7 @@ ctc_beta_grad_kernel(const float* __restrict__ glog, const float* __restrict__ l
   if (b >= B) return;
   int Tb = static_cast<int>(hlens[b]);
   Tb = Tb < 0 ? 0 : (Tb > T ? T : Tb);
-  const int L = static_cast<int>(ylens[b]);
+  const int L = clamp_label_len(ylens[b], Lp, ys_ld);   // never walk past the label row / the lattice columns
   const int S = 2 * L + 1;
   const long long* y = ys + static_cast<long long>(b) * ys_ld;
   const double nll = nll_raw[b];
@@ -422,10 +429,12 @@ __global__ void ctc_gather_cols_kernel(const float* __restrict__ dense, const lo
   const int c = static_cast<int>(i % Lp);
   const long long bt = i / Lp;
   const int b = static_cast<int>(bt / T);
-  const int L = static_cast<int>(ylens[b]);
+  const int L = clamp_label_len(ylens[b], Lp, ys_ld);
   float v = 0.f;
-  if (c == 0) v = dense[bt * V + blank];
-  else if (c <= L) v = dense[bt * V + ys[static_cast<long long>(b) * ys_ld + c - 1]];
+  long long id = -1;
+  if (c == 0) id = blank;
+  else if (c <= L) id = ys[static_cast<long long>(b) * ys_ld + c - 1];
+  if (id >= 0 && id < V) v = dense[bt * V + id];        // ids outside [0, V) (e.g. a -100 pad inside ylens) read nothing
   out[i] = v;
 }
 
@@ -439,22 +448,24 @@ __global__ void ctc_scatter_cols_kernel(const float* __restrict__ src, const lon
   const int c = static_cast<int>(i % Lp);
   const long long bt = i / Lp;
   const int b = static_cast<int>(bt / T);
-  const int L = static_cast<int>(ylens[b]);
+  const int L = clamp_label_len(ylens[b], Lp, ys_ld);
   if (c > L) return;
   const long long v = c == 0 ? blank : ys[static_cast<long long>(b) * ys_ld + c - 1];
+  if (v < 0 || v >= V) return;                          // out-of-range id: nothing to scatter to
   atomicAdd(dense + bt * V + v, src[i]);
 }
 
 // Rows of the (V, D) head weight needed by each utterance's lattice -> Wg (B, Lp, D) bf16 (+ bias -> bg (B, Lp)).
 __global__ void ctc_gather_rows_kernel(const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
                                        const long long* __restrict__ ys, const long long* __restrict__ ylens, int B,
-                                       int Lp, int D, int ys_ld, long long blank, __nv_bfloat16* __restrict__ wg,
-                                       float* __restrict__ bg) {
+                                       int Lp, int D, int ys_ld, long long blank, long long V,
+                                       __nv_bfloat16* __restrict__ wg, float* __restrict__ bg) {
   const int b = blockIdx.x / Lp, c = blockIdx.x % Lp;
-  const int L = static_cast<int>(ylens[b]);
+  const int L = clamp_label_len(ylens[b], Lp, ys_ld);
   long long v = -1;
   if (c == 0) v = blank;
   else if (c <= L) v = ys[static_cast<long long>(b) * ys_ld + c - 1];
+  if (v >= V) v = -1;                                   // ids outside [0, V) gather a zero row (never out of bounds)
   __nv_bfloat16* dst = wg + (static_cast<long long>(b) * Lp + c) * D;
   for (int i = threadIdx.x * 8; i < D; i += blockDim.x * 8) {
     uint4 u = make_uint4(0, 0, 0, 0);
@@ -467,12 +478,13 @@ __global__ void ctc_gather_rows_kernel(const __nv_bfloat16* __restrict__ w, cons
 // dW[v(b,c)][:] += dWg[b][c][:]; db[v] += dbg[b][c]  (fp32 atomics; <= B*(L+1) rows touched).
 __global__ void ctc_scatter_rows_kernel(const float* __restrict__ dwg, const float* __restrict__ dbg,
                                         const long long* __restrict__ ys, const long long* __restrict__ ylens, int B,
-                                        int Lp, int D, int ys_ld, long long blank, float* __restrict__ dw,
-                                        float* __restrict__ db) {
+                                        int Lp, int D, int ys_ld, long long blank, long long V,
+                                        float* __restrict__ dw, float* __restrict__ db) {
   const int b = blockIdx.x / Lp, c = blockIdx.x % Lp;
-  const int L = static_cast<int>(ylens[b]);
+  const int L = clamp_label_len(ylens[b], Lp, ys_ld);
   if (c > L) return;
   const long long v = c == 0 ? blank : ys[static_cast<long long>(b) * ys_ld + c - 1];
+  if (v < 0 || v >= V) return;                          // out-of-range id (e.g. -100 inside ylens): no write
   const float* src = dwg + (static_cast<long long>(b) * Lp + c) * D;
   for (int i = threadIdx.x; i < D; i += blockDim.x) atomicAdd(dw + v * D + i, src[i]);
   if (threadIdx.x == 0 && db && dbg) atomicAdd(db + v, dbg[static_cast<long long>(b) * Lp + c]);
@@ -679,23 +691,24 @@ extern "C" int mtasr_ctc_scatter_cols(const float* src, const int64_t* ys, const
 }
 
 extern "C" int mtasr_ctc_gather_rows(const void* w_bf16, const float* bias, const int64_t* ys, const int64_t* ylens,
-                                     int32_t B, int32_t Lp, int32_t D, int32_t ys_ld, int64_t blank, void* wg_bf16,
+                                     int32_t B, int32_t Lp, int32_t D, int32_t ys_ld, int64_t blank, int64_t V, void* wg_bf16,
                                      float* bg, void* stream) {
-  MTASR_CHECK_ARG(w_bf16 && ylens && wg_bf16 && B > 0 && Lp > 0 && D > 0 && D % 8 == 0, "ctc_gather_rows: bad arguments");
+  MTASR_CHECK_ARG(w_bf16 && ylens && wg_bf16 && B > 0 && Lp > 0 && D > 0 && D % 8 == 0 && V > 0 && blank >= 0 && blank < V,
+                  "ctc_gather_rows: bad arguments");
   ctc_gather_rows_kernel<<<B * Lp, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(w_bf16), bias, reinterpret_cast<const long long*>(ys),
-      reinterpret_cast<const long long*>(ylens), B, Lp, D, ys_ld, blank, reinterpret_cast<__nv_bfloat16*>(wg_bf16), bg);
+      reinterpret_cast<const long long*>(ylens), B, Lp, D, ys_ld, blank, V, reinterpret_cast<__nv_bfloat16*>(wg_bf16), bg);
   g_launches.fetch_add(1);
   MTASR_CHECK_LAUNCH("ctc_gather_rows");
   return MTASR_OK;
 }
 
 extern "C" int mtasr_ctc_scatter_rows(const float* dwg, const float* dbg, const int64_t* ys, const int64_t* ylens,
-                                      int32_t B, int32_t Lp, int32_t D, int32_t ys_ld, int64_t blank, float* dw,
+                                      int32_t B, int32_t Lp, int32_t D, int32_t ys_ld, int64_t blank, int64_t V, float* dw,
                                       float* db, void* stream) {
-  MTASR_CHECK_ARG(dwg && ylens && dw && B > 0 && Lp > 0 && D > 0, "ctc_scatter_rows: bad arguments");
+  MTASR_CHECK_ARG(dwg && ylens && dw && B > 0 && Lp > 0 && D > 0 && V > 0 && blank >= 0 && blank < V, "ctc_scatter_rows: bad arguments");
   ctc_scatter_rows_kernel<<<B * Lp, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dwg, dbg, reinterpret_cast<const long long*>(ys), reinterpret_cast<const long long*>(ylens), B, Lp, D, ys_ld, blank, dw, db);
+      dwg, dbg, reinterpret_cast<const long long*>(ys), reinterpret_cast<const long long*>(ylens), B, Lp, D, ys_ld, blank, V, dw, db);
   g_launches.fetch_add(1);
   MTASR_CHECK_LAUNCH("ctc_scatter_rows");
   return MTASR_OK;

@@ -45,6 +45,7 @@ struct GemmKP {
   int a_inner, a_phase;
   int a_use0, a_use1, b_use0, b_use1;  // 0 => operand broadcast over that batch dim (coordinate forced to 0)
   int m_tiles, n_tiles, num_tiles, num_kb;
+  int n_fast;                          // tile rasterisation: 1 = consecutive tiles walk the N tiles of one M tile first
   int splits, kb_per_split;            // split-K (fp32 TMA reduce-add into a pre-zeroed C) for launches with few tiles
   int stages, stage_bytes;             // smem ring geometry (host-chosen to fit the staging buffers)
   int tma_epi;                         // 1: outputs leave through swizzled smem staging + TMA tiled stores
@@ -175,11 +176,24 @@ struct TileCoord {
   int m_tile, n_tile, b0, b1, kb0, kb1;
 };
 __device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, int tile) {
+  // Tiles that run at the same time (consecutive indices, one per SM or SM pair) should share the LARGER operand slab:
+  // the fast index walks the dimension with fewer tiles, so a wave covers all of it and every slab of the other operand is
+  // fetched from HBM once and served to its siblings from L2.  (With the M tiles always fastest, the vocabulary-sized
+  // weight-gradient GEMMs -- 501 x 4 tiles -- streamed their 4.1 GB A operand once per N tile: 17 GB of DRAM reads for
+  // 4.1 GB of data, profiles/gemm_traffic_r1_v15.csv.)
   TileCoord t;
-  t.m_tile = tile % p.m_tiles;
-  int rest = tile / p.m_tiles;
-  t.n_tile = rest % p.n_tiles;
-  int batch = rest / p.n_tiles;
+  int batch;
+  if (p.n_fast) {
+    t.n_tile = tile % p.n_tiles;
+    const int rest = tile / p.n_tiles;
+    t.m_tile = rest % p.m_tiles;
+    batch = rest / p.m_tiles;
+  } else {
+    t.m_tile = tile % p.m_tiles;
+    const int rest = tile / p.m_tiles;
+    t.n_tile = rest % p.n_tiles;
+    batch = rest / p.n_tiles;
+  }
   if (p.splits > 1) {   // un-batched launch: the outermost index is the K split
     t.b0 = t.b1 = 0;
     t.kb0 = batch * p.kb_per_split;
@@ -782,6 +796,10 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   MTASR_CHECK_ARG(nt < (1LL << 31), "gemm: too many tiles");
   p.num_tiles = static_cast<int>(nt);
   p.num_kb = (d->K + BK - 1) / BK;
+  {
+    const char* rz = getenv("MTASR_GEMM_RASTER");   // debugging / A-B switch: "m" or "n" forces the fast index
+    p.n_fast = rz ? (rz[0] == 'n') : (p.n_tiles < p.m_tiles);
+  }
   p.splits = 1;
   p.kb_per_split = p.num_kb;
   p.c = d->c; p.c_dtype = d->c_dtype; p.c_ld = d->c_ld; p.c_sb0 = d->c_sb0; p.c_sb1 = d->c_sb1;

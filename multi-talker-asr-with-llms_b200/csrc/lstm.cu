@@ -12,6 +12,7 @@
 // four Hs-wide chunks against its resident W_hh^T slice, split-K over the 8 warps with an smem reduction.
 // dW / dx / db are batched GEMMs / column sums over the saved dgates afterwards.
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -44,15 +45,21 @@ __device__ __forceinline__ void grid_arrive(unsigned int* bar) {
   __syncthreads();
   if (threadIdx.x == 0) atomicAdd(bar, 1u);
 }
+// A waiter that spins longer than g_spin_limit SM clocks traps (a missing co-resident CTA would otherwise hang the GPU
+// until the watchdog).  MTASR_LSTM_SPIN_TIMEOUT_MS sets the limit (default 2000 ms at ~2 GHz); 0 disables it -- needed
+// under ncu kernel replay, a debugger or GPU time-slicing, where a CTA can legitimately be descheduled for seconds.
+__device__ long long g_spin_limit = 4000000000LL;
+
 __device__ __forceinline__ void grid_wait(unsigned int* bar, unsigned int target) {
   if (threadIdx.x == 0) {
     unsigned int v;
+    const long long limit = g_spin_limit;
     long long t0 = clock64();
     unsigned int spins = 0;
     while (true) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
       if (v >= target) break;
-      if ((++spins & 0xfff) == 0 && clock64() - t0 > 4000000000LL) __trap();
+      if ((++spins & 0xfff) == 0 && limit > 0 && clock64() - t0 > limit) __trap();
     }
   }
   __syncthreads();
@@ -652,6 +659,17 @@ static size_t lstm_bwd_smem(int Hs, int Bp) {
          static_cast<size_t>(9) * Bp * 8 * 4;
 }
 
+// Push MTASR_LSTM_SPIN_TIMEOUT_MS (once per process) into the device-side spin limit of grid_wait.
+static void lstm_sync_spin_limit() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    const char* e = getenv("MTASR_LSTM_SPIN_TIMEOUT_MS");
+    if (!e) return;
+    const long long cycles = static_cast<long long>(atof(e) * 2.0e6);   // ~2 GHz SM clock
+    cudaMemcpyToSymbol(g_spin_limit, &cycles, sizeof(cycles));
+  });
+}
+
 static int lstm_check(int B, int T, int Hs, int ldw, const char* who) {
   if (B <= 0 || B > 64) return set_error(MTASR_ERR_UNSUPPORTED, "%s: batch %d not in [1,64] (chunk the batch)", who, B);
   if (T <= 0 || Hs <= 0 || Hs % 16 != 0)
@@ -669,6 +687,7 @@ using namespace mtasr;
 extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw, int32_t B, int32_t T, int32_t Hs,
                               void* h_bf16, float* h_f32, float* c_all, float* gates, uint32_t* barrier, void* stream) {
   MTASR_CHECK_ARG(xg && whh_bf16 && h_bf16 && c_all && gates && barrier, "lstm_fwd: null pointer");
+  lstm_sync_spin_limit();
   cudaStream_t st0 = static_cast<cudaStream_t>(stream);
   {
     size_t smem_bs = 0;
@@ -713,6 +732,7 @@ extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw
 extern "C" int mtasr_lstm_bwd(const float* dh_out, const float* gates, const float* c_all, const void* whh_bf16, int32_t ldw,
                               int32_t B, int32_t T, int32_t Hs, void* dgates_bf16, uint32_t* barrier, void* stream) {
   MTASR_CHECK_ARG(dh_out && gates && c_all && whh_bf16 && dgates_bf16 && barrier, "lstm_bwd: null pointer");
+  lstm_sync_spin_limit();
   cudaStream_t st0 = static_cast<cudaStream_t>(stream);
   {
     size_t smem_bs = 0;

@@ -98,7 +98,19 @@ class GradGroupReducer:
     (`ncclGroupStart/End` around per-tensor all-reduces, `ReduceOp.AVG`) reduces the tensors in place on a side stream
     ordered after the producing kernels by an event.  `finish()` flushes groups that never completed (unused / frozen
     parameters) and makes the current stream wait for the collectives.  Call `begin()` before each backward (with
-    `.grad = None`, as `optimizer.zero_grad(set_to_none=True)` leaves them)."""
+    `.grad = None`, as `optimizer.zero_grad(set_to_none=True)` leaves them).
+
+    The sequence of collectives is RANK-INVARIANT by construction, whatever each rank's data did to its autograd graph:
+      * every group is reduced with the full, fixed tensor list of its parameters -- a parameter that received no gradient
+        on this rank (an unused head or branch, a data-dependent path) contributes zeros, it is never dropped from the call;
+      * groups are launched strictly in index order: a group that is complete on this rank but follows an incomplete one
+        waits for `finish()`, so two ranks can never issue the same collectives in different orders.
+    (A parameter unused on every rank therefore ends with a zero gradient, not None, when world_size > 1.)
+
+    One `begin()` ... `finish()` window covers exactly ONE backward pass through `.backward()`.  A gradient hook firing for
+    a group that was already reduced -- a second backward (PCGrad's K+1 passes, gradient accumulation) without `begin()` --
+    raises instead of silently accumulating into averaged tensors.  For those schemes accumulate locally
+    (torch.autograd.grad, or several backward passes outside the window) and call `reduce_now()` once."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group_bytes: int = 256 << 20, group=None):
         self.group = group
@@ -130,6 +142,7 @@ class GradGroupReducer:
     def begin(self):
         self._pending = [len(g) for g in self.groups]
         self._launched = [False] * len(self.groups)
+        self._next = 0                                # groups [0, _next) have been launched
         self._works = []
 
     def _reduce(self, tensors):
@@ -148,9 +161,10 @@ class GradGroupReducer:
         self._launched[gi] = True
         if self.world == 1:
             return
-        tensors = [p.grad for p in self.groups[gi] if p.grad is not None]
-        if not tensors:
-            return
+        for p in self.groups[gi]:                     # rank-invariant tensor list: zeros stand in for a missing gradient
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+        tensors = [p.grad for p in self.groups[gi]]
         if self._cuda:
             ev = torch.cuda.Event()
             ev.record()                               # the gradients of this group are complete on the current stream
@@ -160,16 +174,25 @@ class GradGroupReducer:
         else:
             self._reduce(tensors)
 
+    def _advance(self, force: bool = False):
+        """Launch, in index order, every group that is complete (or every remaining group when `force`)."""
+        while self._next < len(self.groups) and (force or self._pending[self._next] == 0):
+            self._launch(self._next)
+            self._next += 1
+
     def _on_grad(self, p):
         gi = self._gid[p]
+        if self._launched[gi] or self._pending[gi] <= 0:
+            raise RuntimeError(
+                "GradGroupReducer: a gradient arrived for a parameter whose group was already reduced in this begin()/finish() "
+                "window (second backward pass without begin()?).  Reduce once per window: call begin() before every "
+                ".backward(), or accumulate locally and call reduce_now().")
         self._pending[gi] -= 1
-        if self._pending[gi] == 0 and not self._launched[gi]:
-            self._launch(gi)
+        if gi == self._next and self._pending[gi] == 0:
+            self._advance()
 
     def finish(self):
-        for gi in range(len(self.groups)):
-            if not self._launched[gi]:
-                self._launch(gi)
+        self._advance(force=True)
         for w in self._works:
             if w is not None:
                 w.wait()
@@ -178,9 +201,14 @@ class GradGroupReducer:
         if self.world > 1 and not self._avg:
             for g in self.groups:
                 for p in g:
-                    if p.grad is not None:
-                        p.grad.div_(self.world)
+                    p.grad.div_(self.world)
         self._works = []
+
+    def reduce_now(self):
+        """Average whatever is in `.grad` right now (gradients produced outside a hook-driven backward: PCGrad's projected
+        gradients, locally accumulated micro-batches)."""
+        self.begin()
+        self.finish()
 
     def remove(self):
         for h in self._hooks:

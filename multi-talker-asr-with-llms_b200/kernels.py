@@ -468,7 +468,7 @@ def ctc_gather_rows(w_bf16, bias, ys, ylens, Lp, blank):
     bg = torch.empty(B, Lp, device=w_bf16.device, dtype=torch.float32)
     ys_ld = ys.stride(0) if ys.numel() else 0
     check(_lib.load().mtasr_ctc_gather_rows(_p(w_bf16), _p(bias), _p(ys) if ys.numel() else None, _p(ylens), B, Lp, D, ys_ld,
-                                            blank, _p(wg), _p(bg), _stream()), "mtasr_ctc_gather_rows")
+                                            blank, w_bf16.shape[0], _p(wg), _p(bg), _stream()), "mtasr_ctc_gather_rows")
     return wg, bg
 
 
@@ -476,7 +476,7 @@ def ctc_scatter_rows(dwg, dbg, ys, ylens, blank, dw, db):
     B, Lp, D = dwg.shape
     ys_ld = ys.stride(0) if ys.numel() else 0
     check(_lib.load().mtasr_ctc_scatter_rows(_p(dwg), _p(dbg), _p(ys) if ys.numel() else None, _p(ylens), B, Lp, D, ys_ld,
-                                             blank, _p(dw), _p(db), _stream()), "mtasr_ctc_scatter_rows")
+                                             blank, dw.shape[0], _p(dw), _p(db), _stream()), "mtasr_ctc_scatter_rows")
 
 
 # ----------------------------------------------------------------------------------------------------------- misc

@@ -145,3 +145,43 @@ def test_algorithmic_flops_match_survey():
     assert abs(r["fwd"] / 1e9 - 668.9) < 1.0 and abs(r["total"] / 1e9 - 1908.4) < 2.0     # SURVEY 8d / BASELINE.md 3
     r3 = algorithmic_flops(wavlm_config("large"), 240000, 3, 896, V_LLAMA3_CTC, adapter_backward=True)
     assert r3["frames"] == 749 and abs(r3["fwd"] / 1e9 - 1221.6) < 2.0
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_spec_augment_matches_reference_golden(case):
+    """`_mask_hidden_states` (ref:models/modeling_wavlm.py:358-402) is host-side numpy RNG + a boolean scatter and
+    stays in Python in the product; from the same numpy seed it must reproduce the REFERENCE's masked tensor bit for bit
+    (fixture written by oracle/gen_golden_specaug.py running the reference's own method), in training mode with sampled
+    spans (time and feature axis), with explicit `mask_time_indices`, and be the identity in eval mode."""
+    from oracle.model_ref import make_config
+    from mtasr_b200.modeling_wavlm import WavLMModel
+    g = np.load(os.path.join(GOLDEN, "spec_augment.npz"))
+    p, ml, mm, pf, seed = g[f"{case}_cfg"].tolist()
+    cfg = make_config("tiny_large", hidden_size=32, output_hidden_size=32, intermediate_size=64, mask_time_prob=p,
+                      mask_time_length=int(ml), mask_time_min_masks=int(mm), mask_feature_prob=pf, mask_feature_length=8,
+                      mask_feature_min_masks=1)
+    model = WavLMModel(cfg)
+    with torch.no_grad():
+        model.masked_spec_embed.copy_(torch.from_numpy(g[f"{case}_embed"]))
+    h = torch.from_numpy(g[f"{case}_h"])
+    fm = torch.from_numpy(g[f"{case}_fm"])
+    h0 = h.clone()
+    model.train()
+    np.random.seed(int(seed))
+    out = model._mask_hidden_states(h, attention_mask=fm)
+    assert torch.equal(out, torch.from_numpy(g[f"{case}_out"]))
+    assert torch.equal(h, h0)                                   # the product never writes into the caller's tensor
+    masked = (out != h0).any(-1)
+    assert masked.any()
+    if pf == 0.0:
+        assert not (masked & ~fm).any()                         # time spans stay inside the valid frames
+    if f"{case}_out_given" in g.files:
+        given = torch.from_numpy(g[f"{case}_given"])
+        out_g = model._mask_hidden_states(h, mask_time_indices=given)
+        assert torch.equal(out_g, torch.from_numpy(g[f"{case}_out_given"]))
+        assert torch.equal(out_g[given], model.masked_spec_embed.detach().expand(int(given.sum()), -1))
+    model.eval()
+    assert torch.equal(model._mask_hidden_states(h, attention_mask=fm), h0)
+    cfg.apply_spec_augment = False
+    model.train()
+    assert torch.equal(model._mask_hidden_states(h, attention_mask=fm), h0)
