@@ -185,7 +185,7 @@ int mtasr_cast_f32_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
  * a_lo b_hi + a_hi b_lo + a_hi b_hi with fp32 accumulation (~2^-17 per product; small products first, because the
  * tensor core's accumulation truncates).  terms 6: three-way split x = x1 + x2 + x3, A side [a3|a2|a1|a2|a1|a1],
  * B side [b1|b2|b3|b1|b2|b1] (all products down to 2^-24). */
-int mtasr_split_bf16(const float* x, int64_t n, int32_t c, int32_t order, int32_t terms, void* y_bf16, void* stream);
+int mtasr_split_bf16(const float* x, int64_t n, int64_t c, int32_t order, int32_t terms, void* y_bf16, void* stream);
 /* P[r][v] (bf16, row stride ld) = exp(logits[r][v] - lse[r]) * rowscale[r] for v < V; logits fp16 (row stride ld, written by
  * mtasr_gemm_bf16 mode 1), ld % 8 == 0.  The dense term of d nll / d logits of the CTC head (ref:models/ctc.py:53-54).
  * colsum (V) f32, optional: column sums of P (the dense part of the bias gradient) are ACCUMULATED into it (zero it first). */
@@ -253,6 +253,26 @@ int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw, int32_t B
                    float* h_f32, float* c_all, float* gates, uint32_t* barrier, void* stream);
 int mtasr_lstm_bwd(const float* dh_out, const float* gates, const float* c_all, const void* whh_bf16, int32_t ldw,
                    int32_t B, int32_t T, int32_t Hs, void* dgates_bf16, uint32_t* barrier, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * fp32 parity mode (csrc/precise.cu; mtasr_b200.precise): the reference keeps separator, CTC head and loss in fp32
+ * (ref:models/losses.py:265-268, ref:models/ctc.py:53, ref:inference_asr.py:120).  Contractions run on the tcgen05 GEMM
+ * with split operands (mtasr_split_bf16); what is not a contraction is below.
+ *
+ * LSTM recurrence of ref:models/separator.py:6-59 in plain fp32: xg (B,T,4Hs) = x W_ih^T + b (precomputed), whh (4Hs, Hs)
+ * f32 with row stride ldw.  Forward: h_all, c_all (B,T,Hs), gates_act (B,T,4Hs) post-activation i,f,g,o.  Backward:
+ * dgates (B,T,4Hs) f32 = gradient wrt the gate pre-activations; dc_carry (B,Hs) f32 scratch.  One launch per step.
+ */
+int mtasr_lstm_fwd_f32(const float* xg, const float* whh, int32_t ldw, int32_t B, int32_t T, int32_t Hs, float* h_all,
+                       float* c_all, float* gates_act, void* stream);
+int mtasr_lstm_bwd_f32(const float* dh_out, const float* whh, int32_t ldw, int32_t B, int32_t T, int32_t Hs,
+                       const float* c_all, const float* gates_act, float* dgates, float* dc_carry, void* stream);
+/* du = dy where y > 0 else 0 (all f32, n elements). */
+int mtasr_relu_bwd_f32(const float* dy, const float* y, int64_t n, float* du, void* stream);
+/* out[r][c] = exp(logits[r][c] - lse[r]) * rowscale[r] for c < V, 0 for V <= c < ld (f32, in place allowed): the dense
+ * term of d nll / d logits of the CTC head (ref:models/ctc.py:53-54) in fp32. */
+int mtasr_softmax_scale_f32(const float* logits, const float* lse, const float* rowscale, int64_t rows, int32_t V,
+                            int64_t ld, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Feature-extractor layer 0 (hf:709-751): conv1d(1 -> C0, k, stride) on the waveform x (B,S) f32, weights (C0,1,k)

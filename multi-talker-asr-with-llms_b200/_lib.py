@@ -84,11 +84,15 @@ SIGNATURES = {
     "mtasr_conv0_fwd": (C.c_int, [_P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "mtasr_groupnorm_gelu": (C.c_int, [_P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P]),
     "mtasr_groupnorm_gelu_f32": (C.c_int, [_P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P]),
-    "mtasr_split_bf16": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P]),
+    "mtasr_split_bf16": (C.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P]),
     "mtasr_attn_softmax_fwd_split": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _I32, _P, _P]),
     "mtasr_act_bwd": (C.c_int, [_P, _I32, _P, _I32, _I64, _P, _P]),
     "mtasr_lstm_fwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "mtasr_lstm_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "mtasr_lstm_fwd_f32": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "mtasr_lstm_bwd_f32": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "mtasr_relu_bwd_f32": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "mtasr_softmax_scale_f32": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P, _P]),
     "mtasr_glu_bwd": (C.c_int, [_P, _I32, _P, _I32, _I64, _I32, _P, _P]),
 }
 

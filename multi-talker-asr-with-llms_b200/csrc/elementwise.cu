@@ -229,7 +229,7 @@ __device__ __forceinline__ void split_parts(const float (&t)[8], float (&p1)[8],
     p3[j] = r1 - p2[j];
   }
 }
-__global__ void split_bf16_kernel(const float* __restrict__ x, long long n8, int c8, int order, int terms,
+__global__ void split_bf16_kernel(const float* __restrict__ x, long long n8, long long c8, int order, int terms,
                                   __nv_bfloat16* __restrict__ y) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -237,8 +237,8 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, long long n8, int
     ld8(x, MTASR_DT_F32, i * 8, t);
     split_parts(t, p1, p2, p3);
     const long long chunk = i / c8;
-    const int off = static_cast<int>(i % c8) * 8;
-    const int cs = c8 * 8;
+    const long long off = (i % c8) * 8;
+    const long long cs = c8 * 8;
     __nv_bfloat16* o = y + chunk * (static_cast<long long>(terms) * cs) + off;
     // small products first: the tensor core adds every K=16 group into the fp32 accumulator with truncation, so the
     // error grows with (number of accumulation steps) x |accumulator|; the low-order terms are accumulated while the
@@ -934,9 +934,10 @@ extern "C" int mtasr_attn_softmax_fwd_split(const float* S, const float* gate, c
   return MTASR_OK;
 }
 
-extern "C" int mtasr_split_bf16(const float* x, int64_t n, int32_t c, int32_t order, int32_t terms, void* y_bf16, void* stream) {
+extern "C" int mtasr_split_bf16(const float* x, int64_t n, int64_t c, int32_t order, int32_t terms, void* y_bf16, void* stream) {
   MTASR_CHECK_ARG(x && y_bf16 && n > 0 && c > 0 && c % 8 == 0 && n % c == 0 && (order == 0 || order == 1) && (terms == 3 || terms == 6),
-                  "split_bf16: n=%lld must be a multiple of the chunk c=%d, c a multiple of 8, terms 3 or 6", static_cast<long long>(n), c);
+                  "split_bf16: n=%lld must be a multiple of the chunk c=%lld, c a multiple of 8, terms 3 or 6", static_cast<long long>(n),
+                  static_cast<long long>(c));
   MTASR_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y_bf16) & 15) == 0, "split_bf16: unaligned pointer");
   const long long n8 = n / 8;
   split_bf16_kernel<<<grid_for(n8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, n8, c / 8, order, terms,

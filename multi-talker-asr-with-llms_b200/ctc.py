@@ -11,6 +11,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
+from . import precise
 
 
 class CTC(torch.nn.Module):
@@ -35,7 +36,8 @@ class CTC(torch.nn.Module):
         ys_lens = torch.as_tensor(ys_lens, device=hs_pad.device)
         hlens = torch.as_tensor(hlens, device=hs_pad.device)
         Lmax = int(ys_pad.shape[1])
-        return ops.CTCHeadFn.apply(hs_pad, self.ctc_lo.weight, self.ctc_lo.bias, hlens, ys_pad[:, :Lmax].to(torch.int64),
+        fn = precise.CTCHeadF32Fn if precise.get_precision() == "fp32" else ops.CTCHeadFn
+        return fn.apply(hs_pad, self.ctc_lo.weight, self.ctc_lo.bias, hlens, ys_pad[:, :Lmax].to(torch.int64),
                                    ys_lens, self.ctc_loss.blank)
 
     def forward(self, hs_pad, hlens, ys_pad, ys_lens):
@@ -57,7 +59,11 @@ class CTC(torch.nn.Module):
 
     def argmax(self, hs_pad):
         """(B,Tmax) int64 argmax over the vocabulary, fused into the projection epilogue (no logits tensor)."""
+        if precise.get_precision() == "fp32":
+            return precise.ctc_head_argmax(hs_pad, self.ctc_lo.weight, self.ctc_lo.bias)
         return ops.ctc_head_argmax(hs_pad, self.ctc_lo.weight, self.ctc_lo.bias)
 
     def logits(self, hs_pad):
+        if precise.get_precision() == "fp32":
+            return precise.ctc_head_logits(hs_pad, self.ctc_lo.weight, self.ctc_lo.bias)
         return ops.ctc_head_logits(hs_pad, self.ctc_lo.weight, self.ctc_lo.bias)

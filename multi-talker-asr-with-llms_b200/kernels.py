@@ -235,6 +235,49 @@ def split_bf16(x: torch.Tensor, chunk: int, order: int, terms: int = 3) -> torch
     return y
 
 
+def split_rows_bf16(x: torch.Tensor, order: int, terms: int = 3) -> torch.Tensor:
+    """fp32 (R, C) -> bf16 (terms*R, C): the split parts stacked along the ROWS -- the split operand of a contraction that runs
+    over the rows (MN-major GEMM operand): order 0 = [lo; hi; hi] (A side), 1 = [hi; lo; hi] (B side)."""
+    R, Cc = x.shape
+    return split_bf16(x.reshape(1, R * Cc), R * Cc, order, terms).view(terms * R, Cc)
+
+
+def lstm_fwd_f32(xg: torch.Tensor, whh: torch.Tensor):
+    """fp32 recurrence (csrc/precise.cu): xg (B,T,4Hs) f32, whh (4Hs,Hs) f32 (row stride may exceed Hs) -> h, c, gates_act."""
+    B, T, H4 = xg.shape
+    Hs = H4 // 4
+    h = torch.empty(B, T, Hs, device=xg.device, dtype=torch.float32)
+    c = torch.empty(B, T, Hs, device=xg.device, dtype=torch.float32)
+    ga = torch.empty(B, T, H4, device=xg.device, dtype=torch.float32)
+    check(_lib.load().mtasr_lstm_fwd_f32(_p(xg), _p(whh), whh.stride(0), B, T, Hs, _p(h), _p(c), _p(ga), _stream()), "mtasr_lstm_fwd_f32")
+    return h, c, ga
+
+
+def lstm_bwd_f32(dh: torch.Tensor, whh: torch.Tensor, c: torch.Tensor, gates_act: torch.Tensor) -> torch.Tensor:
+    B, T, Hs = dh.shape
+    dh = dh.contiguous()
+    dg = torch.empty(B, T, 4 * Hs, device=dh.device, dtype=torch.float32)
+    carry = torch.empty(B, Hs, device=dh.device, dtype=torch.float32)
+    check(_lib.load().mtasr_lstm_bwd_f32(_p(dh), _p(whh), whh.stride(0), B, T, Hs, _p(c), _p(gates_act), _p(dg), _p(carry), _stream()),
+          "mtasr_lstm_bwd_f32")
+    return dg
+
+
+def relu_bwd_f32(dy: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    dy = dy.contiguous()
+    du = torch.empty_like(dy)
+    check(_lib.load().mtasr_relu_bwd_f32(_p(dy), _p(y), dy.numel(), _p(du), _stream()), "mtasr_relu_bwd_f32")
+    return du
+
+
+def softmax_scale_f32_(logits: torch.Tensor, lse: torch.Tensor, rowscale: torch.Tensor, V: int) -> torch.Tensor:
+    """In place: logits (rows, ld) f32 -> exp(logit - lse[row]) * rowscale[row] (columns >= V zeroed)."""
+    rows, ld = logits.shape
+    check(_lib.load().mtasr_softmax_scale_f32(_p(logits), _p(lse), _p(rowscale), rows, V, ld, _p(logits), _stream()),
+          "mtasr_softmax_scale_f32")
+    return logits
+
+
 def attn_softmax_fwd_split(S, gate, table, klen, B, H, T, Tp, scale, terms):
     Ps = torch.empty(B, H, T, terms * Tp, device=S.device, dtype=torch.bfloat16)
     check(_lib.load().mtasr_attn_softmax_fwd_split(_p(S), _p(gate), _p(table), _p(klen), B, H, T, Tp, scale, terms, _p(Ps), _stream()),

@@ -539,10 +539,14 @@ class PosConvFn(Function):
             xpe = torch.zeros(B * Tpad + k, D, device=dy.device, dtype=BF)
             xpe[: B * Tpad] = xp.view(B * Tpad, D)
             dwk = torch.empty(G, cg, k, cg, device=dy.device, dtype=F32)       # (g, o, tap, c)
-            for g in range(G):                                                 # batch dims are (tap) only: G launches
-                K.gemm(K.Operand(du2, D, major=1, offset=g * cg, rows=B * Tpad),
-                       K.Operand(xpe, D, major=1, sb0=D, offset=g * cg, rows=B * Tpad), cg, cg, B * Tpad,
-                       K.Out(dwk, k * cg, sb0=cg, offset=g * cg * k * cg), batch=(k, 1))
+            if (cg * 2) % 16 == 0:                                             # one launch over (tap, group)
+                K.gemm(K.Operand(du2, D, major=1, sb1=cg, rows=B * Tpad), K.Operand(xpe, D, major=1, sb0=D, sb1=cg, rows=B * Tpad),
+                       cg, cg, B * Tpad, K.Out(dwk, k * cg, sb0=cg, sb1=cg * k * cg), batch=(k, G))
+            else:                                                              # group offsets not 16-byte aligned: per group
+                for g in range(G):
+                    K.gemm(K.Operand(du2, D, major=1, offset=g * cg, rows=B * Tpad),
+                           K.Operand(xpe, D, major=1, sb0=D, offset=g * cg, rows=B * Tpad), cg, cg, B * Tpad,
+                           K.Out(dwk, k * cg, sb0=cg, offset=g * cg * k * cg), batch=(k, 1))
             dw = dwk.permute(0, 1, 3, 2).reshape(D, cg, k)
         if ctx.needs_input_grad[2]:
             db = K.colsum(du.view(B * T, D))
@@ -599,13 +603,15 @@ class LSTMLayerFn(Function):
             dW = torch.empty(4 * Hs, In + Hs, device=dh.device, dtype=F32)
             # input half: dgates^T x
             K.gemm(K.Operand(dg2, 4 * Hs, major=1), K.Operand(xb, In, major=1), 4 * Hs, In, B * T, K.Out(dW, In + Hs))
-            # recurrent half: sum_t dgates_t^T h_{t-1}  (per utterance: rows shifted by one step; accumulate over b)
-            for bi in range(B):
-                K.gemm(K.Operand(dg, 4 * Hs, major=1, offset=(bi * T + 1) * 4 * Hs, rows=T - 1),
-                       K.Operand(hb, Hs, major=1, offset=bi * T * Hs, rows=T - 1), 4 * Hs, Hs, T - 1,
-                       K.Out(dW, In + Hs, offset=In), accumulate=bi > 0) if T > 1 else None
-            if T == 1:
-                dW[:, In:] = 0
+            # recurrent half: sum_{b,t} dgates[b,t]^T h[b,t-1] as ONE contraction over all B*T rows against the hidden
+            # states shifted by one step (h[b,-1] = 0): a 28 MB copy instead of B launches of a K = T-1 GEMM each
+            # (64 launches, 2.5 ms per cfg2 step in profiles/gemm_traffic_r2_by_shape.txt)
+            hprev = torch.empty_like(hb)
+            hprev[:, 0].zero_()
+            if T > 1:
+                hprev[:, 1:].copy_(hb[:, :-1])
+            K.gemm(K.Operand(dg2, 4 * Hs, major=1), K.Operand(hprev.view(B * T, Hs), Hs, major=1), 4 * Hs, Hs, B * T,
+                   K.Out(dW, In + Hs, offset=In))
         if ctx.needs_input_grad[2]:
             db = K.colsum(dg2)
         return dx, dW, db

@@ -198,3 +198,227 @@ def adapter(mod, x: torch.Tensor):
         if i == 1:
             tap = h
     return h, tap
+
+
+# ======================================================================================================================
+# fp32-class Separator and CTC head, forward AND backward  (ref:models/separator.py:151-166, ref:models/ctc.py:129-160,
+# ref:models/losses.py:265-268: the reference keeps this part of the path in fp32 even under AMP, and decodes with fp32
+# weights, ref:inference_asr.py:120).  Every contraction -- forward, input gradient, weight gradient -- is the tcgen05 GEMM
+# on split operands: contractions over the feature dimension split along it (`_a` / `_b`), contractions over the rows (the
+# weight gradients, and x W for the input gradients) use the row-stacked split (`K.split_rows_bf16`) as MN-major operands.
+# The LSTM recurrence, the ReLU backward and the dense softmax term of the CTC gradient are plain fp32 kernels
+# (csrc/precise.cu); LayerNorm, the CTC lattice (alpha / beta) and the column sums are fp32 in the throughput path already.
+# ======================================================================================================================
+def _lin32(x2: torch.Tensor, w: torch.Tensor, b=None, act: int = K.ACT_NONE) -> torch.Tensor:
+    """(M, Kd) f32 @ (N, Kd)^T (+ b) -> (M, N) f32."""
+    M, Kd = x2.shape
+    N = w.shape[0]
+    y = torch.empty(M, N, device=x2.device, dtype=F32)
+    K.gemm(K.Operand(_a(x2), R * Kd), K.Operand(_b(w), R * Kd), M, N, R * Kd, K.Out(y, N), bias=_f(b), act=act)
+    return y
+
+
+def _dgrad32(du: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """(M, N) f32 @ (N, Kd) -> (M, Kd) f32: contraction over N = the ROWS of w (row-stacked split, MN-major B operand)."""
+    M, N = du.shape
+    Kd = w.shape[1]
+    out = torch.empty(M, Kd, device=du.device, dtype=F32)
+    K.gemm(K.Operand(_a(du), R * N), K.Operand(K.split_rows_bf16(w.detach().float().contiguous(), 1, R), Kd, major=1), M, Kd, R * N,
+           K.Out(out, Kd))
+    return out
+
+
+def _wgrad32(du: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
+    """(M, N)^T @ (M, Kd) -> (N, Kd) f32: contraction over the rows of both operands."""
+    M, N = du.shape
+    Kd = x2.shape[1]
+    out = torch.empty(N, Kd, device=du.device, dtype=F32)
+    K.gemm(K.Operand(K.split_rows_bf16(du.contiguous(), 0, R), N, major=1), K.Operand(K.split_rows_bf16(x2.contiguous(), 1, R), Kd, major=1),
+           N, Kd, R * M, K.Out(out, Kd))
+    return out
+
+
+class LinearF32Fn(torch.autograd.Function):
+    """y = act(x W^T + b) with fp32 activations and split-operand contractions; act in {none, ReLU}."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        if act not in (K.ACT_NONE, K.ACT_RELU):
+            raise NotImplementedError("mtasr_b200 fp32 mode: LinearF32Fn supports no activation or ReLU")
+        shp = x.shape
+        x2 = x.contiguous().view(-1, shp[-1]).float()
+        y = _lin32(x2, w, b, act)
+        ctx.act = act
+        ctx.has_bias = b is not None
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(x2, w, y if act == K.ACT_RELU else None)
+        return y.view(*shp[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, y = ctx.saved_tensors
+        N = w.shape[0]
+        du = dy.contiguous().view(-1, N).float()
+        if ctx.act == K.ACT_RELU:
+            du = K.relu_bwd_f32(du, y)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _dgrad32(du, w).view(*dy.shape[:-1], w.shape[1]).to(ctx.x_dtype)
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad32(du, x2)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = K.colsum(du)
+        return dx, dw, db, None
+
+
+class LSTMLayerF32Fn(torch.autograd.Function):
+    """One layer of ref:models/separator.py:27-59 in fp32: input half as one split-operand GEMM, recurrence in the fp32
+    step kernels (csrc/precise.cu), BPTT gradients wrt x, W = [W_ih | W_hh] and b."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        B, T, In = x.shape
+        Hs = W.shape[0] // 4
+        x2 = x.contiguous().view(B * T, In).float()
+        Wf = W.detach().float()
+        w_in, whh = Wf[:, :In].contiguous(), Wf[:, In:].contiguous()
+        xg = _lin32(x2, w_in, b)
+        h, c, ga = K.lstm_fwd_f32(xg.view(B, T, 4 * Hs), whh)
+        ctx.dims = (B, T, In, Hs)
+        ctx.x_dtype = x.dtype
+        ctx.save_for_backward(x2, w_in, whh, h, c, ga)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x2, w_in, whh, h, c, ga = ctx.saved_tensors
+        B, T, In, Hs = ctx.dims
+        dg2 = K.lstm_bwd_f32(dh.float(), whh, c, ga).view(B * T, 4 * Hs)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _dgrad32(dg2, w_in).view(B, T, In).to(ctx.x_dtype)
+        if ctx.needs_input_grad[1]:
+            hprev = torch.zeros_like(h)                                        # h_{t-1} next to dgates_t (data movement)
+            hprev[:, 1:] = h[:, :-1]
+            dW = torch.cat([_wgrad32(dg2, x2), _wgrad32(dg2, hprev.view(B * T, Hs))], 1)
+        if ctx.needs_input_grad[2]:
+            db = K.colsum(dg2)
+        return dx, dW, db
+
+
+def separator(mod, x: torch.Tensor):
+    """`Separator.forward` (ref:models/separator.py:151-166) in fp32-class arithmetic, differentiable."""
+    from . import ops
+    import torch.nn as nn
+    if mod.proj_activation not in ("relu", None):
+        raise NotImplementedError("mtasr_b200 fp32 mode: Separator proj_activation must be 'relu' or None")
+    act = K.ACT_RELU if mod.proj_activation == "relu" else K.ACT_NONE
+    y = LinearF32Fn.apply(x.float(), mod.pre_proj.weight, mod.pre_proj.bias, act)
+    y = ops.layer_norm(y, mod.pre_ln.weight, mod.pre_ln.bias, mod.pre_ln.eps, F32)
+    for l, cell in enumerate(mod.lstm.cells):
+        y = LSTMLayerF32Fn.apply(y, cell.W.weight, cell.W.bias)
+        if mod.lstm.norms:
+            n = mod.lstm.norms[l]
+            y = ops.layer_norm(y, n.weight, n.bias, n.eps, F32)
+        y = mod.lstm.dropout(y)
+    y = ops.layer_norm(y, mod.post_ln.weight, mod.post_ln.bias, mod.post_ln.eps, F32)
+    outs = []
+    for br in mod.sep_branches:
+        h = y
+        mods = list(br)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Linear):
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                h = LinearF32Fn.apply(h, m.weight, m.bias, K.ACT_RELU if relu else K.ACT_NONE)
+                i += 2 if relu else 1
+            elif isinstance(m, nn.Dropout):
+                h = m(h)
+                i += 1
+            elif isinstance(m, nn.LayerNorm):
+                h = ops.layer_norm(h, m.weight, m.bias, m.eps, F32)
+                i += 1
+            else:
+                raise NotImplementedError(type(m))
+        outs.append(h)
+    return outs
+
+
+def _head_operands(hs: torch.Tensor, w: torch.Tensor):
+    B, T, D = hs.shape
+    hs2 = hs.contiguous().view(B * T, D).float()
+    return hs2, _a(hs2), _b(w)                                                 # (B*T, R*D), (V, R*D)
+
+
+def _head_lse_argmax(A, Bw, bias, rows, V, D, want_lse=True, want_argmax=False):
+    nt = K.gemm_n_tiles(V)
+    part = torch.empty(rows, nt, 4, device=A.device, dtype=F32)
+    K.gemm(K.Operand(A, R * D), K.Operand(Bw, R * D), rows, V, R * D, None, bias=bias, mode=1, lse_part=part)
+    return K.lse_finalize(part, rows, nt, want_lse=want_lse, want_argmax=want_argmax)
+
+
+class CTCHeadF32Fn(torch.autograd.Function):
+    """ops.CTCHeadFn in fp32-class arithmetic: ctc_lo -> log_softmax -> CTCLoss(reduction='none', zero_infinity=True)
+    (ref:models/ctc.py:129-160, 51-65).  Forward: the vocabulary GEMM on split operands with the row log-sum-exp in its
+    epilogue (no (B,T,V) tensor), lattice columns from gathered rows of the split weight, alpha recursion.  Backward: the
+    fp32 logits ARE regenerated (rows x V fp32: this is the validation mode, not the memory-lean one), turned in place into
+    softmax * upstream, the sparse occupancy term is scattered in, and dH / dW are two split-operand GEMMs over it."""
+
+    @staticmethod
+    def forward(ctx, hs, w, bias, hlens, ys, ylens, blank):
+        B, T, D = hs.shape
+        V = w.shape[0]
+        hs2, A, Bw = _head_operands(hs, w)
+        bf = bias.detach().float()
+        lse, _ = _head_lse_argmax(A, Bw, bf, B * T, V, D)
+        Lmax = int(ys.shape[1]) if ys.numel() else 0
+        Lp = (Lmax + 1 + 63) // 64 * 64
+        ys = ys.contiguous()
+        hlens = hlens.to(torch.int64).contiguous()
+        ylens = ylens.to(torch.int64).contiguous()
+        wg, bg = K.ctc_gather_rows(Bw, bf, ys, ylens, Lp, blank)              # rows of the SPLIT weight: (B, Lp, R*D)
+        glog = torch.empty(B, T, Lp, device=hs.device, dtype=F32)
+        K.gemm(K.Operand(A, R * D, sb0=T * R * D), K.Operand(wg, R * D, sb0=Lp * R * D), T, Lp, R * D, K.Out(glog, Lp, sb0=T * Lp),
+               batch=(B, 1), bias=bg, bias_sb0=Lp)
+        lse = lse.view(B, T)
+        nll, nll_raw, alpha, coff = K.ctc_alpha_fwd(glog, lse, ys, hlens, ylens, Lmax)
+        ctx.dims = (B, T, D, V, Lp, Lmax, blank)
+        ctx.hs_dtype = hs.dtype
+        ctx.save_for_backward(hs2, w, bf, glog, lse, alpha, coff, nll_raw, hlens, ys, ylens)
+        return nll
+
+    @staticmethod
+    def backward(ctx, gout):
+        hs2, w, bf, glog, lse, alpha, coff, nll_raw, hlens, ys, ylens = ctx.saved_tensors
+        B, T, D, V, Lp, Lmax, blank = ctx.dims
+        dG, rowscale = K.ctc_beta_bwd(glog, lse, ys, hlens, ylens, Lmax, alpha, coff, nll_raw, gout.contiguous().float())
+        Vp = (V + 7) // 8 * 8
+        rows = B * T
+        dl = torch.empty(rows, Vp, device=hs2.device, dtype=F32)
+        K.gemm(K.Operand(_a(hs2), R * D), K.Operand(_b(w), R * D), rows, V, R * D, K.Out(dl, Vp), bias=bf)
+        K.softmax_scale_f32_(dl, lse.view(-1), rowscale.view(-1), V)          # dense term, columns >= V zeroed
+        K.ctc_scatter_cols(dG, ys, ylens, dl.view(B, T, Vp), blank)           # + sparse occupancy term (fp32 atomics)
+        dh = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wpad = w.detach().float()
+            if Vp != V:
+                wpad = torch.cat([wpad, wpad.new_zeros(Vp - V, D)], 0)
+            dh = _dgrad32(dl, wpad).view(B, T, D).to(ctx.hs_dtype)
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad32(dl, hs2)[:V]
+        if ctx.needs_input_grad[2]:
+            db = K.colsum(dl)[:V].contiguous()
+        return dh, dw, db, None, None, None, None
+
+
+def ctc_head_argmax(hs: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """argmax_v (hs W^T + b) at fp32-class accuracy, first maximal index on ties (ref:models/ctc.py:182-190)."""
+    B, T, D = hs.shape
+    _, A, Bw = _head_operands(hs, w)
+    _, am = _head_lse_argmax(A, Bw, bias.detach().float(), B * T, w.shape[0], D, want_lse=False, want_argmax=True)
+    return am.view(B, T)
+
+
+def ctc_head_logits(hs: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    return LinearF32Fn.apply(hs, w, bias, K.ACT_NONE)

@@ -13,6 +13,7 @@ import torch.nn.functional as F
 
 from . import kernels as K
 from . import ops
+from . import precise
 
 BF, F32 = torch.bfloat16, torch.float32
 
@@ -111,6 +112,8 @@ class Separator(nn.Module):
         return h
 
     def forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+        if precise.get_precision() == "fp32":      # fp32-class validation mode (forward + backward), see precise.py
+            return precise.separator(self, x)
         act = {"relu": K.ACT_RELU, "gelu": K.ACT_GELU, None: K.ACT_NONE}[self.proj_activation]
         y = ops.linear(x, self.pre_proj.weight, self.pre_proj.bias, act=act, out_dtype=F32)
         y = ops.layer_norm(y, self.pre_ln.weight, self.pre_ln.bias, self.pre_ln.eps, BF)
