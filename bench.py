@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--profile-run", action="store_true", help="ncu helper: 1 warm-up + 1 step, no e2e/roofline/cpu legs")
     ap.add_argument("--config", default=None, choices=sorted(PRESETS),
                     help="BASELINE.json configuration preset (sets --speakers/--seconds/--batch/--mode); default = cfg2, the headline")
+    ap.add_argument("--dropout", type=float, default=0.0,
+                    help="encoder hidden / activation / attention dropout rate; > 0 runs the step in train() mode the way the "
+                         "reference trains (0.1 each, separator LSTM dropout 0.2); the headline is quoted at 0 (eval mode, both arms)")
     ap.add_argument("--no-stock-gpu", action="store_true", help="skip the stock-PyTorch-on-GPU leg (oracle modules on the same GPU)")
     a = ap.parse_args()
     if a.config:
@@ -313,7 +316,8 @@ def workload_config(args, batch, world):
     return {"workload": workload_name(args),
             "encoder": "wavlm-large-shaped (24L, D=1024, H=16, F=4096), random init", "speakers": args.speakers,
             "seconds": args.seconds, "batch_per_gpu": batch, "global_batch": batch * world, "vocab": 128259,
-            "separator_hidden": 896, "parallelism": f"dp{world}", "spec_augment": "off", "dropout": 0.0,
+            "separator_hidden": 896, "parallelism": f"dp{world}", "spec_augment": "off", "dropout": getattr(args, "dropout", 0.0),
+            "module_mode": "train()" if getattr(args, "dropout", 0.0) > 0 and args.mode == "train" else "eval() (dropout inactive in both arms)",
             "l2": "working set per step (>1 GB of weights, >20 GB of activations) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -347,14 +351,19 @@ def main_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(1234)
-    cfg = wavlm_config("large", **({"num_hidden_layers": args.layers} if args.layers else {}))
+    over = {"num_hidden_layers": args.layers} if args.layers else {}
+    if args.dropout > 0:
+        over.update(hidden_dropout=args.dropout, activation_dropout=args.dropout, attention_dropout=args.dropout)
+    cfg = wavlm_config("large", **over)
     S = int(args.seconds * 16000)
     B = args.batch
     model = SerializedCTCPath(cfg, talker_numbers=args.speakers, separator_hidden=896, vocab_size=V_LLAMA3_CTC - 1).to(dev)
     model.encoder.freeze_feature_encoder()
     for p in model.encoder.adapter.parameters():       # the serialized-CTC loss does not depend on the adapter branch
         p.requires_grad_(False)
-    model.eval()      # dropout 0 / SpecAugment off (RNG streams of the reference are not reproducible); gradients still flow
+    model.eval()      # headline: dropout 0 / SpecAugment off in BOTH arms (eval-mode step; gradients still flow)
+    if args.dropout > 0 and args.mode == "train":
+        model.train()  # fused Philox-free counter-based dropout in the GEMM epilogues / attention kernels, LSTM dropout 0.2
     n_train = sum(p.numel() for p in model.parameters() if p.requires_grad)
     net = model
     # Data parallel: one process per GPU, the only collective is the gradient all-reduce (mean).  Default: the in-place

@@ -107,6 +107,13 @@ typedef struct mtasr_gemm_desc {
   const float* row_vec;
   const float* row_scale;
   float* lse_part;
+  /* fused dropout (mode 0 only; hf:291,294,323,364): drop_seed = two u32 words in device memory (NULL = off), element index
+   * (b*M + m) * drop_ld + n with drop_ld = N rounded up to even, keep probability drop_keep16 / 65536.  Applied to v after
+   * bias / activation and BEFORE the residual add (forward sites); with act 3 / 4 the same mask multiplies the gradient
+   * (backward of an activation-dropout site: v *= mask * gelu'(residual)).  See mtasr_dropout for the generator. */
+  const void* drop_seed;
+  uint32_t drop_site;
+  uint32_t drop_keep16;
 } mtasr_gemm_desc;
 
 int mtasr_gemm_bf16(const mtasr_gemm_desc* desc, void* stream);
@@ -178,6 +185,12 @@ int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t
                         const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D, float* dx_f32,
                         void* dx_bf16, float* dgamma, float* dbeta, void* stream);
 int mtasr_cast_f32_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* Dropout as a stand-alone pass: y[r][c] = x[r][c] * mask(seed, site, r * ld_even + c) * 65536 / keep16 for r < rows,
+ * c < cols (contiguous rows; ld_even = cols rounded up to even), x f32 or bf16 -> y f32 or bf16.  seed: two u32 words in
+ * device memory drawn from torch's CUDA generator; the mask is a pure function of (seed, site, index): forward, backward and
+ * checkpoint replays regenerate it.  Same generator as the fused GEMM / attention sites. */
+int mtasr_dropout(const void* x, int32_t x_dtype, int64_t rows, int64_t cols, const void* seed, uint32_t site, uint32_t keep16,
+                  void* y, int32_t y_dtype, void* stream);
 /* fp32-accurate GEMM mode (north_star tolerance "<= 1e-4 in fp32"; the reference's fp32 run is torch fp32 matmul,
  * ref:models/modeling_wavlm.py:412-465 outside autocast).  x (n fp32 values, rows of chunks of c values, c % 8 == 0)
  * -> y (terms*n bf16).  terms 3: every chunk becomes [lo | hi | hi] (order 0, A-side operand) or [hi | lo | hi]
@@ -226,13 +239,18 @@ int mtasr_attn_softmax_bwd(const void* P_bf16, const float* dP, const float* gat
  * out (B*T, H*64) bf16 = softmax_k(q.k*scale + gate*table[k-q+T-1]) v ; lse (B,H,T) f32 row log-sum-exp (for the backward).
  * S / P tiles never leave TMEM / shared memory. */
 int mtasr_attn_fwd(const void* qkv_bf16, const float* gate, const float* table, const int32_t* klen, int32_t B, int32_t H,
-                   int32_t T, float scale, void* out_bf16, float* lse, void* stream);
+                   int32_t T, float scale, void* out_bf16, float* lse, const void* drop_seed, uint32_t drop_site,
+                   uint32_t drop_keep16, void* stream);
 /* Fused attention backward.  out / dout (B*T, H*64) bf16 are the forward output and its gradient; lse from the forward.
  * Writes dqkv (B*T, 3*H*64) bf16 = [dq | dk | dv].  dq32 (B*T, H*64) f32, dgate (B,H,T) f32 and dtable (H,2T-1) f32 are
  * ACCUMULATED (zero them first); delta (B,H,T) f32 is scratch. */
 int mtasr_attn_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse, const float* gate,
                    const float* table, const int32_t* klen, int32_t B, int32_t H, int32_t T, float scale, void* dqkv_bf16,
-                   float* dq32, float* delta, float* dgate, float* dtable, void* stream);
+                   float* dq32, float* delta, float* dgate, float* dtable, const void* drop_seed, uint32_t drop_site,
+                   uint32_t drop_keep16, void* stream);
+/* drop_seed (two u32 words in device memory, NULL = off) / drop_site / drop_keep16: dropout on the attention PROBABILITIES
+ * (hf:217, attention_dropout): O = (softmax o mask / keep) V, mask index ((b*H + h)*T + q) * ld_even(T) + k, same generator
+ * as mtasr_dropout; the backward must receive the forward's triple. */
 /* y (B,Tpad,D) bf16 = zero-pad(x (B,T,D), pad_l rows left), rows t >= vlen[b] zeroed when vlen != NULL. */
 int mtasr_pad_cast(const void* x, int32_t x_dtype, int32_t B, int32_t T, int32_t D, int32_t pad_l, int32_t Tpad,
                    const int32_t* vlen, void* y_bf16, void* stream);

@@ -40,6 +40,9 @@ class GemmDesc(C.Structure):
         ("row_vec", C.c_void_p),
         ("row_scale", C.c_void_p),
         ("lse_part", C.c_void_p),
+        ("drop_seed", C.c_void_p),
+        ("drop_site", C.c_uint32),
+        ("drop_keep16", C.c_uint32),
     ]
 
 
@@ -75,8 +78,8 @@ SIGNATURES = {
     "mtasr_colsum": (C.c_int, [_P, _I32, _I64, _I32, _I64, _P, _P]),
     "mtasr_relpos_gate_fwd": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
     "mtasr_relpos_gate_bwd": (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
-    "mtasr_attn_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P]),
-    "mtasr_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P, _P]),
+    "mtasr_attn_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P, C.c_uint32, C.c_uint32, _P]),
+    "mtasr_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P, _P, C.c_uint32, C.c_uint32, _P]),
     "mtasr_attn_softmax_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P, _P]),
     "mtasr_attn_softmax_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P, _P, _P, _P]),
     "mtasr_pad_cast": (C.c_int, [_P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
@@ -84,6 +87,7 @@ SIGNATURES = {
     "mtasr_conv0_fwd": (C.c_int, [_P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "mtasr_groupnorm_gelu": (C.c_int, [_P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P]),
     "mtasr_groupnorm_gelu_f32": (C.c_int, [_P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "mtasr_dropout": (C.c_int, [_P, _I32, _I64, _I64, _P, C.c_uint32, C.c_uint32, _P, _I32, _P]),
     "mtasr_split_bf16": (C.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P]),
     "mtasr_attn_softmax_fwd_split": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _I32, _P, _P]),
     "mtasr_act_bwd": (C.c_int, [_P, _I32, _P, _I32, _I64, _P, _P]),

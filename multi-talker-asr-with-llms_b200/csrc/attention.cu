@@ -41,7 +41,20 @@ struct AttnFwdP {
   const int* klen;                // (B) or null
   __nv_bfloat16* out;             // (B*T, H*64)
   float* lse;                     // (B,H,T) natural-log row LSE of the biased scores (saved for the backward)
+  DropP drop;                     // dropout on the attention probabilities (hf:217); index ((b*H + h)*T + q) * drop.ld + k
 };
+
+// Dropout multipliers (0 or 1/keep) of the n consecutive keys kb .. kb+n-1 (kb even, n a multiple of 2) of probability row `row`.
+template <int N>
+__device__ __forceinline__ void attn_drop_mults(uint32_t s0, uint32_t s1, const DropP& d, unsigned long long row, int kb, float (&m)[N]) {
+  const unsigned long long pair0 = (row * static_cast<unsigned long long>(d.ld) + static_cast<unsigned long long>(kb)) >> 1;
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) {
+    const uint32_t h = drop_hash(s0, s1, d.site, pair0 + j);
+    m[2 * j] = (h & 0xffffu) < d.thresh ? d.scale : 0.f;
+    m[2 * j + 1] = (h >> 16) < d.thresh ? d.scale : 0.f;
+  }
+}
 
 // K-major SW128 operand tile [rows][64] bf16: UMMA_K step ks (16 elements) starts 32 bytes further in the swizzle row.
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t base, int ks) { return make_smem_desc(base + ks * 32, 16, 1024); }
@@ -58,6 +71,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -195,6 +209,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
     const int r = wq * 32 + lane;
     const int st = threadIdx.x - 128;              // 0..511 over the four groups
     uint32_t sph = 0, pph = 0, oph = 0;            // phases of this group's S / P buffer and of the O accumulator
+    uint32_t drop_s0 = 0, drop_s1 = 0;
+    if (DROP) { drop_s0 = __ldg(p.drop.seed); drop_s1 = __ldg(p.drop.seed + 1); }
     int cur_h = -1;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int qt = item % p.nq, h = (item / p.nq) % p.H, b = item / (p.nq * p.H);
@@ -281,6 +297,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
           }
 #pragma unroll
           for (int i = 0; i < 32; ++i) l += e[i];
+          if (DROP) {   // the row sum (softmax denominator) is over the UNDROPPED probabilities; P V uses the dropped ones
+            float dm[32];
+            attn_drop_mults<32>(drop_s0, drop_s1, p.drop, (static_cast<unsigned long long>(b) * p.H + h) * p.T + qc, kb, dm);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) e[i] *= dm[i];
+          }
 #pragma unroll
           for (int g16 = 0; g16 < 4; ++g16) {
             uint4 u;
@@ -340,6 +362,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
 // its own tile-local row maximum m_j, so there is neither the max-only first pass of attn_fwd_kernel (a second QK^T per
 // tile and twice the MMA <-> softmax hand-offs, which is what that kernel's time is made of) nor an online rescale of a
 // running accumulator.  The epilogue combines exactly:  O = sum_j 2^(m_j - m) O_j / l,  l = sum_j 2^(m_j - m) l_j.
+template <bool DROP>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -471,6 +494,8 @@ attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP 
     const int r = wq * 32 + lane;
     const int st = threadIdx.x - 128;              // 0..511
     uint32_t sph = 0, pph = 0, oph = 0;
+    uint32_t drop_s0 = 0, drop_s1 = 0;
+    if (DROP) { drop_s0 = __ldg(p.drop.seed); drop_s1 = __ldg(p.drop.seed + 1); }
     int xset = 0;                                  // exchange-slot set, alternating per tile of this buffer
     int cur_h = -1;
     int ipar = 0;                                  // item parity: the combine arrays are double-buffered, so the only
@@ -550,6 +575,12 @@ attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP 
           for (int i = 0; i < 32; ++i) e[i] = ex2_approx(__uint_as_float(cur[i]) - mm);   // exp2(-inf) = 0 for masked keys
 #pragma unroll
           for (int i = 0; i < 32; ++i) lh += e[i];
+          if (DROP) {   // denominator over the undropped probabilities, P V over the dropped ones
+            float dm[32];
+            attn_drop_mults<32>(drop_s0, drop_s1, p.drop, (static_cast<unsigned long long>(b) * p.H + h) * p.T + qc, k0 + c * 32, dm);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) e[i] *= dm[i];
+          }
 #pragma unroll
           for (int g16 = 0; g16 < 4; ++g16) {
             uint4 u;
@@ -651,6 +682,7 @@ struct AttnBwdP {
   float* dq32;             // (B*T, H*64) fp32, zero-initialised, receives dQ partial sums
   float* dgate;            // (B,H,T) zero-initialised (atomics)
   float* dtable;           // (H,2T-1) zero-initialised (atomics)
+  DropP drop;              // dropout on the attention probabilities: must be the forward's (seed, site, keep)
   int dbg;                 // timing experiments only (MTASR_ATTN_DBG): 1 skip table-gradient diagonals, 2 skip dQ reductions, 4 skip softmax math
 };
 
@@ -658,6 +690,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(ATB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do, const AttnBwdP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -801,6 +834,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     uint32_t sdp_ph = 0, pe_ph = 0, dse_ph[2] = {0, 0}, dkv_ph = 0;
     int db = 0;
     int cur_h = -1;
+    uint32_t drop_s0 = 0, drop_s1 = 0;
+    if (DROP) { drop_s0 = __ldg(p.drop.seed); drop_s1 = __ldg(p.drop.seed + 1); }
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int jt = item % p.nk, h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
       named_bar_sync(1, 256);
@@ -859,6 +894,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           }
           const int kb = k0 + c * 16;
           float pe[16], de[16];
+          // dropout on the probabilities: O = (P o M) V with M = mask / keep, so dP = M o (dO V^T), the P^T dO contraction of dV
+          // takes P o M, and delta = rowsum(dO o O) is unchanged
+          float dm[16];
+          if (DROP) attn_drop_mults<16>(drop_s0, drop_s1, p.drop, static_cast<unsigned long long>(bh) * p.T + qc, kb, dm);
           if (p.dbg & 4) {   // timing experiment: no per-element math
 #pragma unroll
             for (int e = 0; e < 16; ++e) { pe[e] = __uint_as_float(sv[e]); de[e] = __uint_as_float(dv[e]); }
@@ -867,9 +906,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
             for (int e = 0; e < 16; ++e) {
               const float t = trel[kb + e];
               const float pv = ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, fmaf(g, t, nlse2)));
-              const float dz = pv * (__uint_as_float(dv[e]) - delta);
+              const float dpv = DROP ? __uint_as_float(dv[e]) * dm[e] : __uint_as_float(dv[e]);
+              const float dz = pv * (dpv - delta);
               dg = fmaf(dz, t, dg);
-              pe[e] = pv;
+              pe[e] = DROP ? pv * dm[e] : pv;
               de[e] = dz * p.scale;
             }
           } else {
@@ -879,9 +919,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
               // masked keys may index past the 2T-1 table entries (uninitialised shared memory): 0 * NaN would poison dg
               const float t = ok ? trel[kb + e] : 0.f;
               const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, fmaf(g, t, nlse2))) : 0.f;
-              const float dz = pv * (__uint_as_float(dv[e]) - delta);
+              const float dpv = DROP ? __uint_as_float(dv[e]) * dm[e] : __uint_as_float(dv[e]);
+              const float dz = pv * (dpv - delta);
               dg = fmaf(dz, t, dg);
-              pe[e] = pv;
+              pe[e] = DROP ? pv * dm[e] : pv;
               de[e] = dz * p.scale;
             }
           }
@@ -1112,8 +1153,23 @@ static int encode_heads_map(CUtensorMap* map, const void* base, int B, int T, in
 
 using namespace mtasr;
 
+static int attn_drop_params(DropP* d, const void* seed, uint32_t site, uint32_t keep16, int T) {
+  d->seed = nullptr;
+  d->site = site;
+  d->thresh = 65536;
+  d->scale = 1.f;
+  d->ld = (static_cast<long long>(T) + 1) & ~1LL;
+  if (seed == nullptr || keep16 >= 65536) return 0;
+  if (keep16 == 0) return set_error(MTASR_ERR_INVALID_ARG, "attention: dropout keep16 must be in (0, 65536]");
+  d->seed = reinterpret_cast<const uint32_t*>(seed);
+  d->thresh = keep16;
+  d->scale = 65536.0f / static_cast<float>(keep16);
+  return 0;
+}
+
 extern "C" int mtasr_attn_fwd(const void* qkv, const float* gate, const float* table, const int32_t* klen, int32_t B, int32_t H,
-                              int32_t T, float scale, void* out, float* lse, void* stream) {
+                              int32_t T, float scale, void* out, float* lse, const void* drop_seed, uint32_t drop_site,
+                              uint32_t drop_keep16, void* stream) {
   MTASR_CHECK_ARG(qkv && gate && table && out && lse && B > 0 && H > 0 && T > 0, "attn_fwd: bad arguments");
   MTASR_CHECK_ARG(T <= 8192, "attn_fwd: T=%d too long for the shared-memory bias table", T);
   CUtensorMap map;
@@ -1127,22 +1183,26 @@ extern "C" int mtasr_attn_fwd(const void* qkv, const float* gate, const float* t
   p.gate = gate; p.table = table; p.klen = klen;
   p.out = reinterpret_cast<__nv_bfloat16*>(out);
   p.lse = lse;
+  if (int rc = attn_drop_params(&p.drop, drop_seed, drop_site, drop_keep16, T)) return rc;
+  const bool drop = p.drop.seed != nullptr;
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
   if (p.nk <= 4 && getenv("MTASR_ATTN_TWO_PASS") == nullptr) {
     // T <= 512: one O accumulator per key tile, no max-only pass (attn_fwd_sp_kernel)
     const int smem = 2 * AT_TILE + AT_KV_SLOTS * AT_TILE + 2 * AT_P_BYTES + attn_table_bytes(T) + (1024 + 1024 + 2048) * 4 + 256;
-    if (cudaFuncSetAttribute(attn_fwd_sp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+    auto kern = drop ? attn_fwd_sp_kernel<true> : attn_fwd_sp_kernel<false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return set_error(MTASR_ERR_LAUNCH, "attn_fwd: cannot set the shared-memory attribute");
-    attn_fwd_sp_kernel<<<grid, AT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map, p);
+    kern<<<grid, AT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map, p);
     MTASR_COUNT_LAUNCH();
     MTASR_CHECK_LAUNCH("attn_fwd");
     return MTASR_OK;
   }
   const int smem = AT_TILE + AT_KV_SLOTS * AT_TILE + 2 * AT_P_BYTES + attn_table_bytes(T) + 2048 + 256;
   MTASR_CHECK_ARG(smem <= 232448, "attn_fwd: T=%d needs %d bytes of shared memory", T, smem);
-  if (cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+  auto kern2 = drop ? attn_fwd_kernel<true> : attn_fwd_kernel<false>;
+  if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return set_error(MTASR_ERR_LAUNCH, "attn_fwd: cannot set the shared-memory attribute");
-  attn_fwd_kernel<<<grid, AT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map, p);
+  kern2<<<grid, AT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map, p);
   MTASR_COUNT_LAUNCH();
   MTASR_CHECK_LAUNCH("attn_fwd");
   return MTASR_OK;
@@ -1150,7 +1210,8 @@ extern "C" int mtasr_attn_fwd(const void* qkv, const float* gate, const float* t
 
 extern "C" int mtasr_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, const float* gate,
                               const float* table, const int32_t* klen, int32_t B, int32_t H, int32_t T, float scale, void* dqkv,
-                              float* dq32, float* delta, float* dgate, float* dtable, void* stream) {
+                              float* dq32, float* delta, float* dgate, float* dtable, const void* drop_seed, uint32_t drop_site,
+                              uint32_t drop_keep16, void* stream) {
   MTASR_CHECK_ARG(qkv && out && dout && lse && gate && table && dqkv && dq32 && delta && dgate && dtable && B > 0 && H > 0 && T > 0,
                   "attn_bwd: bad arguments");
   MTASR_CHECK_ARG(T <= 4096, "attn_bwd: T=%d too long for the shared-memory bias tables", T);
@@ -1175,12 +1236,14 @@ extern "C" int mtasr_attn_bwd(const void* qkv, const void* out, const void* dout
   p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   p.dq32 = dq32; p.dgate = dgate; p.dtable = dtable;
   p.dbg = getenv("MTASR_ATTN_DBG") ? atoi(getenv("MTASR_ATTN_DBG")) : 0;
+  if (int rc = attn_drop_params(&p.drop, drop_seed, drop_site, drop_keep16, T)) return rc;
   const int smem = 6 * AT_TILE + 3 * AT_P_BYTES + 2 * attn_table_bytes(T) + 256 * 4 + 256;
   MTASR_CHECK_ARG(smem <= 232448, "attn_bwd: T=%d needs %d bytes of shared memory", T, smem);
-  if (cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+  auto kern = p.drop.seed != nullptr ? attn_bwd_kernel<true> : attn_bwd_kernel<false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return set_error(MTASR_ERR_LAUNCH, "attn_bwd: cannot set the shared-memory attribute");
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
-  attn_bwd_kernel<<<grid, ATB_THREADS, smem, st>>>(mq, mdo, p);
+  kern<<<grid, ATB_THREADS, smem, st>>>(mq, mdo, p);
   MTASR_COUNT_LAUNCH();
   // dQ scratch (fp32) -> q block of dqkv (bf16)
   const long long rows = static_cast<long long>(B) * T;

@@ -99,6 +99,45 @@ __device__ __forceinline__ float gelu_grad_fast_f(float x) {
 }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// ---- dropout: counter-based, stateless RNG (hf:291,294,323,364,483 hidden / activation dropout; hf:217 attention dropout).
+// The keep decision of element `idx` of dropout site `site` is a pure function of (seed[0], seed[1], site, idx): the forward,
+// the backward and a gradient-checkpoint replay regenerate identical masks without storing them.  `seed` is two 32-bit words
+// in DEVICE memory drawn by a torch op from torch's CUDA generator (no host sync; torch.manual_seed reproduces a run).
+// One 32-bit hash (multiplicative mix + lowbias32 finaliser) yields the decisions of TWO neighbouring elements (16 bits
+// each): keep iff u16 < thresh, thresh = round((1 - p) * 65536); kept values are scaled by 65536 / thresh (exactly unbiased
+// for the quantised keep probability).
+struct DropP {
+  const uint32_t* seed;   // nullptr = no dropout
+  uint32_t site;
+  uint32_t thresh;
+  float scale;
+  long long ld;           // row pitch of the index space (even): idx = row * ld + col
+};
+__device__ __forceinline__ uint32_t drop_hash(uint32_t s0, uint32_t s1, uint32_t site, unsigned long long pair) {
+  const uint32_t lo = static_cast<uint32_t>(pair), hi = static_cast<uint32_t>(pair >> 32);
+  uint32_t h = (lo * 0x9E3779B1u) ^ s0;
+  h ^= ((hi + site * 0x85EBCA77u) * 0xC2B2AE3Du) + s1;
+  h ^= h >> 16; h *= 0x7feb352du;
+  h ^= h >> 15; h *= 0x846ca68bu;
+  h ^= h >> 16;
+  return h;
+}
+// multiplier (0 or scale) of element idx
+__device__ __forceinline__ float drop_mult(uint32_t s0, uint32_t s1, const DropP& d, unsigned long long idx) {
+  const uint32_t h = drop_hash(s0, s1, d.site, idx >> 1);
+  const uint32_t u = (idx & 1ull) ? (h >> 16) : (h & 0xffffu);
+  return u < d.thresh ? d.scale : 0.f;
+}
+// multipliers of the 8 consecutive elements idx .. idx+7, idx even: 4 hashes
+__device__ __forceinline__ void drop_mult8(uint32_t s0, uint32_t s1, const DropP& d, unsigned long long idx, float (&m)[8]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t h = drop_hash(s0, s1, d.site, (idx >> 1) + j);
+    m[2 * j] = (h & 0xffffu) < d.thresh ? d.scale : 0.f;
+    m[2 * j + 1] = (h >> 16) < d.thresh ? d.scale : 0.f;
+  }
+}
+
 // log(exp(a)+exp(b)) that tolerates -inf on either side.
 __device__ __forceinline__ float logaddexp_f(float a, float b) {
   const float m = fmaxf(a, b);

@@ -229,6 +229,20 @@ __device__ __forceinline__ void split_parts(const float (&t)[8], float (&p1)[8],
     p3[j] = r1 - p2[j];
   }
 }
+// stand-alone dropout pass (one thread per element; the fused sites live in the GEMM / attention kernels)
+__global__ void dropout_kernel(const void* __restrict__ x, int x_dtype, long long rows, long long cols, DropP d, void* __restrict__ y,
+                               int y_dtype) {
+  const uint32_t s0 = __ldg(d.seed), s1 = __ldg(d.seed + 1);
+  const long long n = rows * cols;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    const float v = x_dtype == MTASR_DT_F32 ? reinterpret_cast<const float*>(x)[i] : bf2f(reinterpret_cast<const __nv_bfloat16*>(x)[i]);
+    const float o = v * drop_mult(s0, s1, d, static_cast<unsigned long long>(r) * d.ld + c);
+    if (y_dtype == MTASR_DT_F32) reinterpret_cast<float*>(y)[i] = o;
+    else reinterpret_cast<__nv_bfloat16*>(y)[i] = f2bf(o);
+  }
+}
+
 __global__ void split_bf16_kernel(const float* __restrict__ x, long long n8, long long c8, int order, int terms,
                                   __nv_bfloat16* __restrict__ y) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
@@ -931,6 +945,25 @@ extern "C" int mtasr_attn_softmax_fwd_split(const float* S, const float* gate, c
       S, gate, table, klen, B, H, T, Tp, scale, reinterpret_cast<__nv_bfloat16*>(Ps), terms);
   MTASR_COUNT_LAUNCH();
   MTASR_CHECK_LAUNCH("attn_softmax_fwd_split");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_dropout(const void* x, int32_t x_dtype, int64_t rows, int64_t cols, const void* seed, uint32_t site,
+                             uint32_t keep16, void* y, int32_t y_dtype, void* stream) {
+  MTASR_CHECK_ARG(x && y && seed && rows > 0 && cols > 0, "dropout: bad arguments");
+  MTASR_CHECK_ARG(keep16 > 0 && keep16 <= 65536, "dropout: keep16 must be in (0, 65536]");
+  MTASR_CHECK_ARG((x_dtype == MTASR_DT_F32 || x_dtype == MTASR_DT_BF16) && (y_dtype == MTASR_DT_F32 || y_dtype == MTASR_DT_BF16),
+                  "dropout: dtypes must be f32 / bf16");
+  DropP d;
+  d.seed = reinterpret_cast<const uint32_t*>(seed);
+  d.site = site;
+  d.thresh = keep16;
+  d.scale = 65536.0f / static_cast<float>(keep16);
+  d.ld = (cols + 1) & ~1LL;
+  const long long n = rows * cols;
+  dropout_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, x_dtype, rows, cols, d, y, y_dtype);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("dropout");
   return MTASR_OK;
 }
 

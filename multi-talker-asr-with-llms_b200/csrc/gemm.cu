@@ -68,6 +68,7 @@ struct GemmKP {
   const float* row_vec;
   const float* row_scale;
   float4* lse_part;
+  DropP drop;                          // fused dropout (seed == nullptr: off)
 };
 
 __device__ __forceinline__ void load8(const void* base, int dtype, long long idx, int nv, float (&o)[8]) {
@@ -315,6 +316,11 @@ __device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMa
   }
 
   const float nrv = -rvec * 1.4426950408889634f;
+  uint32_t drop_s0 = 0, drop_s1 = 0;
+  if (p.drop.seed != nullptr) {
+    drop_s0 = __ldg(p.drop.seed);
+    drop_s1 = __ldg(p.drop.seed + 1);
+  }
 #pragma unroll
   for (int c8 = 0; c8 < GW / 8; ++c8) {
     if (mode == 1) break;
@@ -348,6 +354,15 @@ __device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMa
       } else if (act == 2) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.drop.seed != nullptr) {
+        // dropout of this GEMM's output (after bias / activation, before the residual add); for the backward forms (act 3 /
+        // 4) the same factor multiplies the gradient next to the activation derivative
+        float dm[8];
+        const unsigned long long grow = static_cast<unsigned long long>(t.b1) * p.batch0 + t.b0;
+        drop_mult8(drop_s0, drop_s1, p.drop, (grow * p.M + row0 + lane) * p.drop.ld + col, dm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= dm[j];
       }
       if (has_res) {
         float rr[8];
@@ -809,6 +824,15 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   p.act = d->act; p.alpha = d->alpha; p.accumulate = d->accumulate; p.mode = d->mode;
   p.row_vec = d->row_vec; p.row_scale = d->row_scale;
   p.lse_part = reinterpret_cast<float4*>(d->lse_part);
+  p.drop.seed = nullptr;
+  if (d->drop_seed != nullptr) {
+    MTASR_CHECK_ARG(d->mode == 0 && d->drop_keep16 > 0 && d->drop_keep16 <= 65536, "gemm: fused dropout needs mode 0 and keep16 in (0, 65536]");
+    p.drop.seed = reinterpret_cast<const uint32_t*>(d->drop_seed);
+    p.drop.site = d->drop_site;
+    p.drop.thresh = d->drop_keep16;
+    p.drop.scale = 65536.0f / static_cast<float>(d->drop_keep16);
+    p.drop.ld = (static_cast<long long>(d->N) + 1) & ~1LL;
+  }
 
   CUtensorMap ma, mb;
   const uint64_t nb0a = p.a_use0 ? d->batch0 : 1, nb1a = p.a_use1 ? d->batch1 : 1;
@@ -889,7 +913,8 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   // contractions with small M x N) is cut along K; partial tiles are summed by TMA reduce-add into a zeroed C.
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (p.tma_epi && d->mode == 0 && d->act == 0 && !d->aux && !d->residual && !d->bias && d->c_dtype == MTASR_DT_F32 &&
-      d->batch0 == 1 && d->batch1 == 1 && d->alpha == 1.0f && p.num_kb >= 16 && getenv("MTASR_GEMM_NO_SPLITK") == nullptr) {
+      d->batch0 == 1 && d->batch1 == 1 && d->alpha == 1.0f && p.num_kb >= 16 && d->drop_seed == nullptr &&
+      getenv("MTASR_GEMM_NO_SPLITK") == nullptr) {
     // choose the split that best fills whole waves of SMs (wave quantisation: e.g. 500 tiles on 148 SMs run as 4 waves at
     // 84 % occupancy, 2 x 500 half-K items as 7 waves at 97 %), keeping >= 32 k-blocks (K >= 2048) per item
     const int sms = num_units(ncta);   // schedulable units: CTAs or CTA pairs

@@ -97,7 +97,7 @@ def gemm(a: Operand, b: Operand, M: int, N: int, K: int, out: Optional[Out], *, 
          bias: Optional[torch.Tensor] = None, bias_sb0: int = 0, act: int = ACT_NONE, residual: Optional[Out] = None,
          aux: Optional[torch.Tensor] = None, alpha: float = 1.0, accumulate: bool = False, mode: int = 0,
          row_vec: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
-         lse_part: Optional[torch.Tensor] = None, block_n: int = 0) -> None:
+         lse_part: Optional[torch.Tensor] = None, block_n: int = 0, drop: Optional[tuple] = None) -> None:
     """C = epilogue(alpha * A @ B^T) on the tcgen05 kernel (csrc/gemm.cu); see include/mtasr.h for the contract."""
     lib = _lib.load()
     if a.t.dtype != torch.bfloat16 or b.t.dtype != torch.bfloat16:
@@ -136,6 +136,8 @@ def gemm(a: Operand, b: Operand, M: int, N: int, K: int, out: Optional[Out], *, 
     d.row_vec = _p(row_vec)
     d.row_scale = _p(row_scale)
     d.lse_part = _p(lse_part)
+    if drop is not None:                      # (seed (2,) int32 device tensor, site, keep16)
+        d.drop_seed, d.drop_site, d.drop_keep16 = _p(drop[0]), int(drop[1]), int(drop[2])
     check(lib.mtasr_gemm_bf16(C.byref(d), _stream()), "mtasr_gemm_bf16")
 
 
@@ -143,22 +145,37 @@ def gemm_n_tiles(N: int, block_n: int = 0) -> int:
     return int(_lib.load().mtasr_gemm_n_tiles(N, block_n))
 
 
+def keep16(p: float) -> int:
+    """Quantised keep probability of a dropout rate p: round((1 - p) * 65536), at least 1."""
+    return max(1, min(65536, int(round((1.0 - float(p)) * 65536.0))))
+
+
+def dropout(x: torch.Tensor, seed: torch.Tensor, site: int, k16: int, out_dtype=None) -> torch.Tensor:
+    """y = x * mask * 65536 / k16 over the trailing dim as columns (mtasr_dropout); mask index = row * ld_even + col."""
+    x = x.contiguous()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
+    check(_lib.load().mtasr_dropout(_p(x), _dt(x), rows, cols, _p(seed), int(site), int(k16), _p(y), _dt(y), _stream()), "mtasr_dropout")
+    return y
+
+
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = ACT_NONE,
                residual: Optional[torch.Tensor] = None, out_dtype=torch.bfloat16, want_aux: bool = False,
-               out: Optional[torch.Tensor] = None):
+               out: Optional[torch.Tensor] = None, drop: Optional[tuple] = None):
     """y[M,N] = act(x[M,K] @ w[N,K]^T + bias) (+ residual).  Returns y (and the bf16 pre-activation if want_aux)."""
     M, K = x.shape
     N = w.shape[0]
     y = out if out is not None else torch.empty(M, N, device=x.device, dtype=out_dtype)
     aux = torch.empty(M, N, device=x.device, dtype=torch.bfloat16) if want_aux else None
     gemm(Operand(x, x.stride(0)), Operand(w, w.stride(0)), M, N, K, Out(y, y.stride(0)), bias=bias, act=act,
-         residual=None if residual is None else Out(residual, residual.stride(0)), aux=aux)
+         residual=None if residual is None else Out(residual, residual.stride(0)), aux=aux, drop=drop)
     return (y, aux) if want_aux else y
 
 
 def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, out_dtype=torch.bfloat16, act: int = ACT_NONE,
                  act_src: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-                 accumulate_into: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 accumulate_into: Optional[torch.Tensor] = None, drop: Optional[tuple] = None) -> torch.Tensor:
     """dx[M,K] = dy[M,N] @ w[N,K]; optional fused activation backward (act 3/4 with act_src) or residual add."""
     M, N = dy.shape
     K = w.shape[1]
@@ -169,7 +186,7 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, *, out_dtype=torch.bfloat16,
     elif residual is not None:
         res = Out(residual, residual.stride(0))
     gemm(Operand(dy, dy.stride(0)), Operand(w, w.stride(0), major=1), M, K, N, Out(dx, dx.stride(0)), act=act,
-         residual=res, accumulate=accumulate_into is not None)
+         residual=res, accumulate=accumulate_into is not None, drop=drop)
     return dx
 
 
@@ -343,16 +360,18 @@ def relpos_gate_bwd(x, wab, bab, cst, dgate, B, T, H):
     return dx, dwab, dbab, dcst
 
 
-def attn_fwd(qkv, gate, table, klen, B, H, T, scale):
-    """Fused attention forward -> (out (B*T, H*64) bf16, lse (B,H,T) f32)."""
+def attn_fwd(qkv, gate, table, klen, B, H, T, scale, drop=None):
+    """Fused attention forward -> (out (B*T, H*64) bf16, lse (B,H,T) f32).  drop = (seed, site, keep16): dropout on the
+    attention probabilities (hf:217), mask index ((b*H + h)*T + q) * ld_even(T) + k."""
     out = torch.empty(B * T, H * 64, device=qkv.device, dtype=torch.bfloat16)
     lse = torch.empty(B, H, T, device=qkv.device, dtype=torch.float32)
-    check(_lib.load().mtasr_attn_fwd(_p(qkv), _p(gate), _p(table), _p(klen), B, H, T, scale, _p(out), _p(lse), _stream()),
+    ds, dsite, dk = (_p(drop[0]), int(drop[1]), int(drop[2])) if drop is not None else (None, 0, 65536)
+    check(_lib.load().mtasr_attn_fwd(_p(qkv), _p(gate), _p(table), _p(klen), B, H, T, scale, _p(out), _p(lse), ds, dsite, dk, _stream()),
           "mtasr_attn_fwd")
     return out, lse
 
 
-def attn_bwd(qkv, out, dout, lse, gate, table, klen, B, H, T, scale):
+def attn_bwd(qkv, out, dout, lse, gate, table, klen, B, H, T, scale, drop=None):
     """Fused attention backward -> (dqkv (B*T, 3*H*64) bf16, dgate (B,H,T) f32, dtable (H,2T-1) f32)."""
     dev = qkv.device
     D = H * 64
@@ -362,8 +381,9 @@ def attn_bwd(qkv, out, dout, lse, gate, table, klen, B, H, T, scale):
     n_g = (B * H * T + 3) // 4 * 4
     acc = torch.zeros(n_g + H * (2 * T - 1), device=dev, dtype=torch.float32)                       # one fill for both
     dgate, dtable = acc[:B * H * T].view(B, H, T), acc[n_g:].view(H, 2 * T - 1)
+    ds, dsite, dk = (_p(drop[0]), int(drop[1]), int(drop[2])) if drop is not None else (None, 0, 65536)
     check(_lib.load().mtasr_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(gate), _p(table), _p(klen), B, H, T, scale, _p(dqkv),
-                                     _p(dq32), _p(delta), _p(dgate), _p(dtable), _stream()), "mtasr_attn_bwd")
+                                     _p(dq32), _p(delta), _p(dgate), _p(dtable), ds, dsite, dk, _stream()), "mtasr_attn_bwd")
     return dqkv, dgate, dtable
 
 

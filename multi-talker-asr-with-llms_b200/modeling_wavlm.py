@@ -11,8 +11,11 @@ Deliberate, documented differences:
   * `output_attentions=True` raises (attention probabilities exist only tile-wise per head);
   * the conv feature encoder has no backward: it is frozen in every reference run (ref:run.sh:231); asking for its
     gradients raises instead of silently falling back (the adapter, which feeds the LLM, does have one);
-  * dropout / LayerDrop inside the encoder are not applied (parity and throughput runs use p=0; ref RNG streams
-    cannot be reproduced anyway).
+  * training-mode dropout (hidden / activation / attention, hf:217,291,294,323,364,407,483 -- the reference trains with
+    0.1 each) IS applied, fused into the GEMM epilogues and the attention kernels, but from a counter-based generator seeded
+    by torch's CUDA generator: the reference's Philox stream cannot be reproduced bit for bit, the distribution
+    is the same.  LayerDrop > 0 in training raises (the reference sets layerdrop = 0,
+    ref:utils/create_from_pretrained.py:212).
 """
 import math
 from dataclasses import dataclass
@@ -331,34 +334,55 @@ class WavLMModel(WavLMPreTrainedModel):
         to gru_rel_pos_linear / gru_rel_pos_const and back into the layer input)."""
         return ops.RelPosGateFn.apply(h, attn.gru_rel_pos_linear.weight, attn.gru_rel_pos_linear.bias, attn.gru_rel_pos_const)
 
-    def _encoder_layer(self, x, layer, table, klen):
+    def _encoder_layer(self, x, layer, table, klen, drop=None, li=0):
+        """One encoder layer.  `drop` (ops.DropState or None) carries the per-forward dropout seed; the sites of layer `li`
+        are the attention probabilities (hf:217), the attention output (hf:323/364), the FFN activation (hf:291) and the FFN
+        output (hf:294) -- all fused into the kernels that produce those tensors."""
         at, ff = layer.attention, layer.feed_forward
         H = at.num_heads
         eps = layer.layer_norm.eps
+        d_attn = drop.attn(li) if drop is not None else None
+        d_ao = drop.hidden(li, ops.SITE_ATTN_OUT) if drop is not None else None
+        d_act = drop.act(li) if drop is not None else None
+        d_fo = drop.hidden(li, ops.SITE_FFN_OUT) if drop is not None else None
         if self.config.do_stable_layer_norm and at.head_dim == 64 and not ops._UNFUSED_ATTN and ops._FUSED_LAYERS:   # hf:355-366
             gl = at.gru_rel_pos_linear
             x = ops.PreLNAttentionFn.apply(x, layer.layer_norm.weight, layer.layer_norm.bias, eps, at.q_proj.weight, at.q_proj.bias,
                                            at.k_proj.weight, at.k_proj.bias, at.v_proj.weight, at.v_proj.bias, at.out_proj.weight,
-                                           at.out_proj.bias, gl.weight, gl.bias, at.gru_rel_pos_const, table, klen, H)
+                                           at.out_proj.bias, gl.weight, gl.bias, at.gru_rel_pos_const, table, klen, H, d_ao, d_attn)
             x = ops.PreLNFFNFn.apply(x, layer.final_layer_norm.weight, layer.final_layer_norm.bias, eps, ff.intermediate_dense.weight,
-                                     ff.intermediate_dense.bias, ff.output_dense.weight, ff.output_dense.bias)
+                                     ff.intermediate_dense.bias, ff.output_dense.weight, ff.output_dense.bias, d_act, d_fo)
         elif self.config.do_stable_layer_norm:
             h1 = ops.layer_norm(x, layer.layer_norm.weight, layer.layer_norm.bias, eps, BF)
             x = ops.AttentionFn.apply(h1, x, at.q_proj.weight, at.q_proj.bias, at.k_proj.weight, at.k_proj.bias, at.v_proj.weight,
-                                      at.v_proj.bias, at.out_proj.weight, at.out_proj.bias, self._gate(h1, at), table, klen, H)
+                                      at.v_proj.bias, at.out_proj.weight, at.out_proj.bias, self._gate(h1, at), table, klen, H,
+                                      d_ao, d_attn)
             h2 = ops.layer_norm(x, layer.final_layer_norm.weight, layer.final_layer_norm.bias, eps, BF)
             x = ops.FFNFn.apply(h2, x, ff.intermediate_dense.weight, ff.intermediate_dense.bias, ff.output_dense.weight,
-                                ff.output_dense.bias)
+                                ff.output_dense.bias, d_act, d_fo)
         else:                                  # hf:314-329
             y = ops.AttentionFn.apply(x, x, at.q_proj.weight, at.q_proj.bias, at.k_proj.weight, at.k_proj.bias, at.v_proj.weight,
-                                      at.v_proj.bias, at.out_proj.weight, at.out_proj.bias, self._gate(x, at), table, klen, H)
+                                      at.v_proj.bias, at.out_proj.weight, at.out_proj.bias, self._gate(x, at), table, klen, H,
+                                      d_ao, d_attn)
             y = ops.layer_norm(y, layer.layer_norm.weight, layer.layer_norm.bias, eps, F32)
             z = ops.FFNFn.apply(y, y, ff.intermediate_dense.weight, ff.intermediate_dense.bias, ff.output_dense.weight,
-                                ff.output_dense.bias)
+                                ff.output_dense.bias, d_act, d_fo)
             x = ops.layer_norm(z, layer.final_layer_norm.weight, layer.final_layer_norm.bias, eps, F32)
         return x
 
-    def _encoder_fwd(self, hidden: torch.Tensor, fmask: Optional[torch.Tensor], output_hidden_states: bool):
+    def _dropout_state(self, device):
+        """ops.DropState for this forward pass, or None outside training / with all rates zero."""
+        cfg = self.config
+        if not self.training:
+            return None
+        if cfg.layerdrop > 0:
+            raise NotImplementedError("mtasr_b200: LayerDrop (config.layerdrop > 0) in training mode is not implemented; the "
+                                      "reference sets layerdrop = 0 (ref:utils/create_from_pretrained.py:212)")
+        if max(cfg.hidden_dropout, cfg.activation_dropout, cfg.attention_dropout, cfg.feat_proj_dropout) <= 0:
+            return None
+        return ops.DropState(device, cfg.hidden_dropout, cfg.activation_dropout, cfg.attention_dropout)
+
+    def _encoder_fwd(self, hidden: torch.Tensor, fmask: Optional[torch.Tensor], output_hidden_states: bool, drop=None):
         """hf:376-447 / hf:450-522."""
         enc = self.encoder
         B, T, D = hidden.shape
@@ -370,18 +394,21 @@ class WavLMModel(WavLMPreTrainedModel):
         hidden = ops.PosConvFn.apply(hidden.contiguous(), ops.pos_conv_weight(conv), conv.bias, conv.groups, None)
         if not self.config.do_stable_layer_norm:
             hidden = ops.layer_norm(hidden, enc.layer_norm.weight, enc.layer_norm.bias, enc.layer_norm.eps, F32)
+        if drop is not None and drop.k_hidden < 65536:             # hf:407 / hf:483: dropout on the encoder input
+            hidden = ops.DropoutFn.apply(hidden, drop.seed, ops.SITE_ENTRY, drop.k_hidden)
         table = self._relpos_table(T, hidden.device)
         all_h = () if output_hidden_states else None
         # `--gradient_checkpointing` (ref:run.sh:239 -> PreTrainedModel.gradient_checkpointing_enable sets the flag on the
         # encoder; the reference's layers are GradientCheckpointingLayers, hf:298,339): recompute each layer in the backward
         ckpt = bool(getattr(enc, "gradient_checkpointing", False)) and self.training and torch.is_grad_enabled()
-        for layer in enc.layers:
+        for li, layer in enumerate(enc.layers):
             if output_hidden_states:
                 all_h = all_h + (hidden,)
-            if ckpt:
-                hidden = torch.utils.checkpoint.checkpoint(self._encoder_layer, hidden, layer, table, klen, use_reentrant=False)
+            if ckpt:   # the recompute receives the same `drop` (seed tensor + static site numbers): identical masks
+                hidden = torch.utils.checkpoint.checkpoint(self._encoder_layer, hidden, layer, table, klen, drop, li,
+                                                           use_reentrant=False)
             else:
-                hidden = self._encoder_layer(hidden, layer, table, klen)
+                hidden = self._encoder_layer(hidden, layer, table, klen, drop, li)
         if self.config.do_stable_layer_norm:
             hidden = ops.layer_norm(hidden, enc.layer_norm.weight, enc.layer_norm.bias, enc.layer_norm.eps, F32)
         if output_hidden_states:
@@ -422,8 +449,11 @@ class WavLMModel(WavLMPreTrainedModel):
             normed_f = K.layernorm_fwd(feats, fp.layer_norm.weight.detach().float(), fp.layer_norm.bias.detach().float(),
                                        fp.layer_norm.eps, out_bf16=False, out_f32=True, save_stats=False)[1]
         hidden = ops.linear(normed_b, fp.projection.weight, fp.projection.bias, out_dtype=F32)
+        drop = self._dropout_state(hidden.device)
+        if drop is not None and self.config.feat_proj_dropout > 0:   # hf:104 (the reference sets it to 0)
+            hidden = ops.DropoutFn.apply(hidden, drop.seed, ops.SITE_FEAT_PROJ, K.keep16(self.config.feat_proj_dropout))
         hidden = self._mask_hidden_states(hidden, mask_time_indices=mask_time_indices, attention_mask=fmask)
-        enc_out, all_h = self._encoder_fwd(hidden, fmask, output_hidden_states)
+        enc_out, all_h = self._encoder_fwd(hidden, fmask, output_hidden_states, drop)
         last, down = self.adapter(enc_out)
         if not return_dict:
             return (last, normed_f) + ((all_h,) if all_h is not None else ())
@@ -436,6 +466,9 @@ class WavLMModel(WavLMPreTrainedModel):
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError("mtasr_b200: precision 'fp32' is a forward-only parity mode; wrap the call in torch.no_grad() "
                                       "(training runs use the bf16-operand path)")
+        if self._dropout_state(input_values.device) is not None:
+            raise NotImplementedError("mtasr_b200: the fp32 encoder mode is an inference / validation mode; it does not apply "
+                                      "training-mode dropout -- call .eval() or use the bf16-operand path")
         cfg = self.config
         with torch.no_grad():
             feats = precise.feature_extractor(self, input_values)                # (B,T,C) fp32

@@ -66,6 +66,60 @@ def cat_cached(params, dtype):
     return val
 
 
+# ------------------------------------------------------------------------------------------------------ dropout
+# Training-mode dropout of the encoder (hf:291 activation_dropout after the FFN's GELU; hf:294 / 323 / 364 hidden_dropout on the
+# FFN and attention outputs before the residual add; hf:407 / 483 on the encoder input after the positional conv; hf:217
+# attention_dropout on the attention probabilities).  The reference trains with all three at 0.1
+# (ref:utils/create_from_pretrained.py:209-212 zeroes only feat_proj_dropout / final_dropout / layerdrop).
+# Masks come from a counter-based generator (csrc/common.cuh drop_hash) keyed by a per-forward seed tensor drawn from torch's
+# CUDA generator and a static site number, so the backward -- and a gradient-checkpoint replay, which receives the same
+# seed tensor -- regenerate them; nothing is stored.  Fused sites: GEMM epilogues and the attention kernels.
+SITE_ENTRY, SITE_FEAT_PROJ = 1, 2
+SITE_ATTN_OUT, SITE_FFN_ACT, SITE_FFN_OUT, SITE_ATTN_PROB = 0, 1, 2, 3
+
+
+def site_id(layer: int, which: int) -> int:
+    return 16 + 4 * int(layer) + which
+
+
+class DropState:
+    """Dropout configuration of one forward pass: seed (2,) int32 on the device + quantised keep probabilities."""
+    __slots__ = ("seed", "k_hidden", "k_act", "k_attn")
+
+    def __init__(self, device, p_hidden: float, p_act: float, p_attn: float):
+        self.seed = torch.randint(0, 2 ** 31 - 1, (2,), device=device, dtype=torch.int32)     # consumes torch's CUDA generator
+        self.k_hidden, self.k_act, self.k_attn = K.keep16(p_hidden), K.keep16(p_act), K.keep16(p_attn)
+
+    def hidden(self, layer, which):
+        return (self.seed, site_id(layer, which), self.k_hidden) if self.k_hidden < 65536 else None
+
+    def act(self, layer):
+        return (self.seed, site_id(layer, SITE_FFN_ACT), self.k_act) if self.k_act < 65536 else None
+
+    def attn(self, layer):
+        return (self.seed, site_id(layer, SITE_ATTN_PROB), self.k_attn) if self.k_attn < 65536 else None
+
+
+class DropoutFn(Function):
+    """Stand-alone dropout pass y = x * mask / keep (sites that are not a GEMM epilogue: the encoder input)."""
+
+    @staticmethod
+    def forward(ctx, x, seed, site, k16):
+        ctx.site, ctx.k16 = site, k16
+        ctx.save_for_backward(seed)
+        return K.dropout(x, seed, site, k16)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (seed,) = ctx.saved_tensors
+        return K.dropout(dy, seed, ctx.site, ctx.k16), None, None, None
+
+
+def _masked_bf16(dy: torch.Tensor, drop) -> torch.Tensor:
+    """bf16 (rows, D) GEMM operand of the gradient that flows back through a fused output-dropout site: dy * mask / keep."""
+    return K.dropout(dy.view(-1, dy.shape[-1]), drop[0], drop[1], drop[2], out_dtype=BF)
+
+
 def _flat2d(x: torch.Tensor) -> torch.Tensor:
     return x.contiguous().view(-1, x.shape[-1])
 
@@ -144,21 +198,24 @@ class FFNFn(Function):
     The GELU backward is fused into the W2-dgrad epilogue (act 3)."""
 
     @staticmethod
-    def forward(ctx, h, res, w1, b1, w2, b2):
+    def forward(ctx, h, res, w1, b1, w2, b2, drop_act=None, drop_out=None):
         shp = h.shape
         hb = K.cast_bf16(_flat2d(h))
         w1b, w2b = bf16_of(w1), bf16_of(w2)
-        a, u = K.linear_fwd(hb, w1b, b1.detach().float(), act=K.ACT_GELU, want_aux=True)
-        y = K.linear_fwd(a, w2b, b2.detach().float(), residual=_flat2d(res), out_dtype=F32)
+        a, u = K.linear_fwd(hb, w1b, b1.detach().float(), act=K.ACT_GELU, want_aux=True, drop=drop_act)
+        y = K.linear_fwd(a, w2b, b2.detach().float(), residual=_flat2d(res), out_dtype=F32, drop=drop_out)
         ctx.h_dtype = h.dtype
+        ctx.drops = (drop_act, drop_out)
         ctx.save_for_backward(hb, u, a, w1b, w2b)
         return y.view(shp[:-1] + (w2.shape[0],))
 
     @staticmethod
     def backward(ctx, dy):
         hb, u, a, w1b, w2b = ctx.saved_tensors
-        dyb = K.cast_bf16(_flat2d(dy))
-        du = K.linear_dgrad(dyb, w2b, act=K.ACT_GELU_BWD, act_src=u)
+        drop_act, drop_out = ctx.drops
+        dy = dy.contiguous()
+        dyb = _masked_bf16(dy, drop_out) if drop_out is not None else K.cast_bf16(_flat2d(dy))
+        du = K.linear_dgrad(dyb, w2b, act=K.ACT_GELU_BWD, act_src=u, drop=drop_act)
         dh = dw1 = db1 = dw2 = db2 = None
         if ctx.needs_input_grad[0]:
             dh = K.linear_dgrad(du, w1b, out_dtype=ctx.h_dtype).view(dy.shape[:-1] + (w1b.shape[1],))
@@ -170,7 +227,7 @@ class FFNFn(Function):
             dw2 = K.linear_wgrad(dyb, a)
         if ctx.needs_input_grad[5]:
             db2 = K.colsum(dyb)
-        return dh, (dy if ctx.needs_input_grad[1] else None), dw1, db1, dw2, db2
+        return dh, (dy if ctx.needs_input_grad[1] else None), dw1, db1, dw2, db2, None, None
 
 
 # ------------------------------------------------------------------------------------------------------ rel-pos gate
@@ -219,7 +276,7 @@ class AttentionFn(Function):
     run in one row kernel that never materialises the (B*H,T,T) fp32 bias of the reference."""
 
     @staticmethod
-    def forward(ctx, h, res, wq, bq, wk, bk, wv, bv, wo, bo, gate, table, klen, H):
+    def forward(ctx, h, res, wq, bq, wk, bk, wv, bv, wo, bo, gate, table, klen, H, drop_out=None, drop_attn=None):
         B, T, D = h.shape
         d = D // H
         hb = K.cast_bf16(_flat2d(h))
@@ -232,10 +289,13 @@ class AttentionFn(Function):
         table = table.detach().contiguous().float()
         fused = d == 64 and not _UNFUSED_ATTN
         if fused:
-            O, lse = K.attn_fwd(qkv, gate, table, klen, B, H, T, scale)      # S / P tiles never leave TMEM / smem
+            O, lse = K.attn_fwd(qkv, gate, table, klen, B, H, T, scale, drop=drop_attn)   # S / P tiles never leave TMEM / smem
             P = None
             Tp = 0
         else:
+            if drop_attn is not None:
+                raise NotImplementedError("mtasr_b200: attention_dropout > 0 in training needs the fused attention kernels "
+                                          "(head_dim 64, MTASR_UNFUSED_ATTN unset)")
             Tp = (T + 7) // 8 * 8
             S = torch.empty(B, H, T, Tp, device=h.device, dtype=F32)
             K.gemm(K.Operand(qkv, 3 * D, sb0=d, sb1=T * 3 * D, rows=T), K.Operand(qkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=D, rows=T),
@@ -246,10 +306,11 @@ class AttentionFn(Function):
             O = torch.empty(B * T, D, device=h.device, dtype=BF)
             K.gemm(K.Operand(P, Tp, sb0=T * Tp, sb1=H * T * Tp), K.Operand(qkv, 3 * D, major=1, sb0=d, sb1=T * 3 * D, offset=2 * D, rows=T),
                    T, d, T, K.Out(O, D, sb0=d, sb1=T * D), batch=(H, B))
-        y = K.linear_fwd(O, wob, bo.detach().float(), residual=_flat2d(res), out_dtype=F32)
+        y = K.linear_fwd(O, wob, bo.detach().float(), residual=_flat2d(res), out_dtype=F32, drop=drop_out)
         ctx.dims = (B, T, D, H, Tp, scale)
         ctx.h_dtype = h.dtype
         ctx.fused = fused
+        ctx.drops = (drop_out, drop_attn)
         ctx.save_for_backward(hb, qkv, P if P is not None else lse, O, wqkv, wob, gate, table, klen)
         return y.view(B, T, D)
 
@@ -259,12 +320,14 @@ class AttentionFn(Function):
         B, T, D, H, Tp, scale = ctx.dims
         d = D // H
         need = ctx.needs_input_grad
-        dyb = K.cast_bf16(_flat2d(dy))
+        drop_out, drop_attn = ctx.drops
+        dy = dy.contiguous()
+        dyb = _masked_bf16(dy, drop_out) if drop_out is not None else K.cast_bf16(_flat2d(dy))
         dO = K.linear_dgrad(dyb, wob)                                         # (B*T, D) bf16
         dwo = K.linear_wgrad(dyb, O) if need[8] else None
         dbo = K.colsum(dyb) if need[9] else None
         if ctx.fused:
-            dqkv, dgate, dtable = K.attn_bwd(qkv, O, dO, P, gate, table, klen, B, H, T, scale)   # P slot holds the row LSE
+            dqkv, dgate, dtable = K.attn_bwd(qkv, O, dO, P, gate, table, klen, B, H, T, scale, drop=drop_attn)   # P slot holds the row LSE
         else:
             dP = torch.empty(B, H, T, Tp, device=dy.device, dtype=F32)
             K.gemm(K.Operand(dO, D, sb0=d, sb1=T * D, rows=T), K.Operand(qkv, 3 * D, sb0=d, sb1=T * 3 * D, offset=2 * D, rows=T),
@@ -289,7 +352,7 @@ class AttentionFn(Function):
             dbqkv = K.colsum(dqkv)
             dbq, dbk, dbv = dbqkv[:D], dbqkv[D:2 * D], dbqkv[2 * D:]
         return (dh, dy if need[1] else None, dwq, dbq, dwk, dbk, dwv, dbv, dwo, dbo,
-                dgate if need[10] else None, dtable if need[11] else None, None, None)
+                dgate if need[10] else None, dtable if need[11] else None, None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------------ fused pre-LN blocks
@@ -337,7 +400,8 @@ class PreLNAttentionFn(Function):
     65 MB elementwise adds / casts per layer launched by the autograd engine."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, eps, wq, bq, wk, bk, wv, bv, wo, bo, gw, gb, gconst, table, klen, H):
+    def forward(ctx, x, ln_w, ln_b, eps, wq, bq, wk, bk, wv, bv, wo, bo, gw, gb, gconst, table, klen, H, drop_out=None,
+                drop_attn=None):
         B, T, D = x.shape
         d = D // H
         if d != 64 or gw.shape != (8, 64):
@@ -354,8 +418,9 @@ class PreLNAttentionFn(Function):
         qkv = K.linear_fwd(h2d, wqkv, bqkv)
         scale = float(d) ** -0.5
         tab = table.detach().contiguous().float()
-        O, lse = K.attn_fwd(qkv, gate, tab, klen, B, H, T, scale)
-        y = K.linear_fwd(O, wob, bo.detach().float(), residual=xf.view(B * T, D), out_dtype=F32)
+        O, lse = K.attn_fwd(qkv, gate, tab, klen, B, H, T, scale, drop=drop_attn)
+        y = K.linear_fwd(O, wob, bo.detach().float(), residual=xf.view(B * T, D), out_dtype=F32, drop=drop_out)
+        ctx.drops = (drop_out, drop_attn)
         ctx.dims = (B, T, D, H, scale)
         ctx.const_shape = gconst.shape
         ctx.save_for_backward(xf, gamma, mean, rstd, h1, qkv, lse, O, wqkv, wob, gate, tab, klen, wab, bab, cst)
@@ -366,12 +431,13 @@ class PreLNAttentionFn(Function):
         xf, gamma, mean, rstd, h1, qkv, lse, O, wqkv, wob, gate, tab, klen, wab, bab, cst = ctx.saved_tensors
         B, T, D, H, scale = ctx.dims
         need = ctx.needs_input_grad
+        drop_out, drop_attn = ctx.drops
         dy = dy.contiguous()
-        dyb = _cast_or_twin(dy)
+        dyb = _masked_bf16(dy, drop_out) if drop_out is not None else _cast_or_twin(dy)
         dO = K.linear_dgrad(dyb, wob)
         dwo = K.linear_wgrad(dyb, O) if need[10] else None
         dbo = K.colsum(dyb) if need[11] else None
-        dqkv, dgate, dtable = K.attn_bwd(qkv, O, dO, lse, gate, tab, klen, B, H, T, scale)
+        dqkv, dgate, dtable = K.attn_bwd(qkv, O, dO, lse, gate, tab, klen, B, H, T, scale, drop=drop_attn)
         dxg, dwab, dbab, dcst = K.relpos_gate_bwd(h1, wab, bab, cst, dgate, B, T, H)           # gate path into LN(x), fp32
         dx = dlnw = dlnb = None
         if need[0] or need[1] or need[2]:
@@ -392,7 +458,7 @@ class PreLNAttentionFn(Function):
         dgb = torch.cat([dbab[0:1].expand(4), dbab[1:2].expand(4)]) if need[13] else None
         dgc = dcst.view(ctx.const_shape) if need[14] else None
         return (dx, dlnw, dlnb, None, dwq, dbq, dwk, dbk, dwv, dbv, dwo, dbo, dgw, dgb, dgc,
-                dtable if need[15] else None, None, None)
+                dtable if need[15] else None, None, None, None, None)
 
 
 class PreLNFFNFn(Function):
@@ -400,7 +466,7 @@ class PreLNFFNFn(Function):
     autograd node (LayerNormFn -> FFNFn with the residual-stream gradient added inside the LayerNorm backward)."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, eps, w1, b1, w2, b2):
+    def forward(ctx, x, ln_w, ln_b, eps, w1, b1, w2, b2, drop_act=None, drop_out=None):
         shp = x.shape
         D = shp[-1]
         xf = x.contiguous()
@@ -408,8 +474,9 @@ class PreLNFFNFn(Function):
         hb, _, mean, rstd = K.layernorm_fwd(xf, gamma, ln_b.detach().float(), eps, out_bf16=True, out_f32=False)
         w1b, w2b = bf16_of(w1), bf16_of(w2)
         h2d = hb.view(-1, D)
-        a, u = K.linear_fwd(h2d, w1b, b1.detach().float(), act=K.ACT_GELU, want_aux=True)
-        y = K.linear_fwd(a, w2b, b2.detach().float(), residual=xf.view(-1, D), out_dtype=F32)
+        a, u = K.linear_fwd(h2d, w1b, b1.detach().float(), act=K.ACT_GELU, want_aux=True, drop=drop_act)
+        y = K.linear_fwd(a, w2b, b2.detach().float(), residual=xf.view(-1, D), out_dtype=F32, drop=drop_out)
+        ctx.drops = (drop_act, drop_out)
         ctx.save_for_backward(xf, gamma, mean, rstd, hb, u, a, w1b, w2b)
         return y.view(shp)
 
@@ -418,9 +485,10 @@ class PreLNFFNFn(Function):
         xf, gamma, mean, rstd, hb, u, a, w1b, w2b = ctx.saved_tensors
         need = ctx.needs_input_grad
         D = xf.shape[-1]
+        drop_act, drop_out = ctx.drops
         dy = dy.contiguous()
-        dyb = _cast_or_twin(dy)
-        du = K.linear_dgrad(dyb, w2b, act=K.ACT_GELU_BWD, act_src=u)
+        dyb = _masked_bf16(dy, drop_out) if drop_out is not None else _cast_or_twin(dy)
+        du = K.linear_dgrad(dyb, w2b, act=K.ACT_GELU_BWD, act_src=u, drop=drop_act)
         dx = dlnw = dlnb = None
         if need[0] or need[1] or need[2]:
             dh = K.linear_dgrad(du, w1b)
@@ -433,7 +501,7 @@ class PreLNFFNFn(Function):
         db1 = K.colsum(du) if need[5] else None
         dw2 = K.linear_wgrad(dyb, a) if need[6] else None
         db2 = K.colsum(dyb) if need[7] else None
-        return dx, dlnw, dlnb, None, dw1, db1, dw2, db2
+        return dx, dlnw, dlnb, None, dw1, db1, dw2, db2, None, None
 
 
 # ------------------------------------------------------------------------------------------------------ pos conv

@@ -306,14 +306,18 @@ class LSTMLayerF32Fn(torch.autograd.Function):
         return dx, dW, db
 
 
-def separator(mod, x: torch.Tensor):
-    """`Separator.forward` (ref:models/separator.py:151-166) in fp32-class arithmetic, differentiable."""
+def separator(mod, x: torch.Tensor, relu_outputs=None):
+    """`Separator.forward` (ref:models/separator.py:151-166) in fp32-class arithmetic, differentiable.  `relu_outputs`: optional
+    list that receives every ReLU output in evaluation order (test hook: lets a float64 oracle use the same sub-gradient
+    choice at pre-activations that are zero to within rounding)."""
     from . import ops
     import torch.nn as nn
     if mod.proj_activation not in ("relu", None):
         raise NotImplementedError("mtasr_b200 fp32 mode: Separator proj_activation must be 'relu' or None")
     act = K.ACT_RELU if mod.proj_activation == "relu" else K.ACT_NONE
     y = LinearF32Fn.apply(x.float(), mod.pre_proj.weight, mod.pre_proj.bias, act)
+    if relu_outputs is not None and act == K.ACT_RELU:
+        relu_outputs.append(y)
     y = ops.layer_norm(y, mod.pre_ln.weight, mod.pre_ln.bias, mod.pre_ln.eps, F32)
     for l, cell in enumerate(mod.lstm.cells):
         y = LSTMLayerF32Fn.apply(y, cell.W.weight, cell.W.bias)
@@ -332,6 +336,8 @@ def separator(mod, x: torch.Tensor):
             if isinstance(m, nn.Linear):
                 relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
                 h = LinearF32Fn.apply(h, m.weight, m.bias, K.ACT_RELU if relu else K.ACT_NONE)
+                if relu_outputs is not None and relu:
+                    relu_outputs.append(h)
                 i += 2 if relu else 1
             elif isinstance(m, nn.Dropout):
                 h = m(h)

@@ -39,6 +39,9 @@ def _no_tf32():
 
 @pytest.mark.parametrize("V,D,T,B", [(515, 128, 60, 3), (4099, 1024, 150, 4), (128259, 1024, 120, 3)])
 def test_ctc_head_fp32_mode_vs_oracle(cuda, V, D, T, B):
+    """Truth = the oracle in float64 on the same device.  (The oracle's own fp32 run is logged beside it: torch's fp32 CTC
+    works in un-rescaled log space, so at nll ~ 1e3 its occupancies carry ~1e-4 of rounding themselves.)"""
+    import copy
     from oracle.model_ref import RefCTC
     from mtasr_b200 import precise
     from mtasr_b200.ctc import CTC
@@ -48,6 +51,7 @@ def test_ctc_head_fp32_mode_vs_oracle(cuda, V, D, T, B):
         head.ctc_lo.weight.mul_(3.0)
     ref = RefCTC(V, D).to(cuda)
     ref.ctc_lo.load_state_dict(head.ctc_lo.state_dict())
+    ref64 = copy.deepcopy(ref).double()
     hs = torch.randn(B, T, D, device=cuda)
     hlens = torch.tensor([T, T - 7, T // 2, 5][:B], device=cuda)
     Lmax = 14
@@ -56,6 +60,7 @@ def test_ctc_head_fp32_mode_vs_oracle(cuda, V, D, T, B):
     ylens = torch.tensor([Lmax, 9, 0, 12][:B], device=cuda)       # row 2: empty target; row 3: infeasible (5 frames)
     h1 = hs.clone().requires_grad_(True)
     h2 = hs.clone().requires_grad_(True)
+    h3 = hs.double().clone().requires_grad_(True)
     up = torch.rand(B, device=cuda) + 0.5
     with precise.precision("fp32"):
         n1 = head.per_utterance_nll(h1, hlens, ys, ylens)
@@ -64,47 +69,101 @@ def test_ctc_head_fp32_mode_vs_oracle(cuda, V, D, T, B):
         scalar = head(hs, hlens, ys, ylens)
     n2 = ref.per_utt_nll(h2, hlens, ys, ylens)
     g2 = torch.autograd.grad((n2 * up).sum(), [h2, ref.ctc_lo.weight, ref.ctc_lo.bias])
-    errs = dict(nll=rel(n1, n2), dh=rel(g1[0], g2[0]), dw=rel(g1[1], g2[1]), db=rel(g1[2], g2[2]))
+    n3 = ref64.per_utt_nll(h3, hlens, ys, ylens)
+    g3 = [t.float() for t in torch.autograd.grad((n3 * up.double()).sum(), [h3, ref64.ctc_lo.weight, ref64.ctc_lo.bias])]
+    errs = dict(nll=rel(n1, n3.float()), dh=rel(g1[0], g3[0]), dw=rel(g1[1], g3[1]), db=rel(g1[2], g3[2]))
+    torch32 = dict(nll=rel(n2, n3.float()), dh=rel(g2[0], g3[0]), dw=rel(g2[1], g3[1]), db=rel(g2[2], g3[2]))
     with torch.no_grad():
-        logits = ref.ctc_lo(hs)
+        logits = ref64.ctc_lo(hs.double())
         am_ref = logits.argmax(-1)
         top2 = logits.topk(2, -1).values
         errs["min_top2_margin"] = (top2[..., 0] - top2[..., 1]).min().item()
         errs["argmax_mismatches"] = int((am != am_ref).sum().item())
-    _log(test="ctc_head_fp32_mode", V=V, **errs)
+        am32_mism = int((ref.ctc_lo(hs).argmax(-1) != am_ref).sum().item())
+    _log(test="ctc_head_fp32_mode", V=V, ours_vs_f64=errs, torch_f32_vs_f64=torch32, torch_f32_argmax_mismatches=am32_mism)
     assert errs["nll"] < 1e-5, errs
-    assert errs["dh"] < 1e-4 and errs["dw"] < 1e-4 and errs["db"] < 1e-4, errs
+    assert errs["dh"] < 1e-4 and errs["dw"] < 1e-4 and errs["db"] < 1e-4, (errs, torch32)
     if B > 3:
         assert n1[3].item() == 0.0 and g1[0][3].abs().max().item() == 0.0
-    assert abs(scalar.item() - ref(hs, hlens, ys, ylens).item()) < 1e-5 * abs(ref(hs, hlens, ys, ylens).item())
+    want = (n3.sum() / B).item()
+    assert abs(scalar.item() - want) < 1e-5 * abs(want)
     assert torch.equal(am, am_ref), errs                           # every frame, no margin mask
 
 
+def _sep64(sep, x64, masks):
+    """float64 restatement of ref:models/separator.py:151-166 whose ReLUs use the GIVEN activity masks (treated as
+    constants): the sub-gradient choice of the implementation under test at pre-activations that vanish to rounding."""
+    import torch.nn.functional as F
+    p = {k: v.detach().double() for k, v in sep.named_parameters()}
+    for v in p.values():
+        v.requires_grad_(True)
+    it = iter(masks)
+    Hs = sep.hidden_size
+    y = F.linear(x64, p["pre_proj.weight"], p["pre_proj.bias"]) * next(it)
+    y = F.layer_norm(y, (Hs,), p["pre_ln.weight"], p["pre_ln.bias"], sep.pre_ln.eps)
+    B, T, _ = y.shape
+    for l in range(len(sep.lstm.cells)):
+        W, b = p[f"lstm.cells.{l}.W.weight"], p[f"lstm.cells.{l}.W.bias"]
+        h = y.new_zeros(B, Hs)
+        c = y.new_zeros(B, Hs)
+        outs = []
+        for t in range(T):
+            i, f, g, o = F.linear(torch.cat([y[:, t], h], -1), W, b).chunk(4, -1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            outs.append(h)
+        y = torch.stack(outs, 1)
+    y = F.layer_norm(y, (Hs,), p["post_ln.weight"], p["post_ln.bias"], sep.post_ln.eps)
+    res = []
+    for n in range(sep.talker_numbers):
+        a = F.linear(y, p[f"sep_branches.{n}.0.weight"], p[f"sep_branches.{n}.0.bias"]) * next(it)
+        z = F.linear(a, p[f"sep_branches.{n}.2.weight"], p[f"sep_branches.{n}.2.bias"]) * next(it)
+        res.append(F.layer_norm(z, (sep.in_dim,), p[f"sep_branches.{n}.4.weight"], p[f"sep_branches.{n}.4.bias"], sep.sep_branches[n][4].eps))
+    return res, p
+
+
 @pytest.mark.parametrize("B,T,D,Hs", [(3, 37, 128, 96), (4, 120, 1024, 896)])
-def test_separator_fp32_mode_vs_oracle(cuda, B, T, D, Hs):
+def test_separator_fp32_mode_vs_oracle(cuda, B, T, D, Hs, monkeypatch):
+    """Forward against the oracle's python time loop (fp32 and float64).  Gradients against a float64 restatement that uses
+    OUR ReLU activity masks: two correct fp32 implementations disagree on relu'(z) wherever |z| is below their rounding error
+    (~1e-5 of the elements), and every such flip moves a whole gradient element, so gradients are only comparable to 1e-4
+    under a common sub-gradient choice.  The flips themselves are checked to sit at |z| < 1e-4."""
     from oracle.model_ref import RefSeparator
     from mtasr_b200 import precise
     from mtasr_b200.separator import Separator
-    torch.manual_seed(2)
+    monkeypatch.setenv("MTASR_GEMM_NO_SPLITK", "1")               # deterministic summation order: the second forward
+    torch.manual_seed(2)                                          # below reproduces the masks of the first bit for bit
     sep = Separator(D, Hs, 2).to(cuda).eval()
     ref = RefSeparator(D, Hs, 2).to(cuda).eval()
     ref.load_state_dict(sep.state_dict())
     x = torch.randn(B, T, D, device=cuda)
     x1 = x.clone().requires_grad_(True)
-    x2 = x.clone().requires_grad_(True)
     w = [torch.randn(B, T, D, device=cuda) for _ in range(2)]
     with precise.precision("fp32"):
         y1 = sep(x1)
         g1 = torch.autograd.grad(sum((a * b).sum() for a, b in zip(y1, w)), [x1] + list(sep.parameters()))
-    y2 = ref(x2)
-    g2 = torch.autograd.grad(sum((a * b).sum() for a, b in zip(y2, w)), [x2] + list(ref.parameters()))
+        with torch.no_grad():
+            relus = []
+            y1b = precise.separator(sep, x, relu_outputs=relus)
+    assert torch.equal(y1b[0], y1[0]) and len(relus) == 5
+    masks = [(r > 0).double() for r in relus]
+    with torch.no_grad():
+        y2 = ref(x)
+        y3 = ref.double()(x.double())
+    x3 = x.double().clone().requires_grad_(True)
+    y4, p64 = _sep64(sep, x3, masks)
     names = ["x"] + [n for n, _ in sep.named_parameters()]
-    errs = {n: rel(a, b) for n, a, b in zip(names, g1, g2)}
-    fwd = max(rel(y1[0], y2[0]), rel(y1[1], y2[1]))
-    _log(test="separator_fp32_mode", Hs=Hs, fwd=fwd, worst=max(errs.values()), grads={k: float(f"{v:.3g}") for k, v in errs.items()})
+    g4 = torch.autograd.grad(sum((a * b.double()).sum() for a, b in zip(y4, w)), [x3] + [p64[n] for n in names[1:]])
+    errs = {n: rel(a, b.float()) for n, a, b in zip(names, g1, g4)}
+    fwd = max(rel(y1[i], y3[i].float()) for i in range(2))
+    fwd_torch32 = max(rel(y2[i], y3[i].float()) for i in range(2))
+    same_sub = max(rel(y4[i].float(), y3[i].float()) for i in range(2))   # masks only differ where |z| ~ 0: same function value
+    _log(test="separator_fp32_mode", Hs=Hs, fwd_vs_f64=fwd, torch_f32_fwd_vs_f64=fwd_torch32, masked_f64_vs_f64=same_sub,
+         worst=max(errs.values()), grads={k: float(f"{v:.3g}") for k, v in errs.items()})
     assert y1[0].dtype == torch.float32
     assert fwd < 1e-4, fwd
-    assert max(errs.values()) < 2e-4, errs
+    assert same_sub < 1e-6, same_sub
+    assert max(errs.values()) < 1e-4, errs
 
 
 @pytest.mark.parametrize("kind", ["tiny_large", "tiny_base"])
