@@ -316,7 +316,7 @@ def workload_config(args, batch, world):
     return {"workload": workload_name(args),
             "encoder": "wavlm-large-shaped (24L, D=1024, H=16, F=4096), random init", "speakers": args.speakers,
             "seconds": args.seconds, "batch_per_gpu": batch, "global_batch": batch * world, "vocab": 128259,
-            "separator_hidden": 896, "parallelism": f"dp{world}", "spec_augment": "off", "dropout": getattr(args, "dropout", 0.0),
+            "separator_hidden": 896, "launch": getattr(args, "graph_note", None), "parallelism": f"dp{world}", "spec_augment": "off", "dropout": getattr(args, "dropout", 0.0),
             "module_mode": "train()" if getattr(args, "dropout", 0.0) > 0 and args.mode == "train" else "eval() (dropout inactive in both arms)",
             "l2": "working set per step (>1 GB of weights, >20 GB of activations) exceeds the 126 MB L2; no explicit flush"}
 
@@ -391,11 +391,15 @@ def main_ours(args):
         d = [t.to(dev, non_blocking=True) for t in host]
         return d[0], d[1], d[2:2 + ns], d[2 + ns:2 + 2 * ns]
 
+    graphed = [None]        # mtasr_b200.graphs.GraphedTrainStep once captured (MTASR_GRAPH=0: eager launches)
+
     def step(w, m, ys, yl):
         if args.mode == "infer":
             with torch.no_grad():
                 ids = model.forward_ctc(w, attention_mask=m)
             return ids.sum().float()
+        if graphed[0] is not None:
+            return graphed[0](w, m, *ys, *yl)
         for p in model.parameters():
             p.grad = None
         if reducer is not None:
@@ -417,12 +421,16 @@ def main_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_issue = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             fn()
+        host_issue["ms_per_step"] = (time.perf_counter() - t0) * 1e3 / steps   # time the host needs to ENQUEUE a step
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -431,6 +439,22 @@ def main_ours(args):
         return ms.item()
 
     dw, dm, dys, dyl = to_dev()
+    graph_note = "eager launches"
+    if args.mode == "train" and dp_mode != "ddp" and not args.profile_run and os.environ.get("MTASR_GRAPH", "1") != "0":
+        # the whole step (forward + backward + gradient all-reduce) as one CUDA graph: the eager step is bound by the host
+        # (see mtasr_b200/graphs.py); `eager_step` below still measures the per-kernel timings of the roofline leg
+        from mtasr_b200.graphs import GraphedTrainStep
+        try:
+            graphed[0] = GraphedTrainStep(
+                lambda w, m, *rest: net(w, attention_mask=m, label_spks=list(rest[:ns]), label_spks_lengths=list(rest[ns:])),
+                [dw, dm, *dys, *dyl], model.parameters(), reducer=reducer,
+                backward_sm_budget=(total_sms - comm_sms) if comm_sms else 0)
+            graph_note = "one CUDA graph per step (forward + backward" + (" + gradient all-reduce)" if reducer is not None else ")")
+        except Exception as ex:                              # capture unsupported in this environment: stay eager, say so
+            graphed[0] = None
+            graph_note = f"eager launches (graph capture failed: {type(ex).__name__}: {str(ex)[:160]})"
+            torch.cuda.synchronize()
+    args.graph_note = graph_note
     if args.profile_run:
         step(dw, dm, dys, dyl)
         torch.cuda.synchronize()
@@ -450,6 +474,8 @@ def main_ours(args):
     l0 = K.launch_count()
     ms = timed(lambda: step(dw, dm, dys, dyl), args.steps)
     launches = K.launch_count() - l0
+    if graphed[0] is not None:                              # replays do not pass through the C ABI: kernels per captured step
+        launches = graphed[0].launches_per_replay * args.steps
 
     e2e = None
     if not args.no_e2e:
@@ -493,10 +519,12 @@ def main_ours(args):
     clocks = sampler.stop() if sampler else None
 
     # roofline of the dominant kernel (gemm_bf16_kernel): per-launch CUDA events on its stream over one more step
+    g_keep, graphed[0] = graphed[0], None                   # eager launches for this leg: per-launch events on the GEMM
     K.profile_begin()
     step(dw, dm, dys, dyl)
     torch.cuda.synchronize()
     gemm_ms, exec_flops, gemm_launches = K.profile_end()
+    graphed[0] = g_keep
     fl = algorithmic_flops(cfg, S, args.speakers, 896, V_LLAMA3_CTC, backward=args.mode == "train")
     alg_step = fl["total"] * B
     # the QK^T / PV contractions run in the fused attention kernels and the recurrent half of the LSTM in the persistent
@@ -549,7 +577,7 @@ def main_ours(args):
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(args, B, world), "roofline": roof, "cpu_baseline": cpu, "stock_torch_gpu": stock, "e2e": e2e,
-                "gpu_launches": int(launches), "clocks": clocks, "loss": loss0, "trainable_params": n_train,
+                "gpu_launches": int(launches), "host_issue_ms_per_step": host_issue.get("ms_per_step"), "clocks": clocks, "loss": loss0, "trainable_params": n_train,
                 "gflop_per_audio_s": fl["total"] / args.seconds / 1e9}
         print(json.dumps(line), flush=True)
     if world > 1:

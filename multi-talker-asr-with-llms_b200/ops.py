@@ -28,10 +28,32 @@ _FUSED_LAYERS = os.environ.get("MTASR_FUSED_LAYERS", "1") not in ("", "0")
 _CTC_KEEP_LOGITS = os.environ.get("MTASR_CTC_KEEP_LOGITS", "1") not in ("", "0")
 
 
+_CAPTURING = False      # inside graphs.GraphedTrainStep capture: parameter-derived operands must be produced BY graph nodes
+
+
+class capturing:
+    """Context manager: bypass the per-parameter-version operand caches (`bf16_of`, `cat_cached`).  A CUDA graph replay
+    cannot observe that an optimizer step changed a weight, so while a step is being captured every cast / concatenation
+    of a parameter is issued as a kernel of the graph and re-executed by each replay."""
+
+    def __enter__(self):
+        global _CAPTURING
+        self._prev = _CAPTURING
+        _CAPTURING = True
+        return self
+
+    def __exit__(self, *exc):
+        global _CAPTURING
+        _CAPTURING = self._prev
+        return False
+
+
 def bf16_of(p: torch.Tensor) -> torch.Tensor:
     """bf16 copy of a (parameter) tensor, cached on (identity, version) so frozen weights are converted once."""
     if p.dtype == BF:
         return p
+    if _CAPTURING:
+        return K.cast_bf16(p.detach())
     key = id(p)
     hit = _bf16_cache.get(key)
     if hit is not None:
@@ -52,6 +74,8 @@ _cat_cache = {}
 def cat_cached(params, dtype):
     """torch.cat(params, 0) converted to `dtype`, cached on the identities / versions of the parameters (the fused
     QKV weight and bias are rebuilt only after an optimizer step changed them)."""
+    if _CAPTURING:
+        return torch.cat([p.detach().to(dtype) for p in params], 0).contiguous()
     key = tuple(id(p) for p in params) + (dtype,)
     sig = tuple((p._version, p.data_ptr()) for p in params)
     hit = _cat_cache.get(key)
