@@ -448,7 +448,7 @@ def main_ours(args):
             graphed[0] = GraphedTrainStep(
                 lambda w, m, *rest: net(w, attention_mask=m, label_spks=list(rest[:ns]), label_spks_lengths=list(rest[ns:])),
                 [dw, dm, *dys, *dyl], model.parameters(), reducer=reducer,
-                backward_sm_budget=(total_sms - comm_sms) if comm_sms else 0)
+                backward_sm_budget=(total_sms - comm_sms) if comm_sms else 0, release=model.release_graph)
             graph_note = "one CUDA graph per step (forward + backward" + (" + gradient all-reduce)" if reducer is not None else ")")
         except Exception as ex:                              # capture unsupported in this environment: stay eager, say so
             graphed[0] = None

@@ -24,6 +24,13 @@ What capture changes, and how it is kept correct:
     events; they are captured as part of the same graph (capture_error_mode="thread_local": the NCCL watchdog thread's CUDA
     calls do not interfere).
 A new input shape needs a new capture (one `GraphedTrainStep` per shape bucket).
+
+Requirement inherited from autograd: no autograd graph that reaches these parameters may still be alive when the step is
+built.  A parameter's gradient accumulator is created with the first graph that uses it, is bound to the stream that graph
+was built on, and is shared by later graphs for as long as any of them lives; an accumulator left over from an eager step on
+the default stream would make the legacy stream wait on the capturing stream (cudaErrorStreamCaptureImplicit).  The usual
+holder is `HybridLoss.last_ctc_per_head` (per-head losses WITH graph, kept for PCGrad): pass `release=` (e.g.
+`SerializedCTCPath.release_graph`) and it is called before the warm-up.
 """
 from typing import Callable, Iterable, Optional, Sequence
 
@@ -35,7 +42,9 @@ from . import ops
 
 class GraphedTrainStep:
     def __init__(self, fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor], params: Iterable[torch.nn.Parameter],
-                 reducer=None, backward_sm_budget: int = 0, warmup: int = 3):
+                 reducer=None, backward_sm_budget: int = 0, warmup: int = 3, release: Optional[Callable[[], None]] = None):
+        if release is not None:
+            release()
         self.fn = fn
         self.params = [p for p in params if p.requires_grad]
         self.reducer = reducer

@@ -62,6 +62,11 @@ class SerializedCTCPath(nn.Module):
         self.ctc_per_head = self.losses.last_ctc_per_head
         return loss
 
+    def release_graph(self) -> None:
+        """Drop the references that keep the last step's autograd graph alive (the per-head losses kept for PCGrad)."""
+        self.ctc_per_head = None
+        self.losses.last_ctc_per_head = None
+
     @torch.no_grad()
     def forward_ctc(self, input_values, attention_mask=None) -> torch.Tensor:
         out = self.encoder(input_values, attention_mask=attention_mask)

@@ -29,15 +29,22 @@ def _setup(cuda, p_drop=0.0):
 
     named = named_params(enc, sep, heads)
     params_l = [v for v in named.values() if v.requires_grad]
-    return enc, fn, [wav, mask, labels[0], labels[1], lens[0], lens[1]], named, params_l
+
+    def release():      # HybridLoss keeps the per-head losses WITH their graph (PCGrad): a stale graph pins the accumulators
+        loss_mod.last_ctc_per_head = None
+
+    return enc, fn, [wav, mask, labels[0], labels[1], lens[0], lens[1]], named, params_l, release
 
 
-def _eager(fn, inputs, params_l):
+def _eager(fn, inputs, params_l, release):
     for p in params_l:
         p.grad = None
     loss = fn(*inputs)
     loss.backward()
-    return loss.detach().clone(), [None if p.grad is None else p.grad.clone() for p in params_l]
+    out = loss.detach().clone(), [None if p.grad is None else p.grad.clone() for p in params_l]
+    del loss
+    release()
+    return out
 
 
 def _compare(ga, gb, tol=1e-4):
@@ -49,9 +56,9 @@ def _compare(ga, gb, tol=1e-4):
 
 def test_graphed_step_matches_eager_and_tracks_weight_updates(cuda):
     from mtasr_b200.graphs import GraphedTrainStep
-    enc, fn, inputs, named, params_l = _setup(cuda)
-    l_e, g_e = _eager(fn, inputs, params_l)
-    step = GraphedTrainStep(fn, inputs, params_l)
+    enc, fn, inputs, named, params_l, release = _setup(cuda)
+    l_e, g_e = _eager(fn, inputs, params_l, release)
+    step = GraphedTrainStep(fn, inputs, params_l, release=release)
     assert step.launches_per_replay > 50
     l_g = step(*inputs).clone()
     g_g = [None if p.grad is None else p.grad.clone() for p in params_l]
@@ -61,7 +68,7 @@ def test_graphed_step_matches_eager_and_tracks_weight_updates(cuda):
     inputs2 = list(inputs)
     inputs2[0] = inputs[0].flip(0).contiguous()
     inputs2[1] = inputs[1].flip(0).contiguous()
-    l_e2, g_e2 = _eager(fn, inputs2, params_l)
+    l_e2, g_e2 = _eager(fn, inputs2, params_l, release)
     l_g2 = step(*inputs2).clone()
     assert abs(l_e2.item() - l_e.item()) > 1e-6 * abs(l_e.item())
     assert abs(l_g2.item() - l_e2.item()) < 1e-5 * abs(l_e2.item())
@@ -70,7 +77,7 @@ def test_graphed_step_matches_eager_and_tracks_weight_updates(cuda):
     with torch.no_grad():
         for p in params_l:
             p.add_(0.01 * torch.randn_like(p))
-    l_e3, g_e3 = _eager(fn, inputs, params_l)
+    l_e3, g_e3 = _eager(fn, inputs, params_l, release)
     l_g3 = step(*inputs).clone()
     assert abs(l_e3.item() - l_e.item()) > 1e-5 * abs(l_e.item())
     assert abs(l_g3.item() - l_e3.item()) < 1e-5 * abs(l_e3.item())
@@ -81,10 +88,10 @@ def test_graphed_step_matches_eager_and_tracks_weight_updates(cuda):
 
 def test_graphed_step_with_dropout_draws_fresh_masks(cuda):
     from mtasr_b200.graphs import GraphedTrainStep
-    enc, fn, inputs, named, params_l = _setup(cuda, p_drop=0.1)
+    enc, fn, inputs, named, params_l, release = _setup(cuda, p_drop=0.1)
     enc.train()
     torch.manual_seed(3)
-    step = GraphedTrainStep(fn, inputs, params_l)
+    step = GraphedTrainStep(fn, inputs, params_l, release=release)
     a = step(*inputs).item()
     b = step(*inputs).item()
     assert a != b                                    # the generator advances per replay
