@@ -45,15 +45,14 @@ __device__ __forceinline__ void grid_arrive(unsigned int* bar) {
   __syncthreads();
   if (threadIdx.x == 0) atomicAdd(bar, 1u);
 }
-// A waiter that spins longer than g_spin_limit SM clocks traps (a missing co-resident CTA would otherwise hang the GPU
-// until the watchdog).  MTASR_LSTM_SPIN_TIMEOUT_MS sets the limit (default 2000 ms at ~2 GHz); 0 disables it -- needed
-// under ncu kernel replay, a debugger or GPU time-slicing, where a CTA can legitimately be descheduled for seconds.
-__device__ long long g_spin_limit = 4000000000LL;
-
-__device__ __forceinline__ void grid_wait(unsigned int* bar, unsigned int target) {
+// A waiter that spins longer than `limit` SM clocks traps (a missing co-resident CTA would otherwise hang the GPU until the
+// watchdog).  MTASR_LSTM_SPIN_TIMEOUT_MS sets the limit (default 2000 ms at ~2 GHz); 0 disables it -- needed under ncu
+// kernel replay, a debugger or GPU time-slicing, where a CTA can legitimately be descheduled for seconds.  The limit
+// travels as a kernel parameter (constant bank): read from a __device__ variable it added a dependent L2 round trip in
+// front of every barrier poll (lstm_bwd 7.4 -> 11.1 ms per cfg2 step, profiles/launch_summary_r2_v4.txt).
+__device__ __forceinline__ void grid_wait(unsigned int* bar, unsigned int target, long long limit) {
   if (threadIdx.x == 0) {
     unsigned int v;
-    const long long limit = g_spin_limit;
     long long t0 = clock64();
     unsigned int spins = 0;
     while (true) {
@@ -80,6 +79,7 @@ struct LstmFwdP {
   float* gates;               // (B,T,4Hs) activations i,f,g,o
   unsigned int* bar;
   int B, T, Hs, ldw, Bp;
+  long long spin_limit;       // grid_wait trap threshold in SM clocks (0 = never)
 };
 
 __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_kernel(const LstmFwdP p) {
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_kernel(const LstmFwdP p)
       }
     }
     if (t > 0) {
-      grid_wait(p.bar, gridDim.x * static_cast<unsigned>(t));
+      grid_wait(p.bar, gridDim.x * static_cast<unsigned>(t), p.spin_limit);
       for (int i = tid; i < B * (Hs / 8); i += LTHREADS) {
         const int b = i / (Hs / 8), kc = i % (Hs / 8);
         *reinterpret_cast<uint4*>(Hsm + b * rs + kc * 8) =
@@ -180,6 +180,7 @@ struct LstmBwdP {
   __nv_bfloat16* dgates;      // (B,T,4Hs) out, pre-activation gradients
   unsigned int* bar;
   int B, T, Hs, ldw, Bp;
+  long long spin_limit;       // grid_wait trap threshold in SM clocks (0 = never)
 };
 
 __global__ void __launch_bounds__(LTHREADS, 1) lstm_bwd_kernel(const LstmBwdP p) {
@@ -211,7 +212,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_bwd_kernel(const LstmBwdP p)
   for (int t = T - 1; t >= 0; --t) {
     if (t < T - 1) {
       ++step;
-      grid_wait(p.bar, gridDim.x * step);
+      grid_wait(p.bar, gridDim.x * step, p.spin_limit);
       float acc[4][4];
 #pragma unroll
       for (int m = 0; m < 4; ++m)
@@ -325,6 +326,7 @@ struct LstmBsP {
   unsigned int* bar;          // [S] group counters
   int B, T, Hs, ldw, G, U;
   int dbg;                    // timing experiments only (MTASR_LSTM_DBG): 1 skip MMA, 2 skip exchange load, 4 skip barrier
+  long long spin_limit;       // grid_wait trap threshold in SM clocks (0 = never)
 };
 
 template <int KPER>
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_bs_kernel(const LstmBsP 
     }
     float gsum[4] = {0.f, 0.f, 0.f, 0.f};
     if (t > 0) {
-      if (!(p.dbg & 4)) grid_wait(bar, static_cast<unsigned>(G) * static_cast<unsigned>(t));
+      if (!(p.dbg & 4)) grid_wait(bar, static_cast<unsigned>(G) * static_cast<unsigned>(t), p.spin_limit);
       if (!(p.dbg & 2))
       for (int i = tid; i < nb * (Hs / 8); i += LTHREADS) {
         const int b = i / (Hs / 8), kc = i % (Hs / 8);
@@ -519,7 +521,7 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_bwd_bs_kernel(const LstmBsP 
     }
     if (t < T - 1) {
       ++step;
-      grid_wait(bar, static_cast<unsigned>(G) * step);
+      grid_wait(bar, static_cast<unsigned>(G) * step, p.spin_limit);
       // all four chunks of dgates_{t+1} are requested at once (registers) so the L2 latency is paid once per step
       uint4 stage[4][4];
 #pragma unroll
@@ -659,15 +661,15 @@ static size_t lstm_bwd_smem(int Hs, int Bp) {
          static_cast<size_t>(9) * Bp * 8 * 4;
 }
 
-// Push MTASR_LSTM_SPIN_TIMEOUT_MS (once per process) into the device-side spin limit of grid_wait.
-static void lstm_sync_spin_limit() {
+// grid_wait trap threshold in SM clocks from MTASR_LSTM_SPIN_TIMEOUT_MS (default 2000 ms at ~2 GHz; 0 disables the trap).
+static long long lstm_spin_limit() {
+  static long long cycles = -1;
   static std::once_flag once;
   std::call_once(once, [] {
     const char* e = getenv("MTASR_LSTM_SPIN_TIMEOUT_MS");
-    if (!e) return;
-    const long long cycles = static_cast<long long>(atof(e) * 2.0e6);   // ~2 GHz SM clock
-    cudaMemcpyToSymbol(g_spin_limit, &cycles, sizeof(cycles));
+    cycles = e ? static_cast<long long>(atof(e) * 2.0e6) : 4000000000LL;
   });
+  return cycles;
 }
 
 static int lstm_check(int B, int T, int Hs, int ldw, const char* who) {
@@ -687,7 +689,6 @@ using namespace mtasr;
 extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw, int32_t B, int32_t T, int32_t Hs,
                               void* h_bf16, float* h_f32, float* c_all, float* gates, uint32_t* barrier, void* stream) {
   MTASR_CHECK_ARG(xg && whh_bf16 && h_bf16 && c_all && gates && barrier, "lstm_fwd: null pointer");
-  lstm_sync_spin_limit();
   cudaStream_t st0 = static_cast<cudaStream_t>(stream);
   {
     size_t smem_bs = 0;
@@ -699,6 +700,7 @@ extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw
       q.h_f32 = h_f32; q.c_all = c_all; q.gates = gates; q.bar = barrier;
       q.B = B; q.T = T; q.Hs = Hs; q.ldw = ldw; q.G = G; q.U = Hs / G;
       q.dbg = getenv("MTASR_LSTM_DBG") ? atoi(getenv("MTASR_LSTM_DBG")) : 0;
+      q.spin_limit = lstm_spin_limit();
       // unrolled instantiation when every warp owns exactly Hs/64 k-steps (Hs = 896 -> 14), generic loop otherwise
       void (*kern)(const LstmBsP) = (Hs == 896) ? lstm_fwd_bs_kernel<14> : lstm_fwd_bs_kernel<0>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bs)) != cudaSuccess)
@@ -713,6 +715,7 @@ extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw
   }
   if (int rc = lstm_check(B, T, Hs, ldw, "lstm_fwd")) return rc;
   LstmFwdP p;
+  p.spin_limit = lstm_spin_limit();
   p.xg = xg; p.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16); p.h_bf16 = reinterpret_cast<__nv_bfloat16*>(h_bf16);
   p.h_f32 = h_f32; p.c_all = c_all; p.gates = gates; p.bar = barrier;
   p.B = B; p.T = T; p.Hs = Hs; p.ldw = ldw; p.Bp = (B + 15) / 16 * 16;
@@ -732,7 +735,6 @@ extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw
 extern "C" int mtasr_lstm_bwd(const float* dh_out, const float* gates, const float* c_all, const void* whh_bf16, int32_t ldw,
                               int32_t B, int32_t T, int32_t Hs, void* dgates_bf16, uint32_t* barrier, void* stream) {
   MTASR_CHECK_ARG(dh_out && gates && c_all && whh_bf16 && dgates_bf16 && barrier, "lstm_bwd: null pointer");
-  lstm_sync_spin_limit();
   cudaStream_t st0 = static_cast<cudaStream_t>(stream);
   {
     size_t smem_bs = 0;
@@ -743,6 +745,7 @@ extern "C" int mtasr_lstm_bwd(const float* dh_out, const float* gates, const flo
       q.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16); q.c_all = const_cast<float*>(c_all); q.gates = const_cast<float*>(gates);
       q.dh_out = dh_out; q.dgates = reinterpret_cast<__nv_bfloat16*>(dgates_bf16); q.bar = barrier;
       q.B = B; q.T = T; q.Hs = Hs; q.ldw = ldw; q.G = G; q.U = Hs / G;
+      q.spin_limit = lstm_spin_limit();
       void (*kern)(const LstmBsP) = (Hs == 896) ? lstm_bwd_bs_kernel<7> : lstm_bwd_bs_kernel<0>;   // Hs/128 k-steps per warp and chunk
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bs)) != cudaSuccess)
         return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: cannot set smem attribute");
@@ -756,6 +759,7 @@ extern "C" int mtasr_lstm_bwd(const float* dh_out, const float* gates, const flo
   }
   if (int rc = lstm_check(B, T, Hs, ldw, "lstm_bwd")) return rc;
   LstmBwdP p;
+  p.spin_limit = lstm_spin_limit();
   p.dh_out = dh_out; p.gates = gates; p.c_all = c_all; p.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16);
   p.dgates = reinterpret_cast<__nv_bfloat16*>(dgates_bf16); p.bar = barrier;
   p.B = B; p.T = T; p.Hs = Hs; p.ldw = ldw; p.Bp = (B + 15) / 16 * 16;
