@@ -581,7 +581,23 @@ def main_ours(args):
                 "gflop_per_audio_s": fl["total"] / args.seconds / 1e9}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Teardown.  A captured step holds NCCL kernels inside a CUDA graph; destroying the communicator while the graph
+        # object is alive blocked for minutes in the 2-GPU run (the JSON line had already been printed).  Release the graph
+        # first, and never let a stuck teardown turn a finished measurement into a time-out: the process leaves after 20 s.
+        graphed[0] = None
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        killer = threading.Timer(20.0, lambda: os._exit(0))
+        killer.daemon = True
+        killer.start()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        finally:
+            killer.cancel()
 
 
 if __name__ == "__main__":

@@ -217,3 +217,34 @@ def synth_batch(B: int, S: int, n_spk: int, vocab: int, seed: int = 1234, varlen
         labels.append(y)
         lab_lens.append(L)
     return wav, mask, labels, lab_lens
+
+
+def make_composite_config(v_txt: int = 40, separator_hidden: int = 96, n_spk: int = 2, enc_kind: str = "tiny_large", dec_hidden: int = 128,
+                          dec_layers: int = 2, dec_heads: int = 2, dec_kv_heads: int = 2, dec_inter: int = 256, **over):
+    """SpeechEncoderDecoderConfig the way ref:utils/create_from_pretrained.py:202-270 assembles it (non-instruct): text ids
+    0..v_txt-1, <sc> = v_txt, <pad> = v_txt + 1 (decoder vocabulary v_txt + 2; the CTC heads add the blank as the last id)."""
+    from transformers import LlamaConfig
+    from transformers.models.speech_encoder_decoder.configuration_speech_encoder_decoder import SpeechEncoderDecoderConfig
+    enc_cfg = make_config(enc_kind)
+    dec_cfg = LlamaConfig(vocab_size=v_txt + 2, hidden_size=dec_hidden, intermediate_size=dec_inter, num_hidden_layers=dec_layers,
+                          num_attention_heads=dec_heads, num_key_value_heads=dec_kv_heads, max_position_embeddings=2048,
+                          pad_token_id=v_txt + 1, bos_token_id=1, eos_token_id=2)
+    dec_cfg.instruct = False
+    dec_cfg.cross_attention_hidden_size = None
+    dec_cfg.sc_token_id = v_txt
+    dec_cfg.ignore_token_id = -100
+    cfg = SpeechEncoderDecoderConfig.from_encoder_decoder_configs(enc_cfg, dec_cfg)
+    cfg.talker_ctc = True
+    cfg.talker_numbers = n_spk
+    cfg.separator_hidden = separator_hidden
+    cfg.ctc_alpha = 0.7
+    cfg.train_mode = "ctc"
+    cfg.pad_token_id = v_txt + 1
+    cfg.sc_token_id = v_txt
+    cfg.ignore_token_id = -100
+    cfg.eos_token_id = 2
+    cfg.decoder_start_token_id = 1
+    cfg.instruct = False
+    for k, v in over.items():
+        setattr(cfg, k, v)
+    return cfg

@@ -185,3 +185,23 @@ def test_spec_augment_matches_reference_golden(case):
     cfg.apply_spec_augment = False
     model.train()
     assert torch.equal(model._mask_hidden_states(h, attention_mask=fm), h0)
+
+
+def test_composite_state_dict_matches_reference_and_unsupported_options_raise():
+    """Row f1 on the host: the B200 composite has exactly the reference composite's parameter names and shapes (fixture written
+    by the reference class itself), and LLM-side options outside the hot path are refused loudly."""
+    from oracle.model_ref import make_composite_config
+    from mtasr_b200.composite import SpeechEncoderDecoderModelLlama, shift_tokens_right
+    g = np.load(os.path.join(GOLDEN, "composite_tiny.npz"))
+    cfg = make_composite_config(int(g["meta"][0]))
+    model = SpeechEncoderDecoderModelLlama(cfg)
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("p:")}
+    assert set(sd) == set(model.state_dict())
+    model.load_state_dict(sd, strict=True)
+    assert model.ctc_blank_id == int(g["meta"][0]) + 3 and model.serialized_ctc[0].ctc_loss.blank == int(g["meta"][0]) + 2
+    assert shift_tokens_right(torch.tensor([[5, 6, -100]]), 41, 1).tolist() == [[1, 5, 6]]
+    for opt in ({"instruct": True}, {"decoder_cross_attention": True}, {"ctc_bridge": True, "ctc_bridge_type": "raw"}):
+        with pytest.raises(NotImplementedError):
+            SpeechEncoderDecoderModelLlama(make_composite_config(40, **opt))
+    with pytest.raises(Exception):           # the product path has no CPU fallback
+        model(inputs=torch.zeros(1, 4000), labels=torch.tensor([[3, 40, 4]]))
