@@ -185,6 +185,16 @@ int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t
                         const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D, float* dx_f32,
                         void* dx_bf16, float* dgamma, float* dbeta, void* stream);
 int mtasr_cast_f32_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
+/* Label splitter of ref:utils/split_labels_by_sc.py:21-75 on the device: labels (B, L) i64 with row stride ld -> out (K, B, L) i64
+ * (must arrive filled with the pad value), lens (K, B) i64, status (3) i32 = {smallest failing row, INT32_MAX if none; kind:
+ * 1 = separator count != K-1, 2 = empty segment while !allow_empty; the count / slot seen} (must arrive as {INT32_MAX,0,0}). */
+int mtasr_split_labels(const int64_t* labels, int32_t B, int32_t L, int64_t ld, int32_t K, int64_t sep_id, int64_t pad_id,
+                       int32_t has_pad, int64_t ignore_id, int32_t has_ignore, int64_t end_id, int32_t has_end, int32_t allow_empty,
+                       int64_t* out, int64_t* lens, int32_t* status, void* stream);
+/* PCGrad projection of ref:src/trainer_seq2seq.py:1116-1124 on flat fp32 gradient vectors, no host synchronisation:
+ * dots: out2 = {<gi,gj>, <gj,gj>};  project: gi -= (dots2[0] < 0 ? dots2[0] / (dots2[1] + 1e-12) : 0) * gj. */
+int mtasr_pcgrad_dots(const float* gi, const float* gj, int64_t n, float* out2, void* stream);
+int mtasr_pcgrad_project(float* gi, const float* gj, int64_t n, const float* dots2, void* stream);
 /* Dropout as a stand-alone pass: y[r][c] = x[r][c] * mask(seed, site, r * ld_even + c) * 65536 / keep16 for r < rows,
  * c < cols (contiguous rows; ld_even = cols rounded up to even), x f32 or bf16 -> y f32 or bf16.  seed: two u32 words in
  * device memory drawn from torch's CUDA generator; the mask is a pure function of (seed, site, index): forward, backward and

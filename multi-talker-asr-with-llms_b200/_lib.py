@@ -87,6 +87,9 @@ SIGNATURES = {
     "mtasr_conv0_fwd": (C.c_int, [_P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "mtasr_groupnorm_gelu": (C.c_int, [_P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P]),
     "mtasr_groupnorm_gelu_f32": (C.c_int, [_P, _P, _P, _F, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "mtasr_split_labels": (C.c_int, [_P, _I32, _I32, _I64, _I32, _I64, _I64, _I32, _I64, _I32, _I64, _I32, _I32, _P, _P, _P, _P]),
+    "mtasr_pcgrad_dots": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "mtasr_pcgrad_project": (C.c_int, [_P, _P, _I64, _P, _P]),
     "mtasr_dropout": (C.c_int, [_P, _I32, _I64, _I64, _P, C.c_uint32, C.c_uint32, _P, _I32, _P]),
     "mtasr_split_bf16": (C.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P]),
     "mtasr_attn_softmax_fwd_split": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _I32, _P, _P]),

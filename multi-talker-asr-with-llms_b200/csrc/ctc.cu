@@ -490,6 +490,49 @@ __global__ void ctc_scatter_rows_kernel(const float* __restrict__ dwg, const flo
   if (threadIdx.x == 0 && db && dbg) atomicAdd(db + v, dbg[static_cast<long long>(b) * Lp + c]);
 }
 
+// ------------------------------------------------------------------------------------------------ label splitter
+// ref:utils/split_labels_by_sc.py:21-75 on the device: per row, cut at the first `end_id`, split at `sep_id`
+// into exactly K segments, drop `ignore_id` everywhere, right-trim `pad_id`; out (K, B, L) arrives filled with the pad value
+// and receives the kept tokens, lens (K, B) the segment lengths.  status[0] = smallest failing row (INT_MAX = none),
+// status[1] = failure kind of that row's last writer (1 wrong separator count, 2 empty segment), status[2] = the separator
+// count / slot it saw.  One thread per row: the scan is sequential and a few hundred tokens long.
+__global__ void split_labels_kernel(const long long* __restrict__ labels, int B, int L, long long ld, int K, long long sep_id,
+                                    long long pad_id, int has_pad, long long ignore_id, int has_ignore, long long end_id, int has_end,
+                                    int allow_empty, long long* __restrict__ out, long long* __restrict__ lens, int* __restrict__ status) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const long long* row = labels + static_cast<long long>(b) * ld;
+  int seg = 0, n = 0, last_keep = 0, nsep = 0;
+  auto close = [&]() {
+    if (seg < K) lens[static_cast<long long>(seg) * B + b] = has_pad ? last_keep : n;
+  };
+  for (int j = 0; j < L; ++j) {
+    const long long tok = row[j];
+    if (has_end && tok == end_id) break;
+    if (tok == sep_id) {
+      close();
+      ++seg; ++nsep; n = 0; last_keep = 0;
+      continue;
+    }
+    if (has_ignore && tok == ignore_id) continue;
+    if (seg < K) out[(static_cast<long long>(seg) * B + b) * L + n] = tok;
+    ++n;
+    if (tok != pad_id) last_keep = n;
+  }
+  close();
+  for (int s2 = seg + 1; s2 < K; ++s2) lens[static_cast<long long>(s2) * B + b] = 0;
+  int kind = 0, info = 0;
+  if (nsep != K - 1) { kind = 1; info = nsep; }
+  else if (!allow_empty) {
+    for (int s2 = 0; s2 < K; ++s2)
+      if (lens[static_cast<long long>(s2) * B + b] == 0) { kind = 2; info = s2; break; }
+  }
+  if (kind) {
+    const int prev = atomicMin(status, b);
+    if (b <= prev) { status[1] = kind; status[2] = info; }   // the smallest failing row reports (ties cannot happen)
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ token segments
 // Segmentation of ref:models/mt_ctctoken_builder.py:56-157 on the greedy path: a segment is a maximal run of one
 // non-blank token and is EMITTED when a blank follows it or the valid region ends; a token change without a blank
@@ -711,6 +754,19 @@ extern "C" int mtasr_ctc_scatter_rows(const float* dwg, const float* dbg, const 
       dwg, dbg, reinterpret_cast<const long long*>(ys), reinterpret_cast<const long long*>(ylens), B, Lp, D, ys_ld, blank, V, dw, db);
   g_launches.fetch_add(1);
   MTASR_CHECK_LAUNCH("ctc_scatter_rows");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_split_labels(const int64_t* labels, int32_t B, int32_t L, int64_t ld, int32_t K, int64_t sep_id, int64_t pad_id,
+                                  int32_t has_pad, int64_t ignore_id, int32_t has_ignore, int64_t end_id, int32_t has_end,
+                                  int32_t allow_empty, int64_t* out, int64_t* lens, int32_t* status, void* stream) {
+  MTASR_CHECK_ARG(labels && out && lens && status && B > 0 && L >= 0 && K > 0 && ld >= L, "split_labels: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  split_labels_kernel<<<(B + 63) / 64, 64, 0, st>>>(reinterpret_cast<const long long*>(labels), B, L, ld, K, sep_id, pad_id, has_pad,
+                                                    ignore_id, has_ignore, end_id, has_end, allow_empty,
+                                                    reinterpret_cast<long long*>(out), reinterpret_cast<long long*>(lens), status);
+  g_launches.fetch_add(1);
+  MTASR_CHECK_LAUNCH("split_labels");
   return MTASR_OK;
 }
 

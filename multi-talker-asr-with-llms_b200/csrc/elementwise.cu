@@ -229,6 +229,31 @@ __device__ __forceinline__ void split_parts(const float (&t)[8], float (&p1)[8],
     p3[j] = r1 - p2[j];
   }
 }
+// PCGrad projection (ref:src/trainer_seq2seq.py:1116-1124) without host round trips: out2 = {<gi, gj>, <gj, gj>} in one pass, then
+// gi -= (dot < 0 ? dot / (norm2 + 1e-12) : 0) * gj with the scalars read from device memory (the reference branches on the
+// host: `if dot < 0`, one synchronisation per head pair).
+__global__ void __launch_bounds__(256) pcgrad_dots_kernel(const float* __restrict__ gi, const float* __restrict__ gj, long long n,
+                                                          float* __restrict__ out2) {
+  __shared__ float red[2][33];
+  double d = 0.0, q = 0.0;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float a = gi[i], b = gj[i];
+    d += static_cast<double>(a) * b;
+    q += static_cast<double>(b) * b;
+  }
+  const float df = block_sum(static_cast<float>(d), red[0]);
+  const float qf = block_sum(static_cast<float>(q), red[1]);
+  if (threadIdx.x == 0) { atomicAdd(out2, df); atomicAdd(out2 + 1, qf); }
+}
+__global__ void __launch_bounds__(256) pcgrad_project_kernel(float* __restrict__ gi, const float* __restrict__ gj, long long n,
+                                                             const float* __restrict__ dots2) {
+  const float dot = dots2[0];
+  if (!(dot < 0.f)) return;
+  const float alpha = dot / (dots2[1] + 1e-12f);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
+    gi[i] -= alpha * gj[i];
+}
+
 // stand-alone dropout pass (one thread per element; the fused sites live in the GEMM / attention kernels)
 __global__ void dropout_kernel(const void* __restrict__ x, int x_dtype, long long rows, long long cols, DropP d, void* __restrict__ y,
                                int y_dtype) {
@@ -945,6 +970,24 @@ extern "C" int mtasr_attn_softmax_fwd_split(const float* S, const float* gate, c
       S, gate, table, klen, B, H, T, Tp, scale, reinterpret_cast<__nv_bfloat16*>(Ps), terms);
   MTASR_COUNT_LAUNCH();
   MTASR_CHECK_LAUNCH("attn_softmax_fwd_split");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_pcgrad_dots(const float* gi, const float* gj, int64_t n, float* out2, void* stream) {
+  MTASR_CHECK_ARG(gi && gj && out2 && n > 0, "pcgrad_dots: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (cudaMemsetAsync(out2, 0, 2 * sizeof(float), st) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "pcgrad_dots: memset failed");
+  pcgrad_dots_kernel<<<num_sms() * 4, 256, 0, st>>>(gi, gj, n, out2);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("pcgrad_dots");
+  return MTASR_OK;
+}
+
+extern "C" int mtasr_pcgrad_project(float* gi, const float* gj, int64_t n, const float* dots2, void* stream) {
+  MTASR_CHECK_ARG(gi && gj && dots2 && n > 0, "pcgrad_project: bad arguments");
+  pcgrad_project_kernel<<<num_sms() * 4, 256, 0, static_cast<cudaStream_t>(stream)>>>(gi, gj, n, dots2);
+  MTASR_COUNT_LAUNCH();
+  MTASR_CHECK_LAUNCH("pcgrad_project");
   return MTASR_OK;
 }
 

@@ -88,9 +88,27 @@ def build_multi_ctc_prefix_from_heads(ctc_transcription_list: List[torch.Tensor]
 def split_k_speakers_and_lengths(labels: torch.Tensor, k_speakers: int, sep_id: int, pad_token_id: int,
                                  ignore_id: Optional[int] = -100, end_token_id: Optional[int] = -100,
                                  allow_empty_segment: bool = True):
-    """Split SOT label rows at `sep_id` into K per-speaker right-padded targets + lengths.  One device->host copy of
-    the (B,L) label matrix and one host->device copy per output, instead of several `.item()`s per sample."""
+    """Split SOT label rows at `sep_id` into K per-speaker right-padded targets + lengths.
+
+    CUDA labels (the training path: the collator's labels are on the device by the time the composite model splits them)
+    never leave the device: one thread-per-row kernel does the cut / split / trim (csrc/ctc.cu split_labels_kernel, SURVEY
+    row f3) and the only host traffic is ONE read of K+3 integers -- the per-head maximum lengths, which fix the output
+    shapes the reference API promises, and the error word (the reference raises ValueError for a wrong separator count or
+    an empty segment; it reads several `.item()`s per sample).  CPU labels are split on the host with numpy."""
     dev = labels.device
+    if labels.is_cuda:
+        B = labels.shape[0]
+        out, lens, status = K.split_labels(labels.detach(), k_speakers, sep_id, pad_token_id, ignore_id, end_token_id,
+                                           allow_empty_segment)
+        host = torch.cat([status.to(torch.int64), lens.max(dim=1).values if B else lens.new_zeros(k_speakers)]).tolist()
+        bad_row, kind, info = host[0], host[1], host[2]
+        if bad_row < B:
+            if kind == 1:
+                raise ValueError(f"[split_k_speakers_and_lengths_strict] Sample index {bad_row}: found {info} separators "
+                                 f"(token id={sep_id}) but expected {k_speakers - 1}. labels[b].shape={tuple(labels[bad_row].shape)}")
+            raise ValueError(f"[split_k_speakers_and_lengths_strict] Sample {bad_row}, speaker-slot {info} resulted in an "
+                             f"empty segment while allow_empty_segment=False.")
+        return ([out[i, :, :host[3 + i]].contiguous() for i in range(k_speakers)], [lens[i] for i in range(k_speakers)])
     rows = labels.detach().to("cpu", torch.int64).numpy()
     B = rows.shape[0]
     segs: List[List[np.ndarray]] = [[] for _ in range(k_speakers)]

@@ -507,6 +507,29 @@ def segment_mean_bwd(dout: torch.Tensor, ss, se, n, T: int):
     return dx
 
 
+def split_labels(labels: torch.Tensor, K: int, sep_id: int, pad_id, ignore_id, end_id, allow_empty: bool):
+    """Device-side label splitter (mtasr_split_labels): -> out (K,B,L) i64, lens (K,B) i64, status (3) i32; no host sync."""
+    B, L = labels.shape
+    labels = labels.to(torch.int64)
+    if labels.stride(1) != 1:
+        labels = labels.contiguous()
+    fill = int(pad_id) if pad_id is not None else 0
+    out = torch.full((K, B, max(L, 1)), fill, device=labels.device, dtype=torch.int64)
+    lens = torch.empty(K, B, device=labels.device, dtype=torch.int64)
+    status = torch.tensor([2 ** 31 - 1, 0, 0], device=labels.device, dtype=torch.int32)
+    opt = lambda v: (int(v), 1) if v is not None else (0, 0)
+    (pv, hp), (iv, hi), (ev, he) = opt(pad_id), opt(ignore_id), opt(end_id)
+    check(_lib.load().mtasr_split_labels(_p(labels), B, L, labels.stride(0), K, int(sep_id), pv, hp, iv, hi, ev, he, int(bool(allow_empty)),
+                                         _p(out), _p(lens), _p(status), _stream()), "mtasr_split_labels")
+    return out, lens, status
+
+
+def pcgrad_project_(gi: torch.Tensor, gj: torch.Tensor, scratch: torch.Tensor) -> None:
+    """gi -= (<gi,gj> < 0 ? <gi,gj> / (<gj,gj> + 1e-12) : 0) * gj on flat fp32 vectors, decided on the device."""
+    check(_lib.load().mtasr_pcgrad_dots(_p(gi), _p(gj), gi.numel(), _p(scratch), _stream()), "mtasr_pcgrad_dots")
+    check(_lib.load().mtasr_pcgrad_project(_p(gi), _p(gj), gi.numel(), _p(scratch), _stream()), "mtasr_pcgrad_project")
+
+
 def ctc_gather_cols(dense, ys, ylens, Lp, blank):
     B, T, V = dense.shape
     out = torch.empty(B, T, Lp, device=dense.device, dtype=torch.float32)
