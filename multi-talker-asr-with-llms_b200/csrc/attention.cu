@@ -248,14 +248,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
         for (int c = 0; c < 2; ++c) {
           uint32_t(&cur)[32] = c ? vb : va;
           const int kb = k0 + c * 32;
+          float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // independent chains (latency-bound warps)
           if (kb + 32 <= kl) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) m = fmaxf(m, fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]));
+            for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]));
           } else if (kb < kl) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (kb + i < kl) m = fmaxf(m, fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]));
+              if (kb + i < kl) mx4[i & 3] = fmaxf(mx4[i & 3], fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]));
           }
+          m = fmaxf(m, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])));
         }
       }
       xch_s[gid * 128 + r] = m;
@@ -295,8 +297,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
             for (int i = 0; i < 32; ++i)
               e[i] = kb + i < kl ? ex2_approx(fmaf(__uint_as_float(cur[i]), p.scale_log2, fmaf(g, trel[kb + i], -mm))) : 0.f;
           }
+          {
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < 32; ++i) l += e[i];
+            for (int i = 0; i < 32; ++i) s4[i & 3] += e[i];
+            l += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          }
           if (DROP) {   // the row sum (softmax denominator) is over the UNDROPPED probabilities; P V uses the dropped ones
             float dm[32];
             attn_drop_mults<32>(drop_s0, drop_s1, p.drop, (static_cast<unsigned long long>(b) * p.H + h) * p.T + qc, kb, dm);
@@ -534,7 +540,9 @@ attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP 
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[grp]);   // S is in registers: the buffer may take tile j + 2
         // z (log2 units) in place, masked keys -> -inf; tile-local max of this half
-        float mh = -INFINITY;
+        // four independent max chains (a single running max is a 64-deep dependent FMNMX chain per thread and tile: the
+        // softmax warps are latency-bound, not issue-bound)
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           uint32_t(&cur)[32] = c ? vb : va;
@@ -544,7 +552,7 @@ attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP 
             for (int i = 0; i < 32; ++i) {
               const float z = fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]);
               cur[i] = __float_as_uint(z);
-              mh = fmaxf(mh, z);
+              mx4[i & 3] = fmaxf(mx4[i & 3], z);
             }
           } else {
 #pragma unroll
@@ -552,10 +560,11 @@ attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP 
               float z = -INFINITY;
               if (kb + i < kl) z = fmaf(__uint_as_float(cur[i]), p.scale_log2, g * trel[kb + i]);
               cur[i] = __float_as_uint(z);
-              mh = fmaxf(mh, z);
+              mx4[i & 3] = fmaxf(mx4[i & 3], z);
             }
           }
         }
+        const float mh = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         // the two halves of a tile share one maximum (one scale per row of P V): exchange through shared memory
         float* xs = xm_s + xset * 512 + grp * 256;
         xs[sub * 128 + r] = mh;
@@ -573,8 +582,12 @@ attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP 
           float e[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) e[i] = ex2_approx(__uint_as_float(cur[i]) - mm);   // exp2(-inf) = 0 for masked keys
+          {
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};   // four independent partial sums instead of one 32-deep FADD chain
 #pragma unroll
-          for (int i = 0; i < 32; ++i) lh += e[i];
+            for (int i = 0; i < 32; ++i) s4[i & 3] += e[i];
+            lh += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          }
           if (DROP) {   // denominator over the undropped probabilities, P V over the dropped ones
             float dm[32];
             attn_drop_mults<32>(drop_s0, drop_s1, p.drop, (static_cast<unsigned long long>(b) * p.H + h) * p.T + qc, k0 + c * 32, dm);
@@ -898,6 +911,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           // takes P o M, and delta = rowsum(dO o O) is unchanged
           float dm[16];
           if (DROP) attn_drop_mults<16>(drop_s0, drop_s1, p.drop, static_cast<unsigned long long>(bh) * p.T + qc, kb, dm);
+          float dg4[4] = {0.f, 0.f, 0.f, 0.f};   // independent partial sums of the gate gradient (no 64-deep FFMA chain)
           if (p.dbg & 4) {   // timing experiment: no per-element math
 #pragma unroll
             for (int e = 0; e < 16; ++e) { pe[e] = __uint_as_float(sv[e]); de[e] = __uint_as_float(dv[e]); }
@@ -908,7 +922,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
               const float pv = ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, fmaf(g, t, nlse2)));
               const float dpv = DROP ? __uint_as_float(dv[e]) * dm[e] : __uint_as_float(dv[e]);
               const float dz = pv * (dpv - delta);
-              dg = fmaf(dz, t, dg);
+              dg4[e & 3] = fmaf(dz, t, dg4[e & 3]);
               pe[e] = DROP ? pv * dm[e] : pv;
               de[e] = dz * p.scale;
             }
@@ -921,11 +935,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
               const float pv = ok ? ex2_approx(fmaf(__uint_as_float(sv[e]), p.scale_log2, fmaf(g, t, nlse2))) : 0.f;
               const float dpv = DROP ? __uint_as_float(dv[e]) * dm[e] : __uint_as_float(dv[e]);
               const float dz = pv * (dpv - delta);
-              dg = fmaf(dz, t, dg);
+              dg4[e & 3] = fmaf(dz, t, dg4[e & 3]);
               pe[e] = DROP ? pv * dm[e] : pv;
               de[e] = dz * p.scale;
             }
           }
+          dg += (dg4[0] + dg4[1]) + (dg4[2] + dg4[3]);
 #pragma unroll
           for (int g16 = 0; g16 < 2; ++g16) {
             const uint32_t off = swz128(static_cast<uint32_t>(r * 128 + c * 32 + g16 * 16));
