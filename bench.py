@@ -33,6 +33,7 @@ UNIT = "audio-s/s"
 # over 8 GPUs = 8 per GPU)
 PRESETS = {"cfg2": dict(speakers=2, seconds=10.0, batch=32, mode="train"),
            "cfg3": dict(speakers=3, seconds=15.0, batch=32, mode="train"),
+           "cfg4": dict(speakers=2, seconds=10.0, batch=16, mode="sot"),
            "cfg5": dict(speakers=3, seconds=30.0, batch=8, mode="infer")}
 
 
@@ -48,9 +49,10 @@ def parse():
     ap.add_argument("--layers", type=int, default=0, help="debug only: override the number of encoder layers")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+    ap.add_argument("--mode", default="train", choices=["train", "infer", "sot"],
                     help="train: fwd+bwd of the serialized-CTC loss (the headline metric); infer: encoder + separator + greedy "
-                         "CTC argmax + collapse (BASELINE config 5 shape), not the headline")
+                         "CTC argmax + collapse (BASELINE config 5 shape); sot: hybrid fwd+bwd of the composite model with the "
+                         "'ctcprompt' bridge and a LLaMA-3.2-1B-shaped random decoder (BASELINE config 4); neither is the headline")
     ap.add_argument("--profile-run", action="store_true", help="ncu helper: 1 warm-up + 1 step, no e2e/roofline/cpu legs")
     ap.add_argument("--config", default=None, choices=sorted(PRESETS),
                     help="BASELINE.json configuration preset (sets --speakers/--seconds/--batch/--mode); default = cfg2, the headline")
@@ -307,8 +309,10 @@ def workload_name(args):
     if args.layers:
         return f"DEBUG {args.layers}-layer encoder"
     shape = (args.speakers, args.seconds, args.mode)
-    tag = {(2, 10.0, "train"): "cfg2", (3, 15.0, "train"): "cfg3", (3, 30.0, "infer"): "cfg5"}.get(shape, "custom")
-    what = "fwd+bwd, feature encoder frozen" if args.mode == "train" else "forward + greedy CTC argmax + collapse (no backward)"
+    tag = {(2, 10.0, "train"): "cfg2", (3, 15.0, "train"): "cfg3", (3, 30.0, "infer"): "cfg5", (2, 10.0, "sot"): "cfg4"}.get(shape, "custom")
+    what = {"train": "fwd+bwd, feature encoder frozen", "infer": "forward + greedy CTC argmax + collapse (no backward)",
+            "sot": "composite model (ctcprompt bridge, LLaMA-3.2-1B-shaped random decoder from stock transformers under bf16 "
+                   "autocast), hybrid loss fwd+bwd, feature encoder frozen"}[args.mode]
     return (f"{tag}: WavLM-Large + Separator(896) + serialized CTC ({args.speakers}mix), {args.seconds:g} s 16 kHz, {what}")
 
 
@@ -357,10 +361,29 @@ def main_ours(args):
     cfg = wavlm_config("large", **over)
     S = int(args.seconds * 16000)
     B = args.batch
-    model = SerializedCTCPath(cfg, talker_numbers=args.speakers, separator_hidden=896, vocab_size=V_LLAMA3_CTC - 1).to(dev)
+    if args.mode == "sot":
+        # BASELINE configs[3]: the full SOT pipeline on the new encoder / CTC path (mtasr_b200.composite)
+        from transformers import LlamaConfig
+        from transformers.models.speech_encoder_decoder.configuration_speech_encoder_decoder import SpeechEncoderDecoderConfig
+        from mtasr_b200.composite import SpeechEncoderDecoderModelLlama
+        vdec = V_LLAMA3_CTC - 1                        # 128256 text ids + <sc> + <pad>
+        dcfg = LlamaConfig(vocab_size=vdec, hidden_size=2048, intermediate_size=8192, num_hidden_layers=16, num_attention_heads=32,
+                           num_key_value_heads=8, max_position_embeddings=4096, pad_token_id=vdec - 1, bos_token_id=128000,
+                           eos_token_id=128001)
+        ccfg = SpeechEncoderDecoderConfig.from_encoder_decoder_configs(cfg, dcfg)
+        for k, v in dict(talker_ctc=True, talker_numbers=args.speakers, separator_hidden=896, ctc_alpha=0.7, train_mode="hybrid",
+                         pad_token_id=vdec - 1, sc_token_id=vdec - 2, ignore_token_id=-100, eos_token_id=128001,
+                         decoder_start_token_id=128000, instruct=False, ctc_bridge=True, ctc_bridge_type="ctcprompt").items():
+            setattr(ccfg, k, v)
+        with torch.device(dev):
+            model = SpeechEncoderDecoderModelLlama(ccfg)
+        model.release_graph = lambda: setattr(model.losses, "last_ctc_per_head", None)
+    else:
+        model = SerializedCTCPath(cfg, talker_numbers=args.speakers, separator_hidden=896, vocab_size=V_LLAMA3_CTC - 1).to(dev)
     model.encoder.freeze_feature_encoder()
-    for p in model.encoder.adapter.parameters():       # the serialized-CTC loss does not depend on the adapter branch
-        p.requires_grad_(False)
+    if args.mode != "sot":
+        for p in model.encoder.adapter.parameters():   # the serialized-CTC loss does not depend on the adapter branch
+            p.requires_grad_(False)
     model.eval()      # headline: dropout 0 / SpecAugment off in BOTH arms (eval-mode step; gradients still flow)
     if args.dropout > 0 and args.mode == "train":
         model.train()  # fused Philox-free counter-based dropout in the GEMM epilogues / attention kernels, LSTM dropout 0.2
@@ -384,6 +407,7 @@ def main_ours(args):
 
     wav, mask, labels, lens = synth_batch(B, S, args.speakers, V_LLAMA3_CTC, seed=1234 + rank)
     host = [wav.pin_memory(), mask.pin_memory()] + [y.pin_memory() for y in labels] + [l.pin_memory() for l in lens]
+    sot_host = [[labels[k][b, :int(lens[k][b])].tolist() for b in range(B)] for k in range(args.speakers)]
     h2d_bytes = sum(t.numel() * t.element_size() for t in host)
     ns = args.speakers
 
@@ -400,6 +424,22 @@ def main_ours(args):
             return ids.sum().float()
         if graphed[0] is not None:
             return graphed[0](w, m, *ys, *yl)
+        if args.mode == "sot":
+            for p in model.parameters():
+                p.grad = None
+            # SOT labels: speaker 1 tokens, <sc>, speaker 2 tokens ..., -100 padded (ref:src/data_collator.py:47-50)
+            rows = []
+            for b in range(w.shape[0]):
+                r = []
+                for k in range(ns):
+                    r += sot_host[k][b] + ([model.sc_token_id] if k + 1 < ns else [])
+                rows.append(r)
+            L = max(len(r) for r in rows)
+            lab = torch.tensor([r + [-100] * (L - len(r)) for r in rows], device=w.device)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = model(inputs=w, attention_mask=m, labels=lab).loss
+            loss.backward()
+            return loss
         for p in model.parameters():
             p.grad = None
         if reducer is not None:
@@ -525,7 +565,8 @@ def main_ours(args):
     torch.cuda.synchronize()
     gemm_ms, exec_flops, gemm_launches = K.profile_end()
     graphed[0] = g_keep
-    fl = algorithmic_flops(cfg, S, args.speakers, 896, V_LLAMA3_CTC, backward=args.mode == "train")
+    fl = algorithmic_flops(cfg, S, args.speakers, 896, V_LLAMA3_CTC, backward=args.mode != "infer",
+                           adapter_backward=args.mode == "sot")   # (the decoder's own FLOPs run in library kernels: not counted)
     alg_step = fl["total"] * B
     # the QK^T / PV contractions run in the fused attention kernels and the recurrent half of the LSTM in the persistent
     # LSTM kernels, not in the GEMM kernel: not credited to it
@@ -573,7 +614,8 @@ def main_ours(args):
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     if rank == 0:
-        line = {"metric": METRIC if args.mode == "train" else "encoder+greedy-CTC forward audio-sec/s", "value": world * B * args.seconds * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+        line = {"metric": {"train": METRIC, "infer": "encoder+greedy-CTC forward audio-sec/s",
+                           "sot": "full SOT (ctcprompt) hybrid fwd+bwd audio-sec/s"}[args.mode], "value": world * B * args.seconds * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(args, B, world), "roofline": roof, "cpu_baseline": cpu, "stock_torch_gpu": stock, "e2e": e2e,

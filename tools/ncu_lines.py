@@ -9,6 +9,12 @@ last_main = None
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr, data = rows[1], rows[2:]
+# several profiled launches in one report: keep the first section only
+for i, r in enumerate(data):
+    if r and r[0] == "Kernel Name":
+        data = data[:i]
+        break
+data = [r for r in data if len(r) == len(hdr)]
 ix = {k: i for i, k in enumerate(hdr)}
 base = int(data[0][ix["Address"]], 16)
 tmp = tempfile.mkdtemp()
