@@ -46,6 +46,7 @@ struct GemmKP {
   int a_use0, a_use1, b_use0, b_use1;  // 0 => operand broadcast over that batch dim (coordinate forced to 0)
   int m_tiles, n_tiles, num_tiles, num_kb;
   int n_fast;                          // tile rasterisation: 1 = consecutive tiles walk the N tiles of one M tile first
+  int tail_start;                      // tiles >= tail_start are HALF tiles (block_n / 2 columns): see decode_tile; = num_tiles if unused
   int splits, kb_per_split;            // split-K (fp32 TMA reduce-add into a pre-zeroed C) for launches with few tiles
   int stages, stage_bytes;             // smem ring geometry (host-chosen to fit the staging buffers)
   int tma_epi;                         // 1: outputs leave through swizzled smem staging + TMA tiled stores
@@ -175,6 +176,7 @@ __device__ __forceinline__ void stg_load8(const uint8_t* buf, int dtype, int row
 
 struct TileCoord {
   int m_tile, n_tile, b0, b1, kb0, kb1;
+  int n0, bn;   // first column and width of this tile (bn = block_n, or block_n / 2 for a tail half tile)
 };
 __device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, int tile) {
   // Tiles that run at the same time (consecutive indices, one per SM or SM pair) should share the LARGER operand slab:
@@ -182,7 +184,19 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, int tile) {
   // fetched from HBM once and served to its siblings from L2.  (With the M tiles always fastest, the vocabulary-sized
   // weight-gradient GEMMs -- 501 x 4 tiles -- streamed their 4.1 GB A operand once per N tile: 17 GB of DRAM reads for
   // 4.1 GB of data, profiles/gemm_traffic_r1_v15.csv.)
+  // Tail splitting: the statically scheduled tiles run in rounds of one tile per SM (pair).  When the last round is less
+  // than half full -- 252 tiles of 256 x 256 on 74 SM pairs are 3.4 rounds, paid as 4 -- its tiles are cut in two along N
+  // (UMMA N = block_n / 2, same TMA boxes: the surplus B rows of the box are simply not read by the MMA), so the last round
+  // costs half a tile time: 3.5 instead of 4 for the N = 1024 projections (out-proj, FFN2, every dgrad into D = 1024).
   TileCoord t;
+  t.bn = p.block_n;
+  int half = 0;
+  if (tile >= p.tail_start) {
+    const int h = tile - p.tail_start;
+    tile = p.tail_start + (h >> 1);
+    half = h & 1;
+    t.bn = p.block_n >> 1;
+  }
   int batch;
   if (p.n_fast) {
     t.n_tile = tile % p.n_tiles;
@@ -205,6 +219,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, int tile) {
     t.kb0 = 0;
     t.kb1 = p.num_kb;
   }
+  t.n0 = t.n_tile * p.block_n + half * t.bn;
   return t;
 }
 
@@ -240,7 +255,7 @@ __device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMa
   const bool has_aux = E::aux(p), has_res = E::res(p), tma = E::tma(p), res_tma = E::res_tma(p);
   const bool store1 = E::store1(p);
   const bool tma_out = tma && (mode != 1 || store1);
-  const int col0 = t.n_tile * p.block_n + g * GW;
+  const int col0 = t.n0 + g * GW;
   const int row0 = t.m_tile * BM + q * 32;
   uint8_t* stg_c = stg;
   uint8_t* stg_aux = stg + (p.stg_aux > 0 ? p.stg_aux : 0) * STG_BYTES;
@@ -492,7 +507,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* sb = sa + A_STAGE_BYTES;
           uint64_t* bar = &full_bar[stage];
           if (leader) mbar_arrive_expect_tx(bar, stage_tx);
-          const int n0 = t.n_tile * p.block_n + cta_rank * b_rows;
+          const int n0 = t.n0 + cta_rank * (t.bn / NCTA);   // half tiles: the box still loads b_rows rows, the MMA reads t.bn / NCTA
           if (NCTA == 2) {
             if (p.a_major == 0) {
               const int kk = kb * BK;
@@ -540,12 +555,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t idesc = make_idesc_bf16(BM * NCTA, p.block_n, p.a_major, p.b_major);
+      const uint32_t idesc_full = make_idesc_bf16(BM * NCTA, p.block_n, p.a_major, p.b_major);
+      const uint32_t idesc_half = make_idesc_bf16(BM * NCTA, p.block_n / 2, p.a_major, p.b_major);
       for (int tile = first_tile; tile < p.num_tiles; tile += tile_step) {
         const TileCoord t = decode_tile(p, tile);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
+        const uint32_t idesc = t.bn == p.block_n ? idesc_full : idesc_half;
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -592,8 +609,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const long long batch = static_cast<long long>(t.b1) * p.batch0 + t.b0;
       const int row = t.m_tile * BM + q * 32 + lane;
       const bool row_ok = row < p.M;
-      const int col_base = t.n_tile * p.block_n;
-      const int ncols = min(p.block_n, p.N - col_base);
+      const int col_base = t.n0;
+      const int ncols = min(t.bn, p.N - col_base);
       const int n_groups = (ncols + p.gw - 1) / p.gw;
       const long long c_off = t.b0 * p.c_sb0 + t.b1 * p.c_sb1 + static_cast<long long>(row) * p.c_ld;
       const long long r_off = t.b0 * p.r_sb0 + t.b1 * p.r_sb1 + static_cast<long long>(row) * p.r_ld;
@@ -937,6 +954,17 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
       p.num_tiles *= p.splits;
       if (cudaMemset2DAsync(d->c, static_cast<size_t>(d->c_ld) * 4, 0, static_cast<size_t>(d->N) * 4, d->M, st) != cudaSuccess)
         return set_error(MTASR_ERR_LAUNCH, "gemm: split-K memset failed");
+    }
+  }
+  // tail splitting (decode_tile): only for un-split, un-batched-or-batched mode 0 / 2 launches whose N is a whole number of
+  // full tiles and whose last round is at most half full
+  p.tail_start = p.num_tiles;
+  if (p.splits == 1 && d->mode != 1 && bn == 256 && d->N % bn == 0 && getenv("MTASR_GEMM_NO_TAILSPLIT") == nullptr) {
+    const int units = num_units(ncta);
+    const int rem = p.num_tiles % units;
+    if (p.num_tiles > units && rem > 0 && 2 * rem <= units) {
+      p.tail_start = p.num_tiles - rem;
+      p.num_tiles += rem;               // every tile of the last round becomes two half tiles
     }
   }
   p.stage_bytes = A_STAGE_BYTES + (bn / ncta) * BK * 2;

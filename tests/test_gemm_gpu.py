@@ -190,3 +190,34 @@ def test_split_k_wgrad(cuda, M, N, K):
     dw = torch.full((M, N + 8), float("nan"), device=cuda)[:, :N]          # strided C view (ld = N + 8)
     Kn.gemm(Kn.Operand(dy, M, major=1), Kn.Operand(x, N, major=1), M, N, K, Kn.Out(dw, dw.stride(0)))
     assert _rel(dw, dy.float().t() @ x.float()) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,amaj,bmaj", [(5120, 1024, 512, 0, 0),     # 80 pair tiles on 74 SM pairs: 6 tail tiles -> 12 half tiles
+                                             (5120, 1024, 520, 0, 1),     # dgrad form (B MN-major), ragged K
+                                             (5000, 1024, 512, 1, 1),     # wgrad form, ragged last M tile
+                                             (384, 256 * 160, 256, 0, 0),  # single-CTA tiles (M < 512): 480 tiles on 148 SMs, 36 tail tiles
+                                             (15968, 1024, 1024, 0, 0)])  # the cfg2 out-proj / FFN2 / dgrad shape (252 tiles = 3.4 rounds)
+def test_tail_split_tiles(cuda, monkeypatch, M, N, K, amaj, bmaj):
+    """The last, less-than-half-full round of tiles is cut into half-width tiles (gemm.cu decode_tile): results must be those
+    of the un-split schedule, for every operand layout, with the fused bias + residual epilogue and for bf16 / fp32 outputs."""
+    from mtasr_b200 import kernels as Kn
+    a = _rand((K, M) if amaj else (M, K), cuda, 0.5, seed=7)
+    b = _rand((K, N) if bmaj else (N, K), cuda, 0.5, seed=8)
+    bias = torch.randn(N, device=cuda)
+    res = torch.randn(M, N, device=cuda)
+    A = a.float().t() if amaj else a.float()
+    Bm = b.float().t() if bmaj else b.float()
+    ref = A @ Bm.t() + bias + res
+
+    def run(dtype):
+        c = torch.full((M, N), float("nan"), device=cuda, dtype=dtype)
+        Kn.gemm(Kn.Operand(a, a.stride(0), major=amaj), Kn.Operand(b, b.stride(0), major=bmaj), M, N, K, Kn.Out(c, N), bias=bias,
+                residual=Kn.Out(res, N))
+        return c
+
+    c32, c16 = run(torch.float32), run(torch.bfloat16)
+    assert torch.isfinite(c32).all() and _rel(c32, ref) < 1e-5, _rel(c32, ref)
+    assert _rel(c16, ref) < 5e-3
+    monkeypatch.setenv("MTASR_GEMM_NO_TAILSPLIT", "1")
+    c32_ref = run(torch.float32)
+    assert torch.equal(c32, c32_ref)            # same products, same accumulation order per output element
