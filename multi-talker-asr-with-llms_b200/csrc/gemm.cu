@@ -30,12 +30,13 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;    // 16 KB; the B stage is block_n * BK * 2 bytes
 static constexpr int CTRL_WARPS = 4;                 // TMA producer, MMA issuer, TMEM allocator, spare
-static constexpr int EPI_WARPS = 8;                  // 2 warps per TMEM lane quadrant, alternating column groups
+static constexpr int EPI_WARPS = 8;                  // default: 2 warps per TMEM lane quadrant, alternating column groups
+static constexpr int EPI_WARPS_MAX = 16;             // EW = 16 variant: 4 warps per quadrant (see epilogue_group16)
 static constexpr int GEMM_THREADS = (CTRL_WARPS + EPI_WARPS) * 32;
 static constexpr int STG_BYTES = 4096;               // one 32-row x 128-byte swizzled staging box per warp and tensor
 static constexpr int MAX_STAGES = 8;
 static constexpr int BAR_BYTES = 512;                // mbarriers + TMEM slot
-static constexpr int BIAS_BYTES = EPI_WARPS * 64 * 4; // per-warp bias slot of one column group
+static constexpr int BIAS_BYTES = EPI_WARPS * 64 * 4; // per-warp bias slot of one column group (EW warps: EW * 256 bytes)
 static constexpr int SMEM_LIMIT = 232448;            // 227 KB of dynamic shared memory per CTA on sm_100
 static constexpr int TMEM_COLS = 512;
 
@@ -420,13 +421,157 @@ __device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMa
   }
 }
 
+// ---- EW = 16 epilogue ------------------------------------------------------------------------------------------------
+// The 8-warp epilogue is LATENCY-bound, not issue-bound: ncu on the FFN1 shape (GELU + pre-activation tap, K = 1024) shows
+// 38 % issue-slot utilisation with the two epilogue warps of each scheduler at ~0.2 IPC while the tensor pipe idles 51 % of
+// the time waiting for an accumulator stage (profiles/prof_gemm_gelu_aux_r2_lines.txt).  With 16 epilogue warps every
+// scheduler holds four of them and each warp owns ONE 64-column group (bf16 outputs) of a 256-wide tile instead of two.
+// 640 threads leave 102 registers per thread and 16 x 4 KB of staging must not cost pipeline stages, so this variant
+//   * reads the accumulator in 32-column halves (32 live accumulator registers instead of 64),
+//   * keeps ONE staging box per warp: a TMA-loaded residual / activation-backward source of the SAME dtype as the output is
+//     combined in place (thread-private 16-byte pieces), and the pre-activation tap is written and stored first, the
+//     activated output second, through the same box (one extra store-read wait per group, hidden by the other warps).
+// Mode 0 only; launches whose residual has another dtype than the output, or that carry tap AND residual, use EW = 8.
+template <int GW, int CFG>
+__device__ __forceinline__ void epilogue_group16(const GemmKP& p, const CUtensorMap* tmap_c, const CUtensorMap* tmap_aux,
+                                                 const CUtensorMap* tmap_r, uint8_t* stg, float* bias_s, uint64_t* res_bar,
+                                                 uint32_t& res_phase, uint32_t taddr, const TileCoord& t, int q, int lane, int g,
+                                                 const float* bias) {
+  using E = Epi<CFG>;
+  const int act = E::act(p);
+  const bool has_aux = E::aux(p), has_res = E::res(p);
+  const int col0 = t.n0 + g * GW;
+  const int row0 = t.m_tile * BM + q * 32;
+  const bool scale = p.alpha != 1.f;
+  uint32_t drop_s0 = 0, drop_s1 = 0;
+  if (p.drop.seed != nullptr) {
+    drop_s0 = __ldg(p.drop.seed);
+    drop_s1 = __ldg(p.drop.seed + 1);
+  }
+  // the previous group's bulk store must have finished READING the box before anything overwrites it
+  if (lane == 0) bulk_wait_read<0>();
+  if (has_res) fence_proxy_async();
+  __syncwarp();
+  if (bias) {
+#pragma unroll
+    for (int j = 0; j < GW / 32; ++j) {
+      const int col = col0 + j * 32 + lane;
+      bias_s[j * 32 + lane] = col < p.N ? __ldg(bias + col) : 0.f;
+    }
+  }
+  __syncwarp();
+  if (has_aux) {   // pass A: the pre-activation tap (bf16) leaves through the box first
+#pragma unroll
+    for (int hh = 0; hh < GW / 32; ++hh) {
+      uint32_t r[32];
+      tmem_ld32(taddr + g * GW + hh * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c8 = 0; c8 < 4; ++c8) {
+        const int col = col0 + hh * 32 + c8 * 8;
+        if (col >= p.N) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[c8 * 8 + j]);
+        if (scale) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+        }
+        if (bias) {
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_s + hh * 32 + c8 * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_s + hh * 32 + c8 * 8 + 4);
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        stg_store8(stg, MTASR_DT_BF16, lane, GW, hh * 4 + c8, v);
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(tmap_aux, stg, col0, row0, t.b0, t.b1);
+      bulk_commit();
+      bulk_wait_read<0>();
+    }
+    __syncwarp();
+  }
+  if (has_res && lane == 0) {   // residual / activation-backward source -> the SAME box (same dtype as the output)
+    mbar_arrive_expect_tx(res_bar, GW * 32 * (p.res_dtype == MTASR_DT_BF16 ? 2 : 4));
+    tma_load_4d(stg, tmap_r, res_bar, col0, row0, t.b0, t.b1);
+  }
+#pragma unroll
+  for (int hh = 0; hh < GW / 32; ++hh) {
+    uint32_t r[32];
+    tmem_ld32(taddr + g * GW + hh * 32, r);
+    tmem_ld_wait();
+    if (has_res && hh == 0) {
+      mbar_wait(res_bar, res_phase);
+      res_phase ^= 1;
+    }
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      const int col = col0 + hh * 32 + c8 * 8;
+      if (col >= p.N) break;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[c8 * 8 + j]);
+      if (scale) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= p.alpha;
+      }
+      if (bias) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + hh * 32 + c8 * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(bias_s + hh * 32 + c8 * 8 + 4);
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (act == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = gelu_fast_f(v[j]);
+      } else if (act == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.drop.seed != nullptr) {
+        float dm[8];
+        const unsigned long long grow = static_cast<unsigned long long>(t.b1) * p.batch0 + t.b0;
+        drop_mult8(drop_s0, drop_s1, p.drop, (grow * p.M + row0 + lane) * p.drop.ld + col, dm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= dm[j];
+      }
+      if (has_res) {
+        float rr[8];
+        stg_load8(stg, p.res_dtype, lane, GW, hh * 4 + c8, rr);   // this thread's own piece: overwritten in place below
+        if (act == 3) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= gelu_grad_fast_f(rr[j]);
+        } else if (act == 4) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = rr[j] > 0.f ? v[j] : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += rr[j];
+        }
+      }
+      stg_store8(stg, p.c_dtype, lane, GW, hh * 4 + c8, v);
+    }
+  }
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    if (p.splits > 1) tma_reduce_add_4d(tmap_c, stg, col0, row0, t.b0, t.b1);
+    else tma_store_4d(tmap_c, stg, col0, row0, t.b0, t.b1);
+    bulk_commit();
+  }
+}
+
 // NCTA = 1: one CTA per 128 x block_n tile (tcgen05 cta_group::1).
 // NCTA = 2: a CTA PAIR (cluster of 2, same TPC) per 256 x block_n tile (cta_group::2, UMMA M = 256): each CTA loads its own
 // 128 rows of A and HALF of the B tile, the leader's MMA thread issues for both and each CTA's TMEM receives its 128 x
 // block_n accumulator -- per-CTA shared-memory operand traffic drops from 48 KB to 32 KB per 64-wide k-block, which is
 // what kept the single-CTA kernel (96 B/clk of operand reads next to the epilogue staging traffic) off the tensor peak.
-template <int CFG, int NCTA>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int CFG, int NCTA, int EW>
+__global__ void __launch_bounds__((CTRL_WARPS + EW) * 32, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_aux,
                  const __grid_constant__ CUtensorMap tmap_r, const GemmKP p) {
@@ -437,12 +582,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* stg_base = smem + p.stages * p.stage_bytes;                       // 1024-aligned (stage_bytes % 1024 == 0)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + EPI_WARPS * p.n_stg * STG_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + EW * p.n_stg * STG_BYTES);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint64_t* res_bar = tmem_empty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS_MAX);
   float* bias_smem = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + BAR_BYTES);   // EPI_WARPS x 64 floats
 
   const int warp = threadIdx.x >> 5;
@@ -470,9 +615,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tmem_full[i], 1);
-        mbar_init(&tmem_empty[i], EPI_WARPS * NCTA);  // one arrive per epilogue warp of every CTA of the pair
+        mbar_init(&tmem_empty[i], EW * NCTA);  // one arrive per epilogue warp of every CTA of the pair
       }
-      for (int i = 0; i < EPI_WARPS; ++i) mbar_init(&res_bar[i], 1);
+      for (int i = 0; i < EW; ++i) mbar_init(&res_bar[i], 1);
       fence_barrier_init();
     }
   } else if (warp == 2) {
@@ -596,7 +741,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // 32q..32q+31 and the column groups g with (g & 1) == half
     const int e = warp - CTRL_WARPS;
     const int q = e & 3;
-    const int half = e >> 2;
+    const int half = e >> 2;               // column-group slot of this warp: 0..EW/4-1
     uint8_t* stg = stg_base + e * p.n_stg * STG_BYTES;
     float* bias_s = bias_smem + e * 64;
     const int mode = E::mode(p);
@@ -626,6 +771,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+      if constexpr (EW == 16) {
+        for (int g = half; g < n_groups; g += 4) {
+          if (p.gw == 64)
+            epilogue_group16<64, CFG>(p, &tmap_c, &tmap_aux, &tmap_r, stg, bias_s, &res_bar[e], res_phase, taddr, t, q, lane, g, bias);
+          else
+            epilogue_group16<32, CFG>(p, &tmap_c, &tmap_aux, &tmap_r, stg, bias_s, &res_bar[e], res_phase, taddr, t, q, lane, g, bias);
+        }
+      } else
       for (int g = half; g < n_groups; g += 2) {
         if (p.gw == 64)
           epilogue_group<64, CFG>(p, &tmap_c, &tmap_aux, &tmap_r, stg, bias_s, &res_bar[e], res_phase, taddr, t, q, lane, g,
@@ -666,26 +819,32 @@ typedef void (*GemmKernelFn)(const CUtensorMap, const CUtensorMap, const CUtenso
 
 struct KernelEntry {
   int cfg;
-  GemmKernelFn fn;    // one CTA per tile
-  GemmKernelFn fn2;   // CTA pair per 256-row tile
+  GemmKernelFn fn;      // one CTA per tile
+  GemmKernelFn fn2;     // CTA pair per 256-row tile
+  GemmKernelFn fn16;    // 16 epilogue warps (mode 0 only; nullptr otherwise)
+  GemmKernelFn fn16_2;
 };
 #define MTASR_GEMM_CFG(mode, act, aux, res) \
-  { make_cfg(mode, act, aux, res), gemm_bf16_kernel<make_cfg(mode, act, aux, res), 1>, gemm_bf16_kernel<make_cfg(mode, act, aux, res), 2> }
+  { make_cfg(mode, act, aux, res), gemm_bf16_kernel<make_cfg(mode, act, aux, res), 1, 8>, gemm_bf16_kernel<make_cfg(mode, act, aux, res), 2, 8>, \
+    nullptr, nullptr }
+#define MTASR_GEMM_CFG16(mode, act, aux, res) \
+  { make_cfg(mode, act, aux, res), gemm_bf16_kernel<make_cfg(mode, act, aux, res), 1, 8>, gemm_bf16_kernel<make_cfg(mode, act, aux, res), 2, 8>, \
+    gemm_bf16_kernel<make_cfg(mode, act, aux, res), 1, 16>, gemm_bf16_kernel<make_cfg(mode, act, aux, res), 2, 16> }
 // the epilogue combinations the model issues (TMA-staged outputs); anything else runs the generic kernel
 static const KernelEntry kKernels[] = {
-    MTASR_GEMM_CFG(0, 0, false, false),  // plain (+bias): QKV, every dgrad / wgrad, attention contractions, conv FE
-    MTASR_GEMM_CFG(0, 0, false, true),   // + residual: out-proj, FFN2, pos-conv dgrad
-    MTASR_GEMM_CFG(0, 1, false, false),  // GELU: conv FE (group-norm variant)
-    MTASR_GEMM_CFG(0, 1, true, false),   // GELU + pre-activation tap: FFN1
-    MTASR_GEMM_CFG(0, 1, true, true),    // GELU + tap + residual: pos-conv
-    MTASR_GEMM_CFG(0, 2, false, false),  // ReLU
-    MTASR_GEMM_CFG(0, 2, true, false),   // ReLU + tap: separator projections
-    MTASR_GEMM_CFG(0, 3, false, true),   // GELU backward: FFN2 dgrad
-    MTASR_GEMM_CFG(0, 4, false, true),   // ReLU backward
+    MTASR_GEMM_CFG16(0, 0, false, false),  // plain (+bias): QKV, every dgrad / wgrad, attention contractions, conv FE
+    MTASR_GEMM_CFG16(0, 0, false, true),   // + residual: out-proj, FFN2, pos-conv dgrad
+    MTASR_GEMM_CFG(0, 1, false, false),    // GELU: conv FE (group-norm variant)
+    MTASR_GEMM_CFG16(0, 1, true, false),   // GELU + pre-activation tap: FFN1
+    MTASR_GEMM_CFG(0, 1, true, true),      // GELU + tap + residual: pos-conv
+    MTASR_GEMM_CFG(0, 2, false, false),    // ReLU
+    MTASR_GEMM_CFG(0, 2, true, false),     // ReLU + tap: separator projections
+    MTASR_GEMM_CFG16(0, 3, false, true),   // GELU backward: FFN2 dgrad
+    MTASR_GEMM_CFG(0, 4, false, true),     // ReLU backward
     MTASR_GEMM_CFG(1, 0, false, false),  // row LSE / argmax partials: greedy argmax, CTC head forward without autograd
     MTASR_GEMM_CFG(1, 0, true, false),   // row LSE partials + fp16 logits tile: CTC head forward for training
     MTASR_GEMM_CFG(2, 0, false, false),  // softmax regeneration: CTC head backward
-    {CFG_GENERIC, gemm_bf16_kernel<CFG_GENERIC, 1>, gemm_bf16_kernel<CFG_GENERIC, 2>},
+    {CFG_GENERIC, gemm_bf16_kernel<CFG_GENERIC, 1, 8>, gemm_bf16_kernel<CFG_GENERIC, 2, 8>, nullptr, nullptr},
 };
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -967,26 +1126,6 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
       p.num_tiles += rem;               // every tile of the last round becomes two half tiles
     }
   }
-  p.stage_bytes = A_STAGE_BYTES + (bn / ncta) * BK * 2;
-  const int fixed = BAR_BYTES + BIAS_BYTES + EPI_WARPS * p.n_stg * STG_BYTES;
-  int stages = (SMEM_LIMIT - fixed) / p.stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages < 2) return set_error(MTASR_ERR_UNSUPPORTED, "gemm: shared memory budget allows %d pipeline stages", stages);
-  p.stages = stages;
-  const int smem_bytes = fixed + stages * p.stage_bytes;
-
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    for (const KernelEntry& k : kKernels) {
-      cudaError_t e = cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-      if (e != cudaSuccess) attr_err = e;
-      e = cudaFuncSetAttribute(k.fn2, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-      if (e != cudaSuccess) attr_err = e;
-    }
-  });
-  if (attr_err != cudaSuccess)
-    return set_error(MTASR_ERR_LAUNCH, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
   // specialised kernel when the outputs are TMA-staged (mode 1 has no tensor output) and the residual is TMA-loaded
   const KernelEntry* entry = &kKernels[sizeof(kKernels) / sizeof(kKernels[0]) - 1];
   const bool special_ok = getenv("MTASR_GEMM_GENERIC") == nullptr && !d->accumulate &&
@@ -997,7 +1136,41 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
     for (const KernelEntry& k : kKernels)
       if (k.cfg == want) entry = &k;
   }
-  GemmKernelFn kernel = ncta == 2 ? entry->fn2 : entry->fn;
+  // 16 epilogue warps (epilogue_group16): mode-0 configurations compiled for it, 256-wide tiles, one staging box per warp --
+  // so a TMA-loaded residual must have the output's dtype, and tap + residual together stay on the 8-warp kernel
+  const char* ew_env = getenv("MTASR_GEMM_EW");
+  const bool ew16 = special_ok && entry->fn16 != nullptr && d->mode == 0 && bn == 256 && p.tma_epi &&
+                    !(d->aux && d->residual) && (!d->residual || d->res_dtype == d->c_dtype) &&
+                    (!d->aux || d->c_dtype == MTASR_DT_BF16) && !(ew_env && ew_env[0] == '8');
+  const int ew = ew16 ? 16 : EPI_WARPS;
+  if (ew16) {
+    p.n_stg = 1;
+    p.stg_aux = d->aux ? 0 : -1;
+    p.stg_res = d->residual ? 0 : -1;
+  }
+  p.stage_bytes = A_STAGE_BYTES + (bn / ncta) * BK * 2;
+  const int fixed = BAR_BYTES + ew * 64 * 4 + ew * p.n_stg * STG_BYTES;
+  int stages = (SMEM_LIMIT - fixed) / p.stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return set_error(MTASR_ERR_UNSUPPORTED, "gemm: shared memory budget allows %d pipeline stages", stages);
+  p.stages = stages;
+  const int smem_bytes = fixed + stages * p.stage_bytes;
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    for (const KernelEntry& k : kKernels) {
+      for (GemmKernelFn f : {k.fn, k.fn2, k.fn16, k.fn16_2}) {
+        if (f == nullptr) continue;
+        cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        if (e != cudaSuccess) attr_err = e;
+      }
+    }
+  });
+  if (attr_err != cudaSuccess)
+    return set_error(MTASR_ERR_LAUNCH, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+  GemmKernelFn kernel = ew16 ? (ncta == 2 ? entry->fn16_2 : entry->fn16) : (ncta == 2 ? entry->fn2 : entry->fn);
+  const int threads = (CTRL_WARPS + ew) * 32;
 
   const int units = num_units(ncta);
   const int grid = (p.num_tiles < units ? p.num_tiles : units) * ncta;
@@ -1016,7 +1189,7 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   if (ncta == 2) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -1029,7 +1202,7 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
     cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, ma, mb, mc, maux, mr, p);
     if (le != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "gemm: cluster launch failed: %s", cudaGetErrorString(le));
   } else {
-    kernel<<<grid, GEMM_THREADS, smem_bytes, st>>>(ma, mb, mc, maux, mr, p);
+    kernel<<<grid, threads, smem_bytes, st>>>(ma, mb, mc, maux, mr, p);
   }
   g_launches.fetch_add(1);
   if (prof) {
