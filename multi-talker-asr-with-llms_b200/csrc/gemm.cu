@@ -832,10 +832,14 @@ struct KernelEntry {
     gemm_bf16_kernel<make_cfg(mode, act, aux, res), 1, 16>, gemm_bf16_kernel<make_cfg(mode, act, aux, res), 2, 16> }
 // the epilogue combinations the model issues (TMA-staged outputs); anything else runs the generic kernel
 static const KernelEntry kKernels[] = {
-    MTASR_GEMM_CFG16(0, 0, false, false),  // plain (+bias): QKV, every dgrad / wgrad, attention contractions, conv FE
-    MTASR_GEMM_CFG16(0, 0, false, true),   // + residual: out-proj, FFN2, pos-conv dgrad
+    // (measured at M = 15968, N = 4096, K = 1024, TFLOP/s with 8 -> 16 epilogue warps: plain bf16 1234 -> 1147, + residual
+    //  1180 -> 1109, GELU + tap 976 -> 970, GELU backward 856 -> 962: the 16-warp variant pays for its single staging box with
+    //  an extra store-read wait per group and for its 64 KB of staging with two pipeline stages, and only wins where the
+    //  per-element work is longest -- it is enabled for the GELU-backward epilogue only)
+    MTASR_GEMM_CFG(0, 0, false, false),    // plain (+bias): QKV, every dgrad / wgrad, attention contractions, conv FE
+    MTASR_GEMM_CFG(0, 0, false, true),     // + residual: out-proj, FFN2, pos-conv dgrad
     MTASR_GEMM_CFG(0, 1, false, false),    // GELU: conv FE (group-norm variant)
-    MTASR_GEMM_CFG16(0, 1, true, false),   // GELU + pre-activation tap: FFN1
+    MTASR_GEMM_CFG(0, 1, true, false),     // GELU + pre-activation tap: FFN1
     MTASR_GEMM_CFG(0, 1, true, true),      // GELU + tap + residual: pos-conv
     MTASR_GEMM_CFG(0, 2, false, false),    // ReLU
     MTASR_GEMM_CFG(0, 2, true, false),     // ReLU + tap: separator projections

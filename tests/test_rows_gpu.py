@@ -190,3 +190,29 @@ def test_host_prefetcher_and_scalar_reader(cuda):
         if len(pend) == 2:
             assert pend.pop(0).result() == float(i - 1)
     assert pend.pop(0).result() == 4.0
+
+
+def test_bf16_twin_registry_hit_and_miss_paths(cuda):
+    """ops._publish_twin / _cast_or_twin (the bf16 copy of a residual-stream gradient published by the LayerNorm backward for
+    the next block's GEMMs): a hit needs the very same tensor object, unmodified; anything else -- another tensor, an in-place
+    update (gradient accumulation, a hook), a twin of another size, a second consumer (retain_graph / PCGrad re-entry: the
+    entry is popped by its first use) -- must fall back to a fresh cast of the values actually passed."""
+    from mtasr_b200 import ops
+    g = torch.Generator(device=cuda).manual_seed(0)
+    a = torch.randn(64, 128, device=cuda, generator=g)
+    wrong = torch.full((64, 128), 7.0, device=cuda, dtype=torch.bfloat16)      # a twin with recognisable content
+    ops._publish_twin(a, wrong)
+    assert torch.equal(ops._cast_or_twin(a), wrong)                            # hit: same object, same version
+    assert torch.equal(ops._cast_or_twin(a), a.to(torch.bfloat16))             # popped by the first consumer: second use casts
+    ops._publish_twin(a, wrong)
+    a.add_(1.0)                                                                # version bump (accumulation / hook)
+    assert torch.equal(ops._cast_or_twin(a), a.to(torch.bfloat16))
+    ops._publish_twin(a, wrong)
+    b = a.clone()                                                              # another object with equal values
+    assert torch.equal(ops._cast_or_twin(b), b.to(torch.bfloat16))
+    ops._publish_twin(a, wrong[:32])                                           # size mismatch
+    assert torch.equal(ops._cast_or_twin(a), a.to(torch.bfloat16))
+    ops._publish_twin(a, wrong)
+    del a                                                                      # the weak reference dies with the tensor
+    c = torch.randn(64, 128, device=cuda, generator=g)                        # may reuse the id: the dead weakref is no match
+    assert torch.equal(ops._cast_or_twin(c), c.to(torch.bfloat16))
