@@ -184,6 +184,12 @@ int mtasr_layernorm_fwd(const void* x, int32_t x_dtype, const float* gamma, cons
 int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
                         const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D, float* dx_f32,
                         void* dx_bf16, float* dgamma, float* dbeta, void* stream);
+/* The same pass additionally ACCUMULATES dxsum[c] += sum_rows dx[row][c] (zero it first): the bias gradient of the Linear
+ * whose output gradient this dx is (out-proj / FFN2 of the neighbouring half encoder layer, hf:355-366), so that no
+ * separate column-sum pass re-reads dx.  dxsum needs dx_f32 or dx_bf16; any of dgamma / dbeta / dxsum may be NULL. */
+int mtasr_layernorm_bwd_sums(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
+                             const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D,
+                             float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, void* stream);
 int mtasr_cast_f32_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
 /* Label splitter of ref:utils/split_labels_by_sc.py:21-75 on the device: labels (B, L) i64 with row stride ld -> out (K, B, L) i64
  * (must arrive filled with the pad value), lens (K, B) i64, status (3) i32 = {smallest failing row, INT32_MAX if none; kind:
@@ -224,14 +230,14 @@ int mtasr_weightnorm_bwd(const float* dw, const float* v, const float* g, const 
                          float* dg, float* dot, void* stream);
 /* out[n] = sum_m x[m][n] (bias gradients) */
 int mtasr_colsum(const void* x, int32_t dtype, int64_t M, int32_t N, int64_t ld, float* out, void* stream);
-/* gru_rel_pos gate of hf:167-176 for every (b, t, head), head_dim 64: wab (128) = [sum of weight rows 0..3 | rows 4..7]
- * of gru_rel_pos_linear, bab (2) the matching bias sums, cst (H) = gru_rel_pos_const; x (B,T,H*64) f32|bf16 is the
- * attention input.  gate (B,H,T) f32 = sigmoid(a) * (sigmoid(b) * cst[h] - 1) + 2.  Backward: dx (B,T,H*64) f32 written,
- * dwab / dbab / dcst ACCUMULATED (zero them first). */
-int mtasr_relpos_gate_fwd(const void* x, int32_t x_dtype, const float* wab, const float* bab, const float* cst, int32_t B,
+/* gru_rel_pos gate of hf:167-176 for every (b, t, head), head_dim 64: w8 (8,64) / b8 (8) = gru_rel_pos_linear as stored
+ * (rows 0..3 and 4..7 are summed inside the kernel: view(..., 2, 4).sum(-1)), cst (H) = gru_rel_pos_const; x (B,T,H*64)
+ * f32|bf16 is the attention input.  gate (B,H,T) f32 = sigmoid(a) * (sigmoid(b) * cst[h] - 1) + 2.  Backward: dx
+ * (B,T,H*64) f32 written, dw8 (8,64) / db8 (8) / dcst (H) ACCUMULATED (zero them first). */
+int mtasr_relpos_gate_fwd(const void* x, int32_t x_dtype, const float* w8, const float* b8, const float* cst, int32_t B,
                           int32_t T, int32_t H, float* gate, void* stream);
-int mtasr_relpos_gate_bwd(const void* x, int32_t x_dtype, const float* wab, const float* bab, const float* cst,
-                          const float* dgate, int32_t B, int32_t T, int32_t H, float* dx, float* dwab, float* dbab, float* dcst,
+int mtasr_relpos_gate_bwd(const void* x, int32_t x_dtype, const float* w8, const float* b8, const float* cst,
+                          const float* dgate, int32_t B, int32_t T, int32_t H, float* dx, float* dw8, float* db8, float* dcst,
                           void* stream);
 /* softmax(S*scale + gate[b,h,q]*table[h,k-q+T-1]) over keys k < klen[b] (hf:167-180 + hf:206-228 fused);
  * S (B,H,T,Tp) f32, gate (B,H,T) f32, table (H,2T-1) f32, klen (B) i32 or NULL, P (B,H,T,Tp) bf16. */
@@ -274,9 +280,11 @@ int mtasr_glu_bwd(const void* x, int32_t x_dtype, const void* dy, int32_t dy_dty
  * xg (B,T,4Hs) f32 = x_t W_ih^T + b for every step (one batched GEMM beforehand); whh (4Hs, ldw) bf16 is the
  * recurrent half W[:, in:] with row stride ldw.  B <= 64, Hs % 16 == 0, Hs/8 <= #SMs (cooperative launch).
  * Outputs: h (B,T,Hs) bf16 (+ optional f32), c (B,T,Hs) f32, gates (B,T,4Hs) f32 activations (saved for BPTT).
- * `barrier` is a 4-byte device scratch word.  Backward: dgates (B,T,4Hs) bf16 = gradient wrt the gate
- * pre-activations; dx / dW / db follow as GEMMs / column sums over it.
+ * `barrier` is a 16-byte aligned device scratch area of mtasr_lstm_scratch_bytes(B, Hs, backward) bytes (group counters
+ * and the step-flagged exchange words of the recurrence; initialised by the call).  Backward: dgates (B,T,4Hs) bf16 =
+ * gradient wrt the gate pre-activations; dx / dW / db follow as GEMMs / column sums over it.
  */
+int64_t mtasr_lstm_scratch_bytes(int32_t B, int32_t Hs, int32_t backward);
 int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw, int32_t B, int32_t T, int32_t Hs, void* h_bf16,
                    float* h_f32, float* c_all, float* gates, uint32_t* barrier, void* stream);
 int mtasr_lstm_bwd(const float* dh_out, const float* gates, const float* c_all, const void* whh_bf16, int32_t ldw,

@@ -71,6 +71,7 @@ SIGNATURES = {
     "mtasr_ctc_scatter_rows": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, _P]),
     "mtasr_layernorm_fwd": (C.c_int, [_P, _I32, _P, _P, _F, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
     "mtasr_layernorm_bwd": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
+    "mtasr_layernorm_bwd_sums": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
     "mtasr_cast_f32_bf16": (C.c_int, [_P, _P, _I64, _P]),
     "mtasr_softmax_from_logits": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P, _P, _P]),
     "mtasr_weightnorm_fwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P]),
@@ -94,6 +95,7 @@ SIGNATURES = {
     "mtasr_split_bf16": (C.c_int, [_P, _I64, _I64, _I32, _I32, _P, _P]),
     "mtasr_attn_softmax_fwd_split": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _I32, _P, _P]),
     "mtasr_act_bwd": (C.c_int, [_P, _I32, _P, _I32, _I64, _P, _P]),
+    "mtasr_lstm_scratch_bytes": (C.c_int64, [_I32, _I32, _I32]),
     "mtasr_lstm_fwd": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "mtasr_lstm_bwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "mtasr_lstm_fwd_f32": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),

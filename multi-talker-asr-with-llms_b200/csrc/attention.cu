@@ -45,6 +45,20 @@ struct AttnFwdP {
 };
 
 // Dropout multipliers (0 or 1/keep) of the n consecutive keys kb .. kb+n-1 (kb even, n a multiple of 2) of probability row `row`.
+// Work items are ordered (head, utterance, tile) and every CTA takes ONE CONTIGUOUS chunk of them: a CTA then stays on one
+// head for (almost) its whole run -- the relative-position table (and, in the backward, its gradient accumulator) in shared
+// memory is reloaded / flushed once or twice per launch instead of once per item (with the former round-robin order over
+// (utterance, head, tile) the head changed on every item: 148 / nq is not a multiple of H), and consecutive items of a CTA
+// re-use the K / V tiles of the same (utterance, head).
+__device__ __forceinline__ int item_begin(int n_items) {
+  const int base = n_items / static_cast<int>(gridDim.x), rem = n_items % static_cast<int>(gridDim.x);
+  return static_cast<int>(blockIdx.x) * base + min(static_cast<int>(blockIdx.x), rem);
+}
+__device__ __forceinline__ int item_end(int n_items) {
+  const int base = n_items / static_cast<int>(gridDim.x), rem = n_items % static_cast<int>(gridDim.x);
+  return item_begin(n_items) + base + (static_cast<int>(blockIdx.x) < rem ? 1 : 0);
+}
+
 template <int N>
 __device__ __forceinline__ void attn_drop_mults(uint32_t s0, uint32_t s1, const DropP& d, unsigned long long row, int kb, float (&m)[N]) {
   const unsigned long long pair0 = (row * static_cast<unsigned long long>(d.ld) + static_cast<unsigned long long>(kb)) >> 1;
@@ -128,8 +142,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
     if (elect_one()) {
       int slot = 0;
       uint32_t ph = 0, qph = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int qt = item % p.nq, h = (item / p.nq) % p.H, b = item / (p.nq * p.H);
+      for (int item = item_begin(p.n_items); item < item_end(p.n_items); ++item) {
+        const int qt = item % p.nq, b = (item / p.nq) % p.B, h = item / (p.nq * p.B);
         mbar_wait(q_empty, qph ^ 1);
         qph ^= 1;
         mbar_arrive_expect_tx(q_full, AT_TILE);
@@ -169,7 +183,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
         umma_commit(&s_full[buf]);
         if (++slot == AT_KV_SLOTS) { slot = 0; ph ^= 1; }
       };
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = item_begin(p.n_items); item < item_end(p.n_items); ++item) {
         mbar_wait(q_full, qph);
         qph ^= 1;
         for (int j = 0; j < nk; ++j) { issue_s(sb); sb ^= 1; }          // pass A
@@ -212,8 +226,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
     uint32_t drop_s0 = 0, drop_s1 = 0;
     if (DROP) { drop_s0 = __ldg(p.drop.seed); drop_s1 = __ldg(p.drop.seed + 1); }
     int cur_h = -1;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int qt = item % p.nq, h = (item / p.nq) % p.H, b = item / (p.nq * p.H);
+    for (int item = item_begin(p.n_items); item < item_end(p.n_items); ++item) {
+      const int qt = item % p.nq, b = (item / p.nq) % p.B, h = item / (p.nq * p.B);
       named_bar_sync(1, 512);                      // every softmax thread is done with the previous item's table / xch
       if (h != cur_h) {
         const float* trow = p.table + static_cast<long long>(h) * (2 * p.T - 1);
@@ -425,8 +439,8 @@ attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP 
     if (elect_one()) {
       int slot = 0, qb = 0;
       uint32_t ph = 0, qph[2] = {0, 0};
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int qt = item % p.nq, h = (item / p.nq) % p.H, b = item / (p.nq * p.H);
+      for (int item = item_begin(p.n_items); item < item_end(p.n_items); ++item) {
+        const int qt = item % p.nq, b = (item / p.nq) % p.B, h = item / (p.nq * p.B);
         mbar_wait(&q_empty[qb], qph[qb] ^ 1);
         qph[qb] ^= 1;
         mbar_arrive_expect_tx(&q_full[qb], AT_TILE);
@@ -465,7 +479,7 @@ attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP 
         umma_commit(&s_full[buf]);
         if (++slot == AT_KV_SLOTS) { slot = 0; ph ^= 1; }
       };
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = item_begin(p.n_items); item < item_end(p.n_items); ++item) {
         mbar_wait(&q_full[qb], qph[qb]);
         qph[qb] ^= 1;
         issue_s(0);                                                      // key tile j always uses S / P buffer j & 1
@@ -506,8 +520,17 @@ attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP 
     int cur_h = -1;
     int ipar = 0;                                  // item parity: the combine arrays are double-buffered, so the only
                                                    // CTA-wide barrier per item is the one in front of the combination
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int qt = item % p.nq, h = (item / p.nq) % p.H, b = item / (p.nq * p.H);
+    // the row's gate value of item i + 1 is requested while item i is processed (it sat as a dependent L2 round trip in
+    // front of the first score of every item: 11 % of the softmax warps' stall samples)
+    auto gate_of = [&](int it) {
+      const int qt_ = it % p.nq, b_ = (it / p.nq) % p.B, h_ = it / (p.nq * p.B);
+      const int q_ = min(qt_ * AT_BQ + r, p.T - 1);
+      return p.gate[(static_cast<long long>(b_) * p.H + h_) * p.T + q_];
+    };
+    const int it_end = item_end(p.n_items);
+    float g_next = item_begin(p.n_items) < it_end ? gate_of(item_begin(p.n_items)) : 0.f;
+    for (int item = item_begin(p.n_items); item < it_end; ++item) {
+      const int qt = item % p.nq, b = (item / p.nq) % p.B, h = item / (p.nq * p.B);
       if (h != cur_h) {                            // uniform over the CTA: the table changes once per head
         named_bar_sync(1, 512);                    // every softmax thread is done with the previous head's table
         const float* trow = p.table + static_cast<long long>(h) * (2 * p.T - 1);
@@ -522,7 +545,8 @@ attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP 
       const bool q_ok = q < p.T;
       const int qc = q_ok ? q : p.T - 1;
       const int kl = p.klen ? min(p.klen[b], p.T) : p.T;
-      const float g = p.gate[(static_cast<long long>(b) * p.H + h) * p.T + qc];
+      const float g = g_next;
+      if (item + 1 < it_end) g_next = gate_of(item + 1);
       const float* trel = tbl_s + (p.T - 1 - qc);   // trel[k] = log2e * table[h, k - q + T - 1]
       const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
       const uint32_t tm_mine = tm_s[grp] + lane_off + sub * 64;
@@ -759,8 +783,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     if (elect_one()) {
       uint32_t kvph = 0, qph[2] = {0, 0};
       int st = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int jt = item % p.nk, h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
+      for (int item = item_begin(p.n_items); item < item_end(p.n_items); ++item) {
+        const int jt = item % p.nk, b = (item / p.nk) % p.B, h = item / (p.nk * p.B);
         mbar_wait(kv_empty, kvph ^ 1);
         kvph ^= 1;
         mbar_arrive_expect_tx(kv_full, 2 * AT_TILE);
@@ -800,7 +824,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         umma_commit(sdp_full);
         st ^= 1;
       };
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (int item = item_begin(p.n_items); item < item_end(p.n_items); ++item) {
         mbar_wait(kv_full, kvph);
         kvph ^= 1;
         issue_sdp();
@@ -849,8 +873,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     int cur_h = -1;
     uint32_t drop_s0 = 0, drop_s1 = 0;
     if (DROP) { drop_s0 = __ldg(p.drop.seed); drop_s1 = __ldg(p.drop.seed + 1); }
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int jt = item % p.nk, h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
+    for (int item = item_begin(p.n_items); item < item_end(p.n_items); ++item) {
+      const int jt = item % p.nk, b = (item / p.nk) % p.B, h = item / (p.nk * p.B);
       named_bar_sync(1, 256);
       if (h != cur_h) {
         const float* trow = p.table + static_cast<long long>(h) * (2 * p.T - 1);
@@ -1004,10 +1028,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     uint32_t pds_ph[2] = {0, 0}, dq_ph = 0;
     int db = 0;
     const float inv_scale = 1.f / p.scale;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int jt = item % p.nk, h = (item / p.nk) % p.H, b = item / (p.nk * p.H);
-      for (int i = t; i < 2 * p.T - 1; i += 128) acc_s[i] = 0.f;
-      named_bar_sync(2, 128);
+    int red_h = -1;
+    for (int item = item_begin(p.n_items); item < item_end(p.n_items); ++item) {
+      const int jt = item % p.nk, b = (item / p.nk) % p.B, h = item / (p.nk * p.B);
+      if (h != red_h) {                            // uniform: the accumulator follows the head (once or twice per CTA)
+        named_bar_sync(2, 128);                    // every diagonal sum of the previous head has landed
+        float* dt = p.dtable + static_cast<long long>(red_h < 0 ? 0 : red_h) * (2 * p.T - 1);
+        for (int i = t; i < 2 * p.T - 1; i += 128) {
+          const float v = acc_s[i];
+          if (red_h >= 0 && v != 0.f) atomicAdd(dt + i, v * inv_scale);
+          acc_s[i] = 0.f;
+        }
+        red_h = h;
+        named_bar_sync(2, 128);
+      }
       for (int i = 0; i < nq; ++i) {
         mbar_wait(&pds_full[db], pds_ph[db]);
         pds_ph[db] ^= 1;
@@ -1071,13 +1105,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                        __uint_as_float(a1[v4 * 4 + 2]), __uint_as_float(a1[v4 * 4 + 3]));
         }
       }
-      named_bar_sync(2, 128);
-      float* dt = p.dtable + static_cast<long long>(h) * (2 * p.T - 1);
+    }
+    named_bar_sync(2, 128);
+    if (red_h >= 0) {
+      float* dt = p.dtable + static_cast<long long>(red_h) * (2 * p.T - 1);
       for (int i = t; i < 2 * p.T - 1; i += 128) {
         const float v = acc_s[i];
         if (v != 0.f) atomicAdd(dt + i, v * inv_scale);
       }
-      named_bar_sync(2, 128);
     }
   }
 

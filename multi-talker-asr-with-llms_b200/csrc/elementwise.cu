@@ -200,6 +200,146 @@ layernorm_bwd_param_kernel(const void* __restrict__ dy, int dy_dtype, const void
   }
 }
 
+// Fused LayerNorm backward: dx (+ dres) AND the three column reductions that used to be separate passes over the same
+// rows -- dgamma = sum_rows dy * xhat, dbeta = sum_rows dy, and dxsum = sum_rows dx (the bias gradient of the Linear
+// whose output gradient this dx is: out-proj / FFN2 of the neighbouring half layer).  A row is owned by a GROUP of NW
+// warps, thread = 8 consecutive columns, so the running column sums are 24 registers per thread (the warp-per-row kernel
+// above would need 3 x D/32); the two row scalars cross the group's warps through a parity-double-buffered smem slot and
+// ONE named barrier per row.  The next row's loads are issued before the current row's reductions.
+__device__ __forceinline__ void ld_raw8(const void* base, int dtype, long long idx, uint4& u0, uint4& u1) {
+  if (dtype == MTASR_DT_BF16) {
+    u0 = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(base) + idx);
+  } else {
+    u0 = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(base) + idx);
+    u1 = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(base) + idx + 4);
+  }
+}
+__device__ __forceinline__ void cvt_raw8(int dtype, const uint4& u0, const uint4& u1, float (&o)[8]) {
+  if (dtype == MTASR_DT_BF16) {
+    float2 t;
+    t = unpack_bf16x2(u0.x); o[0] = t.x; o[1] = t.y;
+    t = unpack_bf16x2(u0.y); o[2] = t.x; o[3] = t.y;
+    t = unpack_bf16x2(u0.z); o[4] = t.x; o[5] = t.y;
+    t = unpack_bf16x2(u0.w); o[6] = t.x; o[7] = t.y;
+  } else {
+    o[0] = __uint_as_float(u0.x); o[1] = __uint_as_float(u0.y); o[2] = __uint_as_float(u0.z); o[3] = __uint_as_float(u0.w);
+    o[4] = __uint_as_float(u1.x); o[5] = __uint_as_float(u1.y); o[6] = __uint_as_float(u1.z); o[7] = __uint_as_float(u1.w);
+  }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(256, 2)
+layernorm_bwd_fused_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
+                           const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                           const float* __restrict__ dres, long long rows, int D, float* __restrict__ dx_f32,
+                           __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                           float* __restrict__ dxsum) {
+  constexpr int G = NW * 32;                       // threads per row group
+  constexpr int NG = NW == 3 ? 2 : 256 / G;        // row groups per CTA (blockDim.x = NG * G)
+  constexpr int GC = G * 8;                        // columns a group spans
+  __shared__ float2 red[2][NG][NW];
+  __shared__ float acc[NG][GC];
+  const int g = threadIdx.x / G, tg = threadIdx.x % G, wg = tg >> 5, lane = tg & 31;
+  const int c0 = tg * 8;
+  const bool active = c0 < D;
+  const bool has_res = dres != nullptr;
+  float gm[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gm[j] = 0.f;
+  if (active) ld8(gamma, MTASR_DT_F32, c0, gm);
+  float ag[8], ab[8], ax[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ag[j] = ab[j] = ax[j] = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * NG;
+  long long row = static_cast<long long>(blockIdx.x) * NG + g;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  uint4 ra0 = z4, ra1 = z4, rb0 = z4, rb1 = z4, rd0 = z4, rd1 = z4;
+  float mu = 0.f, rs = 0.f;
+  if (row < rows) {
+    if (active) {
+      ld_raw8(dy, dy_dtype, row * D + c0, ra0, ra1);
+      ld_raw8(x, x_dtype, row * D + c0, rb0, rb1);
+      if (has_res) ld_raw8(dres, MTASR_DT_F32, row * D + c0, rd0, rd1);
+    }
+    mu = mean[row];
+    rs = rstd[row];
+  }
+  const float inv_d = 1.0f / static_cast<float>(D);
+  int par = 0;
+  for (; row < rows; row += stride, par ^= 1) {
+    float a[8], b[8], d[8];
+    cvt_raw8(dy_dtype, ra0, ra1, a);
+    cvt_raw8(x_dtype, rb0, rb1, b);
+    cvt_raw8(MTASR_DT_F32, rd0, rd1, d);
+    const float mu_c = mu, rs_c = rs;
+    const long long nxt = row + stride;
+    if (nxt < rows) {                               // next row's loads in flight under this row's reductions
+      if (active) {
+        ld_raw8(dy, dy_dtype, nxt * D + c0, ra0, ra1);
+        ld_raw8(x, x_dtype, nxt * D + c0, rb0, rb1);
+        if (has_res) ld_raw8(dres, MTASR_DT_F32, nxt * D + c0, rd0, rd1);
+      }
+      mu = mean[nxt];
+      rs = rstd[nxt];
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xhat = (b[j] - mu_c) * rs_c;
+      const float gg = a[j] * gm[j];
+      s1 += gg;
+      s2 = fmaf(gg, xhat, s2);
+      ab[j] += a[j];
+      ag[j] = fmaf(a[j], xhat, ag[j]);
+      b[j] = xhat;
+      a[j] = gg;
+    }
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    if (NW > 1) {
+      if (lane == 0) red[par][g][wg] = make_float2(s1, s2);
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "r"(G) : "memory");
+      s1 = s2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const float2 t = red[par][g][w];
+        s1 += t.x;
+        s2 += t.y;
+      }
+    }
+    s1 *= inv_d;
+    s2 *= inv_d;
+    if (active) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = rs_c * (a[j] - s1 - b[j] * s2) + d[j];
+        ax[j] += o[j];
+      }
+      if (dx_f32) st8_f32(dx_f32 + row * D + c0, o);
+      if (dx_bf16) st8_bf16(dx_bf16 + row * D + c0, o);
+    }
+  }
+  // CTA-level combination of the NG groups' column sums, one atomic per column and quantity
+  float* const outs[3] = {dgamma, dbeta, dxsum};
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    if (outs[q] == nullptr) continue;             // uniform
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[g][c0 + j] = q == 0 ? ag[j] : (q == 1 ? ab[j] : ax[j]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < GC; c += NG * G) {
+      if (c < D) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) t += acc[i][c];
+        atomicAdd(outs[q] + c, t);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ cast / colsum
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n8) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
@@ -485,11 +625,17 @@ __device__ __forceinline__ void gate_load32(const void* x, int x_dtype, long lon
   }
 }
 
+// entry i of the summed projection: i < 64 -> rows 0..3 of the (8, 64) weight (gate a), else rows 4..7 (gate b), hf:170-173
+__device__ __forceinline__ float gate_wsum(const float* __restrict__ w8, int i) {
+  const float* p = w8 + (i >> 6) * 256 + (i & 63);
+  return (p[0] + p[64]) + (p[128] + p[192]);
+}
+
 __global__ void __launch_bounds__(256)
-relpos_gate_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ wab, const float* __restrict__ bab,
+relpos_gate_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ w8, const float* __restrict__ b8,
                        const float* __restrict__ cst, int B, int T, int H, float* __restrict__ gate) {
   __shared__ __align__(16) float w_s[128];
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) w_s[i] = wab[i];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) w_s[i] = gate_wsum(w8, i);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -498,7 +644,7 @@ relpos_gate_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __r
   const bool active = h < H;
   const float* wa = w_s + half * 32;
   const float* wb = w_s + 64 + half * 32;
-  const float ba = bab[0], bb = bab[1];
+  const float ba = (b8[0] + b8[1]) + (b8[2] + b8[3]), bb = (b8[4] + b8[5]) + (b8[6] + b8[7]);
   const float c_h = active ? cst[h] : 0.f;
   const long long rows = static_cast<long long>(B) * T;
   const int D = H * 64;
@@ -523,15 +669,15 @@ relpos_gate_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __r
   }
 }
 
-// Backward: dx (B,T,D) fp32 = da*wa + db*wb per head slice; dwab (128), dbab (2), dcst (H) accumulated with atomics
+// Backward: dx (B,T,D) fp32 = da*wa + db*wb per head slice; dw8 (8,64), db8 (8), dcst (H) accumulated with atomics
 // (zero them first).
 __global__ void __launch_bounds__(128, 3)
-relpos_gate_bwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ wab, const float* __restrict__ bab,
+relpos_gate_bwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ w8, const float* __restrict__ b8,
                        const float* __restrict__ cst, const float* __restrict__ dgate, int B, int T, int H,
-                       float* __restrict__ dx, float* __restrict__ dwab, float* __restrict__ dbab, float* __restrict__ dcst) {
+                       float* __restrict__ dx, float* __restrict__ dw8, float* __restrict__ db8, float* __restrict__ dcst) {
   __shared__ __align__(16) float w_s[128];
   __shared__ float red_s[132];
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) w_s[i] = wab[i];
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) w_s[i] = gate_wsum(w8, i);
   for (int i = threadIdx.x; i < 132; i += blockDim.x) red_s[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -541,7 +687,7 @@ relpos_gate_bwd_kernel(const void* __restrict__ x, int x_dtype, const float* __r
   const bool active = h < H;
   const float* wa = w_s + half * 32;
   const float* wb = w_s + 64 + half * 32;
-  const float ba = bab[0], bb = bab[1];
+  const float ba = (b8[0] + b8[1]) + (b8[2] + b8[3]), bb = (b8[4] + b8[5]) + (b8[6] + b8[7]);
   const float c_h = active ? cst[h] : 0.f;
   const long long rows = static_cast<long long>(B) * T;
   const int D = H * 64;
@@ -605,10 +751,14 @@ relpos_gate_bwd_kernel(const void* __restrict__ x, int x_dtype, const float* __r
   if (lane == 0) { atomicAdd(red_s + 128, dba); atomicAdd(red_s + 129, dbb); }
   if (active && half == 0 && dc != 0.f) atomicAdd(dcst + h, dc);
   __syncthreads();
+  // the four weight rows (bias entries) that were summed into one share its gradient
   for (int i = threadIdx.x; i < 130; i += blockDim.x) {
     const float sv = red_s[i];
-    if (i < 128) atomicAdd(dwab + i, sv);
-    else atomicAdd(dbab + (i - 128), sv);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (i < 128) atomicAdd(dw8 + ((i >> 6) * 4 + r) * 64 + (i & 63), sv);
+      else atomicAdd(db8 + (i - 128) * 4 + r, sv);
+    }
   }
 }
 
@@ -816,18 +966,30 @@ extern "C" int mtasr_layernorm_fwd(const void* x, int32_t x_dtype, const float* 
   return MTASR_OK;
 }
 
-extern "C" int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
-                                   const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D,
-                                   float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, void* stream) {
-  MTASR_CHECK_ARG(dy && x && mean && rstd && gamma && rows > 0 && (dx_f32 || dx_bf16 || dgamma), "layernorm_bwd: bad arguments");
+static int layernorm_bwd_launch(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
+                                const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D,
+                                float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, cudaStream_t st) {
+  MTASR_CHECK_ARG(dy && x && mean && rstd && gamma && rows > 0 && (dx_f32 || dx_bf16 || dgamma || dbeta), "layernorm_bwd: bad arguments");
   MTASR_CHECK_ARG(D % 8 == 0 && D <= 32 * MAXV, "layernorm_bwd: D=%d must be a multiple of 8 and <= 1024", D);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MTASR_CHECK_ARG(!dxsum || dx_f32 || dx_bf16, "layernorm_bwd: dxsum needs a dx output");
   if (dx_f32 || dx_bf16) {
-    layernorm_bwd_kernel<<<grid_for(rows, 8), 256, 0, st>>>(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres, rows, D, dx_f32,
-                                                           reinterpret_cast<__nv_bfloat16*>(dx_bf16));
+    // one pass: dx, dgamma, dbeta and the column sums of dx (all three reductions accumulate into zeroed buffers)
+    const int nw = (D / 8 + 31) / 32;
+    const int ng = nw == 3 ? 2 : 8 / nw;
+    long long g = (rows + ng - 1) / ng;
+    if (g > num_sms() * 2) g = num_sms() * 2;
+    const unsigned grid = static_cast<unsigned>(g), block = static_cast<unsigned>(ng * nw * 32);
+    __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+#define MTASR_LNB(NW) layernorm_bwd_fused_kernel<NW><<<grid, block, 0, st>>>(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres, rows, D, dx_f32, dxb, dgamma, dbeta, dxsum)
+    switch (nw) {
+      case 1: MTASR_LNB(1); break;
+      case 2: MTASR_LNB(2); break;
+      case 3: MTASR_LNB(3); break;
+      default: MTASR_LNB(4); break;
+    }
+#undef MTASR_LNB
     MTASR_COUNT_LAUNCH();
-  }
-  if (dgamma || dbeta) {
+  } else {
     const int gx = (D + 255) / 256;
     int gy = static_cast<int>((rows + 63) / 64);
     const int cap = (num_sms() * 4 + gx - 1) / gx;
@@ -838,6 +1000,20 @@ extern "C" int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void*
   }
   MTASR_CHECK_LAUNCH("layernorm_bwd");
   return MTASR_OK;
+}
+
+extern "C" int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
+                                   const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D,
+                                   float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, void* stream) {
+  return layernorm_bwd_launch(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres, rows, D, dx_f32, dx_bf16, dgamma, dbeta, nullptr,
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mtasr_layernorm_bwd_sums(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
+                                        const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D,
+                                        float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, void* stream) {
+  return layernorm_bwd_launch(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres, rows, D, dx_f32, dx_bf16, dgamma, dbeta, dxsum,
+                              static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mtasr_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
@@ -923,8 +1099,9 @@ extern "C" int mtasr_colsum(const void* x, int32_t dtype, int64_t M, int32_t N, 
   return MTASR_OK;
 }
 
-extern "C" int mtasr_relpos_gate_fwd(const void* x, int32_t x_dtype, const float* wab, const float* bab, const float* cst,
+extern "C" int mtasr_relpos_gate_fwd(const void* x, int32_t x_dtype, const float* w8, const float* b8, const float* cst,
                                      int32_t B, int32_t T, int32_t H, float* gate, void* stream) {
+  const float *wab = w8, *bab = b8;
   MTASR_CHECK_ARG(x && wab && bab && cst && gate && B > 0 && T > 0 && H > 0 && H <= 32, "relpos_gate_fwd: bad arguments");
   MTASR_CHECK_ARG(H <= 16, "relpos_gate_fwd: H=%d > 16 heads not supported", H);
   relpos_gate_fwd_kernel<<<grid_for(static_cast<long long>(B) * T, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -934,9 +1111,11 @@ extern "C" int mtasr_relpos_gate_fwd(const void* x, int32_t x_dtype, const float
   return MTASR_OK;
 }
 
-extern "C" int mtasr_relpos_gate_bwd(const void* x, int32_t x_dtype, const float* wab, const float* bab, const float* cst,
-                                     const float* dgate, int32_t B, int32_t T, int32_t H, float* dx, float* dwab, float* dbab,
+extern "C" int mtasr_relpos_gate_bwd(const void* x, int32_t x_dtype, const float* w8, const float* b8, const float* cst,
+                                     const float* dgate, int32_t B, int32_t T, int32_t H, float* dx, float* dw8, float* db8,
                                      float* dcst, void* stream) {
+  const float *wab = w8, *bab = b8;
+  float *dwab = dw8, *dbab = db8;
   MTASR_CHECK_ARG(x && wab && bab && cst && dgate && dx && dwab && dbab && dcst && B > 0 && T > 0 && H > 0 && H <= 32,
                   "relpos_gate_bwd: bad arguments");
   MTASR_CHECK_ARG(H <= 16, "relpos_gate_bwd: H=%d > 16 heads not supported", H);

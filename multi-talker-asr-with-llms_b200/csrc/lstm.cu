@@ -625,6 +625,373 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_bwd_bs_kernel(const LstmBsP 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ flag-in-data exchange
+// The batch-sliced kernels above pay three dependent L2 round trips per step: exchange store -> fence -> atomic arrive,
+// the waiter's poll of the counter, then the exchange loads -- plus five CTA-wide barriers around the smem staging.  The
+// *_ll kernels below exchange h_t (forward) / dgates_t (backward) the way NCCL's LL protocol moves small messages: every
+// 8-byte word of the exchange buffer is {two bf16 values, 32-bit step flag}, written by ONE 64-bit store and read by
+// 64-bit loads (single-copy atomic), so a consumer that sees the flag of the step it waits for has the data -- no fence,
+// no counter, ONE L2 round trip per step.  The words are laid out so that one 16-byte load is exactly the {b0, b1}
+// B-fragment pair of an mma.sync m16n8k16 lane (units 16 ks + 2 j + {0,1} and 16 ks + 8 + 2 j + {0,1} of utterance
+// lane / 4): the consumer warps poll their own fragments straight from L2 into registers -- no shared-memory staging, no
+// barrier in front of the MMAs -- and the per-warp partial products are double-buffered, which leaves ONE __syncthreads
+// per step.  The buffer holds two step parities (a CTA can run at most one step ahead of the slowest CTA of its group).
+__device__ __forceinline__ void ll_store(unsigned long long* p, uint32_t data, uint32_t flag) {
+  const unsigned long long v = static_cast<unsigned long long>(data) | (static_cast<unsigned long long>(flag) << 32);
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void ll_load2(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.volatile.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// Spin until both words of the fragment pair carry `flag`; -> {b0, b1}.  A waiter that spins past `limit` clocks traps.
+__device__ __forceinline__ void ll_wait2(const unsigned long long* p, unsigned long long& a, unsigned long long& b, uint32_t flag,
+                                         long long limit) {
+  if (static_cast<uint32_t>(a >> 32) == flag && static_cast<uint32_t>(b >> 32) == flag) return;
+  const long long t0 = clock64();
+  unsigned int spins = 0;
+  do {
+    ll_load2(p, a, b);
+    if ((++spins & 0x3ff) == 0 && limit > 0 && clock64() - t0 > limit) __trap();
+  } while (static_cast<uint32_t>(a >> 32) != flag || static_cast<uint32_t>(b >> 32) != flag);
+}
+// Batched wait over N fragment pairs at p + i * stride (64-bit words): every pair that does not carry `flag` yet is
+// re-requested in the SAME round, so a round costs one L2 round trip however many pairs were early (waiting for them one
+// after the other serialised up to N round trips per step).
+template <int N>
+__device__ __forceinline__ void ll_wait_all(const unsigned long long* p, int stride, unsigned long long (&a)[N],
+                                            unsigned long long (&b)[N], uint32_t flag, long long limit) {
+  long long t0 = 0;
+  unsigned int spins = 0;
+  while (true) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      if (static_cast<uint32_t>(a[i] >> 32) != flag || static_cast<uint32_t>(b[i] >> 32) != flag) {
+        ok = false;
+        ll_load2(p + i * stride, a[i], b[i]);
+      }
+    }
+    if (ok) return;
+    if (spins == 0) t0 = clock64();
+    if ((++spins & 0x3ff) == 0 && limit > 0 && clock64() - t0 > limit) __trap();
+  }
+}
+// 64-bit word index of unit pair (k, k+1), k even, inside one utterance's row of `ksteps` 16-unit k-steps:
+// [ks][j = (k % 8) / 2][half = (k % 16) / 8]
+__device__ __forceinline__ int ll_word(int k) { return (k >> 4) * 8 + ((k & 7) >> 1) * 2 + ((k >> 3) & 1); }
+
+struct LstmLlP {
+  const float* xg;            // (B,T,4Hs)   fwd
+  const __nv_bfloat16* whh;   // (4Hs, ldw)
+  __nv_bfloat16* h_bf16;      // (B,T,Hs)    fwd out
+  float* h_f32;               // optional
+  float* c_all;               // (B,T,Hs)
+  float* gates;               // (B,T,4Hs)
+  const float* dh_out;        // (B,T,Hs)    bwd
+  __nv_bfloat16* dgates;      // (B,T,4Hs)   bwd out
+  unsigned long long* ll;     // exchange words: [2 parities][S][8 utterances][Hs/2 (fwd) | 4Hs/2 (bwd)]
+  int B, T, Hs, ldw, G, U;
+  long long spin_limit;
+};
+
+// KPER > 0: every warp owns exactly KPER k-steps (fully unrolled, all fragment loads of a step in flight at once).
+template <int KPER>
+__global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_ll_kernel(const LstmLlP p) {
+  extern __shared__ __align__(16) uint8_t lsm[];
+  const int Hs = p.Hs, T = p.T, U = p.U, G = p.G;
+  const int rs = Hs + LPAD;
+  const int M = 4 * U, m_tiles = (M + 15) / 16;
+  const int prow = m_tiles * 16;
+  __nv_bfloat16* Ws = reinterpret_cast<__nv_bfloat16*>(lsm);          // [4U][rs]
+  float* P = reinterpret_cast<float*>(Ws + M * rs);                   // [2 step parities][4 K-quarters][prow][8]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = gridDim.x / G;
+  const int s = blockIdx.x / G, j = blockIdx.x % G;
+  const int b0 = s * RB, nb = min(RB, p.B - b0);
+  const int u0 = j * U;
+
+  for (int i = tid; i < M * (Hs / 8); i += LTHREADS) {
+    const int lc = i / (Hs / 8), kc = i % (Hs / 8);
+    const int gcol = (lc / U) * Hs + u0 + (lc % U);
+    *reinterpret_cast<uint4*>(Ws + lc * rs + kc * 8) =
+        *reinterpret_cast<const uint4*>(p.whh + static_cast<long long>(gcol) * p.ldw + kc * 8);
+  }
+  __syncthreads();
+
+  const int ksteps = Hs / 16;
+  const int kper = (ksteps + 3) / 4;
+  const int kq = warp & 3, mh = warp >> 2;
+  const int k_lo = kq * kper, k_hi = min(ksteps, k_lo + kper);
+  const int mt_half = (m_tiles + 1) / 2;
+  const int mt_lo = mh * mt_half;
+  const int pr = tid;                       // (b, u) pair owned by this thread
+  const bool has_pair = pr < nb * U;
+  const int pb = has_pair ? pr / U : 0, pu = has_pair ? pr % U : 0;
+  float creg = 0.f;
+  const int wpr = Hs / 2;                   // exchange words per utterance
+  const bool frag_ok = (lane >> 2) < nb;    // utterance (MMA column) lane / 4 exists
+  // this lane's fragment pair of k-step ks lives at frag0 + parity * S * RB * wpr + ks * 8
+  const unsigned long long* frag0 = p.ll + (static_cast<long long>(s) * RB + (lane >> 2)) * wpr + (lane & 3) * 2;
+  unsigned long long* const out0 = p.ll + (static_cast<long long>(s) * RB + pb) * wpr + ll_word(u0 + pu);
+  const long long par_stride = static_cast<long long>(S) * RB * wpr;
+
+  for (int t = 0; t < T; ++t) {
+    float xv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (has_pair) {
+      const float* xr = p.xg + (static_cast<long long>(b0 + pb) * T + t) * 4 * Hs + u0 + pu;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) xv[g] = xr[g * Hs];
+    }
+    float gsum[4] = {0.f, 0.f, 0.f, 0.f};
+    if (t > 0) {
+      const uint32_t flag = static_cast<uint32_t>(t);                 // h_{t-1} was published with flag (t-1) + 1
+      const unsigned long long* fr = frag0 + ((t - 1) & 1) * par_stride;
+      float acc[4][4];
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[mi][q] = 0.f;
+      if constexpr (KPER > 0) {
+        unsigned long long fa[KPER], fb[KPER];
+#pragma unroll
+        for (int i = 0; i < KPER; ++i) {
+          fa[i] = fb[i] = 0ull;
+          if (frag_ok) ll_load2(fr + (k_lo + i) * 8, fa[i], fb[i]);
+        }
+        if (frag_ok) ll_wait_all<KPER>(fr + k_lo * 8, 8, fa, fb, flag, p.spin_limit);
+#pragma unroll
+        for (int i = 0; i < KPER; ++i) {
+          const int k0 = (k_lo + i) * 16;
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) {
+            const int mt = mt_lo + mi;
+            if (mi < mt_half && mt < m_tiles) {
+              const int row = min(mt * 16 + (lane & 15), M - 1);
+              uint32_t a0, a1, a2, a3;
+              ldsm_x4(smem_addr(Ws + row * rs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+              mma16816(acc[mi], a0, a1, a2, a3, static_cast<uint32_t>(fa[i]), static_cast<uint32_t>(fb[i]));
+            }
+          }
+        }
+      } else {
+        for (int ks = k_lo; ks < k_hi; ++ks) {
+          unsigned long long fa = 0ull, fb = 0ull;
+          if (frag_ok) {
+            ll_load2(fr + ks * 8, fa, fb);
+            ll_wait2(fr + ks * 8, fa, fb, flag, p.spin_limit);
+          }
+          const int k0 = ks * 16;
+#pragma unroll
+          for (int mi = 0; mi < 4; ++mi) {
+            const int mt = mt_lo + mi;
+            if (mi < mt_half && mt < m_tiles) {
+              const int row = min(mt * 16 + (lane & 15), M - 1);
+              uint32_t a0, a1, a2, a3;
+              ldsm_x4(smem_addr(Ws + row * rs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+              mma16816(acc[mi], a0, a1, a2, a3, static_cast<uint32_t>(fa), static_cast<uint32_t>(fb));
+            }
+          }
+        }
+      }
+      float* Pt = P + (t & 1) * 4 * prow * 8;
+      float* Pw = Pt + kq * prow * 8;
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int mt = mt_lo + mi;
+        if (mi < mt_half && mt < m_tiles) {
+          const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
+          *reinterpret_cast<float2*>(Pw + r * 8 + c) = make_float2(acc[mi][0], acc[mi][1]);
+          *reinterpret_cast<float2*>(Pw + (r + 8) * 8 + c) = make_float2(acc[mi][2], acc[mi][3]);
+        }
+      }
+      __syncthreads();
+      if (has_pair) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int lc = g * U + pu;
+          float a = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) a += Pt[(w * prow + lc) * 8 + pb];
+          gsum[g] = a;
+        }
+      }
+    }
+    const float ai = xv[0] + gsum[0], af = xv[1] + gsum[1], ag = xv[2] + gsum[2], ao = xv[3] + gsum[3];
+    const float ig = sigmoid_sfu(ai), fg = sigmoid_sfu(af);
+    const float gg = tanh_sfu(ag), og = sigmoid_sfu(ao);
+    const float c = fg * creg + ig * gg;
+    creg = c;
+    const float h = has_pair ? og * tanh_sfu(c) : 0.f;
+    const __nv_bfloat16 hb = f2bf(h);
+    // exchange: the even unit of a pair publishes {h_u, h_{u+1}, flag}; U is even, so the partner is the next lane
+    const uint32_t mine = static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(&hb));
+    const uint32_t next = __shfl_down_sync(0xffffffffu, mine, 1);
+    if (has_pair && !(pu & 1) && t + 1 < T) ll_store(out0 + (t & 1) * par_stride, mine | (next << 16), static_cast<uint32_t>(t + 1));
+    if (has_pair) {                                // outputs / saves for the backward: off the critical path
+      const long long o = (static_cast<long long>(b0 + pb) * T + t) * Hs + u0 + pu;
+      p.h_bf16[o] = hb;
+      if (p.h_f32) p.h_f32[o] = h;
+      p.c_all[o] = c;
+      float* gr = p.gates + (static_cast<long long>(b0 + pb) * T + t) * 4 * Hs + u0 + pu;
+      gr[0] = ig; gr[Hs] = fg; gr[2 * Hs] = gg; gr[3 * Hs] = og;
+    }
+  }
+}
+
+template <int KPER>
+__global__ void __launch_bounds__(LTHREADS, 1) lstm_bwd_ll_kernel(const LstmLlP p) {
+  extern __shared__ __align__(16) uint8_t lsm[];
+  const int Hs = p.Hs, T = p.T, U = p.U, G = p.G;
+  const int K4 = 4 * Hs;
+  const int wrs = K4 + LPAD;
+  const int m_tiles = (U + 15) / 16;        // <= 2
+  const int prow = m_tiles * 16;
+  __nv_bfloat16* Wt = reinterpret_cast<__nv_bfloat16*>(lsm);        // [U][wrs]: Wt[u][col] = whh[col][u0+u]
+  float* P = reinterpret_cast<float*>(Wt + U * wrs);                // [2 step parities][8 warps][prow][8]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = gridDim.x / G;
+  const int s = blockIdx.x / G, j = blockIdx.x % G;
+  const int b0 = s * RB, nb = min(RB, p.B - b0);
+  const int u0 = j * U;
+
+  for (int i = tid; i < U * K4; i += LTHREADS) {
+    const int u = i % U, col = i / U;
+    Wt[u * wrs + col] = p.whh[static_cast<long long>(col) * p.ldw + u0 + u];
+  }
+  __syncthreads();
+
+  const int ksteps = Hs / 16;
+  const int kper = (ksteps + 7) / 8;
+  const int k_lo = warp * kper, k_hi = min(ksteps, k_lo + kper);
+  const int pr = tid;
+  const bool has_pair = pr < nb * U;
+  const int pb = has_pair ? pr / U : 0, pu = has_pair ? pr % U : 0;
+  float dc_carry = 0.f;
+  const int wpr = K4 / 2;                   // exchange words per utterance: [gate][Hs / 2]
+  const bool frag_ok = (lane >> 2) < nb;
+  const unsigned long long* frag0 = p.ll + (static_cast<long long>(s) * RB + (lane >> 2)) * wpr + (lane & 3) * 2;
+  unsigned long long* const out0 = p.ll + (static_cast<long long>(s) * RB + pb) * wpr + ll_word(u0 + pu);
+  const long long par_stride = static_cast<long long>(S) * RB * wpr;
+  unsigned int step = 0;
+
+  for (int t = T - 1; t >= 0; --t, ++step) {
+    float dh_rec = 0.f;
+    // this step's saved activations / upstream gradient: issued before the exchange wait so HBM latency is hidden
+    float ig = 0.f, fg = 0.f, gg = 0.f, og = 0.f, cv = 0.f, cprev = 0.f, dho = 0.f;
+    if (has_pair) {
+      const long long o = (static_cast<long long>(b0 + pb) * T + t) * Hs + u0 + pu;
+      const float* gr = p.gates + (static_cast<long long>(b0 + pb) * T + t) * K4 + u0 + pu;
+      ig = gr[0]; fg = gr[Hs]; gg = gr[2 * Hs]; og = gr[3 * Hs];
+      cv = p.c_all[o];
+      cprev = t > 0 ? p.c_all[o - Hs] : 0.f;
+      dho = p.dh_out[o];
+    }
+    if (step > 0) {
+      const uint32_t flag = step;                                     // dgates_{t+1} were published with flag (step-1) + 1
+      const unsigned long long* fr = frag0 + ((step - 1) & 1) * par_stride;
+      float acc[2][2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[a][b][q] = 0.f;
+      if constexpr (KPER > 0) {
+        // gate chunk g + 1's fragments are requested before chunk g's MMAs
+        unsigned long long fa[2][KPER], fb[2][KPER];
+#pragma unroll
+        for (int i = 0; i < KPER; ++i) {
+          fa[0][i] = fb[0][i] = 0ull;
+          if (frag_ok) ll_load2(fr + (k_lo + i) * 8, fa[0][i], fb[0][i]);
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int cur = g & 1;
+          if (g + 1 < 4) {
+#pragma unroll
+            for (int i = 0; i < KPER; ++i) {
+              fa[cur ^ 1][i] = fb[cur ^ 1][i] = 0ull;
+              if (frag_ok) ll_load2(fr + (g + 1) * (Hs / 2) + (k_lo + i) * 8, fa[cur ^ 1][i], fb[cur ^ 1][i]);
+            }
+          }
+          if (frag_ok) ll_wait_all<KPER>(fr + g * (Hs / 2) + k_lo * 8, 8, fa[cur], fb[cur], flag, p.spin_limit);
+#pragma unroll
+          for (int i = 0; i < KPER; ++i) {
+            const int k0 = (k_lo + i) * 16;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              if (mt < m_tiles) {
+                const int row = min(mt * 16 + (lane & 15), U - 1);
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4(smem_addr(Wt + row * wrs + g * Hs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+                mma16816(acc[mt][i & 1], a0, a1, a2, a3, static_cast<uint32_t>(fa[cur][i]), static_cast<uint32_t>(fb[cur][i]));
+              }
+            }
+          }
+        }
+      } else {
+        for (int g = 0; g < 4; ++g) {
+          for (int ks = k_lo; ks < k_hi; ++ks) {
+            unsigned long long fa = 0ull, fb = 0ull;
+            if (frag_ok) {
+              ll_load2(fr + g * (Hs / 2) + ks * 8, fa, fb);
+              ll_wait2(fr + g * (Hs / 2) + ks * 8, fa, fb, flag, p.spin_limit);
+            }
+            const int k0 = ks * 16;
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              if (mt < m_tiles) {
+                const int row = min(mt * 16 + (lane & 15), U - 1);
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4(smem_addr(Wt + row * wrs + g * Hs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+                mma16816(acc[mt][0], a0, a1, a2, a3, static_cast<uint32_t>(fa), static_cast<uint32_t>(fb));
+              }
+            }
+          }
+        }
+      }
+      float* Pt = P + (step & 1) * 8 * prow * 8;
+      float* Pw = Pt + warp * prow * 8;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        if (mt < m_tiles) {
+          const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
+          *reinterpret_cast<float2*>(Pw + r * 8 + c) = make_float2(acc[mt][0][0] + acc[mt][1][0], acc[mt][0][1] + acc[mt][1][1]);
+          *reinterpret_cast<float2*>(Pw + (r + 8) * 8 + c) =
+              make_float2(acc[mt][0][2] + acc[mt][1][2], acc[mt][0][3] + acc[mt][1][3]);
+        }
+      }
+      __syncthreads();
+      if (has_pair) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) dh_rec += Pt[(w * prow + pu) * 8 + pb];
+      }
+    }
+    const float dh = dho + dh_rec;
+    const float tc = tanhf(cv);
+    const float dc = dh * og * (1.f - tc * tc) + dc_carry;
+    dc_carry = dc * fg;
+    const float dg4[4] = {dc * gg * ig * (1.f - ig), dc * cprev * fg * (1.f - fg), dc * ig * (1.f - gg * gg), dh * tc * og * (1.f - og)};
+    uint32_t mine[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const __nv_bfloat16 v = f2bf(has_pair ? dg4[g] : 0.f);
+      mine[g] = static_cast<uint32_t>(*reinterpret_cast<const unsigned short*>(&v));
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t next = __shfl_down_sync(0xffffffffu, mine[g], 1);
+      if (has_pair && !(pu & 1) && t > 0)
+        ll_store(out0 + (step & 1) * par_stride + g * (Hs / 2), mine[g] | (next << 16), step + 1);
+    }
+    if (has_pair) {                                // full dgates tensor for the dW / dx GEMMs: off the critical path
+      unsigned short* dg = reinterpret_cast<unsigned short*>(p.dgates) + (static_cast<long long>(b0 + pb) * T + t) * K4 + u0 + pu;
+      dg[0] = static_cast<unsigned short>(mine[0]); dg[Hs] = static_cast<unsigned short>(mine[1]);
+      dg[2 * Hs] = static_cast<unsigned short>(mine[2]); dg[3 * Hs] = static_cast<unsigned short>(mine[3]);
+    }
+  }
+}
+
 // Pick the group size G (CTAs per 8-utterance slice): U = Hs / G hidden units per CTA must be integral, the 8 x U
 // (utterance, unit) pairs must fit one thread each, the weight slice must fit shared memory and all S * G CTAs must be
 // co-resident.  Returns 0 when the batch-sliced kernels do not apply (the whole-batch kernels are used instead).
@@ -651,6 +1018,33 @@ static int lstm_bs_pick(int B, int Hs, bool bwd, size_t* smem_out) {
     return G;
   }
   return 0;
+}
+
+// The flag-in-data kernels apply when the batch-sliced partition exists, U is even (unit pairs never straddle CTAs) and
+// their shared-memory layout (weights + double-buffered partials, no staging tile) fits.
+static int lstm_ll_pick(int B, int Hs, bool bwd, size_t* smem_out) {
+  if (getenv("MTASR_LSTM_NO_LL")) return 0;
+  size_t dummy = 0;
+  const int G = lstm_bs_pick(B, Hs, bwd, &dummy);
+  if (G <= 0) return 0;
+  const int U = Hs / G;
+  if (U % 2 != 0) return 0;
+  size_t smem;
+  if (!bwd) {
+    const int M = 4 * U, mt = (M + 15) / 16;
+    smem = static_cast<size_t>(M) * (Hs + LPAD) * 2 + static_cast<size_t>(2) * 4 * mt * 16 * 8 * 4;
+  } else {
+    const int mt = (U + 15) / 16;
+    smem = static_cast<size_t>(U) * (4 * Hs + LPAD) * 2 + static_cast<size_t>(2) * 8 * mt * 16 * 8 * 4;
+  }
+  if (smem > 232448) return 0;
+  *smem_out = smem;
+  return G;
+}
+static constexpr size_t LL_OFFSET = 256;   // the group counters of the counter-based kernels live in front of the words
+static size_t lstm_ll_bytes(int B, int Hs, bool bwd) {
+  const size_t S = (B + RB - 1) / RB;
+  return static_cast<size_t>(2) * S * RB * (static_cast<size_t>(bwd ? 4 : 1) * Hs / 2) * 8;
 }
 
 static size_t lstm_fwd_smem(int Hs, int Bp) {
@@ -686,10 +1080,38 @@ static int lstm_check(int B, int T, int Hs, int ldw, const char* who) {
 
 using namespace mtasr;
 
+extern "C" int64_t mtasr_lstm_scratch_bytes(int32_t B, int32_t Hs, int32_t backward) {
+  if (B <= 0 || Hs <= 0) return static_cast<int64_t>(LL_OFFSET);
+  return static_cast<int64_t>(LL_OFFSET + lstm_ll_bytes(B, Hs, backward != 0));
+}
+
 extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw, int32_t B, int32_t T, int32_t Hs,
                               void* h_bf16, float* h_f32, float* c_all, float* gates, uint32_t* barrier, void* stream) {
   MTASR_CHECK_ARG(xg && whh_bf16 && h_bf16 && c_all && gates && barrier, "lstm_fwd: null pointer");
+  MTASR_CHECK_ARG((reinterpret_cast<uintptr_t>(barrier) & 15) == 0, "lstm_fwd: scratch must be 16-byte aligned");
   cudaStream_t st0 = static_cast<cudaStream_t>(stream);
+  {
+    size_t smem_ll = 0;
+    const int G = lstm_ll_pick(B, Hs, false, &smem_ll);
+    if (G > 0 && T > 0 && ldw % 8 == 0) {
+      const int S = (B + RB - 1) / RB;
+      LstmLlP q{};
+      q.xg = xg; q.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16); q.h_bf16 = reinterpret_cast<__nv_bfloat16*>(h_bf16);
+      q.h_f32 = h_f32; q.c_all = c_all; q.gates = gates;
+      q.ll = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(barrier) + LL_OFFSET);
+      q.B = B; q.T = T; q.Hs = Hs; q.ldw = ldw; q.G = G; q.U = Hs / G;
+      q.spin_limit = lstm_spin_limit();
+      void (*kern)(const LstmLlP) = (Hs == 896) ? lstm_fwd_ll_kernel<14> : lstm_fwd_ll_kernel<0>;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_ll)) != cudaSuccess)
+        return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: cannot set smem attribute");
+      if (cudaMemsetAsync(q.ll, 0, lstm_ll_bytes(B, Hs, false), st0) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: memset failed");
+      void* args[] = {&q};
+      cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(S * G), dim3(LTHREADS), args, smem_ll, st0);
+      MTASR_COUNT_LAUNCH();
+      if (e != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: cooperative launch failed: %s", cudaGetErrorString(e));
+      return MTASR_OK;
+    }
+  }
   {
     size_t smem_bs = 0;
     const int G = getenv("MTASR_LSTM_WHOLE_BATCH") ? 0 : lstm_bs_pick(B, Hs, false, &smem_bs);
@@ -735,7 +1157,30 @@ extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw
 extern "C" int mtasr_lstm_bwd(const float* dh_out, const float* gates, const float* c_all, const void* whh_bf16, int32_t ldw,
                               int32_t B, int32_t T, int32_t Hs, void* dgates_bf16, uint32_t* barrier, void* stream) {
   MTASR_CHECK_ARG(dh_out && gates && c_all && whh_bf16 && dgates_bf16 && barrier, "lstm_bwd: null pointer");
+  MTASR_CHECK_ARG((reinterpret_cast<uintptr_t>(barrier) & 15) == 0, "lstm_bwd: scratch must be 16-byte aligned");
   cudaStream_t st0 = static_cast<cudaStream_t>(stream);
+  {
+    size_t smem_ll = 0;
+    const int G = lstm_ll_pick(B, Hs, true, &smem_ll);
+    if (G > 0 && T > 0 && ldw % 8 == 0) {
+      const int S = (B + RB - 1) / RB;
+      LstmLlP q{};
+      q.whh = reinterpret_cast<const __nv_bfloat16*>(whh_bf16); q.c_all = const_cast<float*>(c_all); q.gates = const_cast<float*>(gates);
+      q.dh_out = dh_out; q.dgates = reinterpret_cast<__nv_bfloat16*>(dgates_bf16);
+      q.ll = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(barrier) + LL_OFFSET);
+      q.B = B; q.T = T; q.Hs = Hs; q.ldw = ldw; q.G = G; q.U = Hs / G;
+      q.spin_limit = lstm_spin_limit();
+      void (*kern)(const LstmLlP) = (Hs == 896) ? lstm_bwd_ll_kernel<7> : lstm_bwd_ll_kernel<0>;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_ll)) != cudaSuccess)
+        return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: cannot set smem attribute");
+      if (cudaMemsetAsync(q.ll, 0, lstm_ll_bytes(B, Hs, true), st0) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: memset failed");
+      void* args[] = {&q};
+      cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(S * G), dim3(LTHREADS), args, smem_ll, st0);
+      MTASR_COUNT_LAUNCH();
+      if (e != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_bwd: cooperative launch failed: %s", cudaGetErrorString(e));
+      return MTASR_OK;
+    }
+  }
   {
     size_t smem_bs = 0;
     const int G = getenv("MTASR_LSTM_WHOLE_BATCH") ? 0 : lstm_bs_pick(B, Hs, true, &smem_bs);

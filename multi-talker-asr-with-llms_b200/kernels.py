@@ -217,16 +217,23 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor, *,
                   dres: Optional[torch.Tensor] = None, want_f32: bool = True, want_bf16: bool = False,
-                  want_param_grads: bool = True):
+                  want_param_grads: bool = True, want_dxsum: bool = False):
+    """-> dx_f32, dx_bf16, dgamma, dbeta[, dxsum].  One kernel: dx (+ dres) and every requested column reduction
+    (dxsum = sum over rows of dx, the bias gradient of the Linear that produced the tensor dx is the gradient of)."""
     D = x.shape[-1]
     rows = x.numel() // D
     dy = dy.contiguous()
     dxf = torch.empty(x.shape, device=x.device, dtype=torch.float32) if want_f32 else None
     dxb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
-    dgb = torch.zeros(2, D, device=x.device, dtype=torch.float32) if want_param_grads else None   # one fill for both
-    dg, db = (dgb[0], dgb[1]) if want_param_grads else (None, None)
-    check(_lib.load().mtasr_layernorm_bwd(_p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma), _p(dres), rows, D,
-                                          _p(dxf), _p(dxb), _p(dg), _p(db), _stream()), "mtasr_layernorm_bwd")
+    want_dxsum = want_dxsum and (want_f32 or want_bf16)
+    nsum = (2 if want_param_grads else 0) + (1 if want_dxsum else 0)
+    sums = torch.zeros(nsum, D, device=x.device, dtype=torch.float32) if nsum else None   # one fill for all reductions
+    dg, db = (sums[0], sums[1]) if want_param_grads else (None, None)
+    dxs = sums[nsum - 1] if want_dxsum else None
+    check(_lib.load().mtasr_layernorm_bwd_sums(_p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma), _p(dres), rows, D,
+                                               _p(dxf), _p(dxb), _p(dg), _p(db), _p(dxs), _stream()), "mtasr_layernorm_bwd_sums")
+    if want_dxsum:
+        return dxf, dxb, dg, db, dxs
     return dxf, dxb, dg, db
 
 
@@ -344,20 +351,22 @@ def colsum(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def relpos_gate_fwd(x, wab, bab, cst, B, T, H):
+def relpos_gate_fwd(x, w8, b8, cst, B, T, H):
+    """w8 (8,64) / b8 (8) fp32 = gru_rel_pos_linear as stored (the 4-row sums of hf:170-173 happen inside the kernel)."""
     gate = torch.empty(B, H, T, device=x.device, dtype=torch.float32)
-    check(_lib.load().mtasr_relpos_gate_fwd(_p(x), _dt(x), _p(wab), _p(bab), _p(cst), B, T, H, _p(gate), _stream()),
+    check(_lib.load().mtasr_relpos_gate_fwd(_p(x), _dt(x), _p(w8), _p(b8), _p(cst), B, T, H, _p(gate), _stream()),
           "mtasr_relpos_gate_fwd")
     return gate
 
 
-def relpos_gate_bwd(x, wab, bab, cst, dgate, B, T, H):
+def relpos_gate_bwd(x, w8, b8, cst, dgate, B, T, H):
+    """-> dx (B,T,H*64) f32, dw8 (8,64), db8 (8), dcst (H)."""
     dx = torch.empty(B, T, H * 64, device=x.device, dtype=torch.float32)
-    acc = torch.zeros(128 + 4 + H, device=x.device, dtype=torch.float32)                            # one fill for the three
-    dwab, dbab, dcst = acc[:128], acc[128:130], acc[132:132 + H]
-    check(_lib.load().mtasr_relpos_gate_bwd(_p(x), _dt(x), _p(wab), _p(bab), _p(cst), _p(dgate), B, T, H, _p(dx), _p(dwab),
-                                            _p(dbab), _p(dcst), _stream()), "mtasr_relpos_gate_bwd")
-    return dx, dwab, dbab, dcst
+    acc = torch.zeros(512 + 8 + H, device=x.device, dtype=torch.float32)                            # one fill for the three
+    dw8, db8, dcst = acc[:512].view(8, 64), acc[512:520], acc[520:520 + H]
+    check(_lib.load().mtasr_relpos_gate_bwd(_p(x), _dt(x), _p(w8), _p(b8), _p(cst), _p(dgate), B, T, H, _p(dx), _p(dw8),
+                                            _p(db8), _p(dcst), _stream()), "mtasr_relpos_gate_bwd")
+    return dx, dw8, db8, dcst
 
 
 def attn_fwd(qkv, gate, table, klen, B, H, T, scale, drop=None):
@@ -614,7 +623,7 @@ def lstm_fwd(xg: torch.Tensor, whh: torch.Tensor, ldw: int, want_h_f32: bool = F
     hf = torch.empty(B, T, Hs, device=dev, dtype=torch.float32) if want_h_f32 else None
     c = torch.empty(B, T, Hs, device=dev, dtype=torch.float32)
     gates = torch.empty(B, T, H4, device=dev, dtype=torch.float32)
-    bar = torch.zeros(64, device=dev, dtype=torch.int32)      # one counter per 8-utterance slice
+    bar = torch.empty(int(_lib.load().mtasr_lstm_scratch_bytes(B, Hs, 0)), device=dev, dtype=torch.uint8)   # initialised by the call
     check(_lib.load().mtasr_lstm_fwd(_p(xg), _p(whh), ldw, B, T, Hs, _p(h), _p(hf), _p(c), _p(gates), _p(bar), _stream()),
           "mtasr_lstm_fwd")
     return h, hf, c, gates
@@ -624,7 +633,7 @@ def lstm_bwd(dh: torch.Tensor, gates: torch.Tensor, c: torch.Tensor, whh: torch.
     B, T, Hs = dh.shape
     dh = dh.contiguous()
     dgates = torch.empty(B, T, 4 * Hs, device=dh.device, dtype=torch.bfloat16)
-    bar = torch.zeros(64, device=dh.device, dtype=torch.int32)
+    bar = torch.empty(int(_lib.load().mtasr_lstm_scratch_bytes(B, Hs, 1)), device=dh.device, dtype=torch.uint8)
     check(_lib.load().mtasr_lstm_bwd(_p(dh), _p(gates), _p(c), _p(whh), ldw, B, T, Hs, _p(dgates), _p(bar), _stream()),
           "mtasr_lstm_bwd")
     return dgates

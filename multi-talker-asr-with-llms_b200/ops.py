@@ -266,26 +266,22 @@ class RelPosGateFn(Function):
         if weight.shape != (8, 64) or D % 64 != 0:
             raise NotImplementedError("mtasr_b200: gru_rel_pos gate expects head_dim 64 and an (8, 64) projection")
         H = D // 64
-        w = weight.detach().float()
-        b = bias.detach().float()
-        wab = torch.cat([w[:4].sum(0), w[4:].sum(0)]).contiguous()
-        bab = torch.stack([b[:4].sum(), b[4:].sum()]).contiguous()
-        cst = const.detach().float().reshape(H).contiguous()
+        w8, b8, cst = _gate_params(weight, bias, const, H)
         x = h.detach().contiguous()
-        gate = K.relpos_gate_fwd(x, wab, bab, cst, B, T, H)
+        gate = K.relpos_gate_fwd(x, w8, b8, cst, B, T, H)
         ctx.dims = (B, T, H)
-        ctx.save_for_backward(x, wab, bab, cst)
+        ctx.save_for_backward(x, w8, b8, cst)
         ctx.const_shape = const.shape
         return gate
 
     @staticmethod
     def backward(ctx, dgate):
-        x, wab, bab, cst = ctx.saved_tensors
+        x, w8, b8, cst = ctx.saved_tensors
         B, T, H = ctx.dims
-        dx, dwab, dbab, dcst = K.relpos_gate_bwd(x, wab, bab, cst, dgate.contiguous().float(), B, T, H)
+        dx, dw8, db8, dcst = K.relpos_gate_bwd(x, w8, b8, cst, dgate.contiguous().float(), B, T, H)
         dh = dx.to(x.dtype) if ctx.needs_input_grad[0] else None
-        dw = torch.cat([dwab[:64].expand(4, 64), dwab[64:].expand(4, 64)], 0) if ctx.needs_input_grad[1] else None
-        db = torch.cat([dbab[0:1].expand(4), dbab[1:2].expand(4)]) if ctx.needs_input_grad[2] else None
+        dw = dw8 if ctx.needs_input_grad[1] else None
+        db = db8 if ctx.needs_input_grad[2] else None
         dc = dcst.view(ctx.const_shape) if ctx.needs_input_grad[3] else None
         return dh, dw, db, dc
 
@@ -388,30 +384,36 @@ class AttentionFn(Function):
 _bf16_twins = {}
 
 
-def _publish_twin(t32: torch.Tensor, tb: torch.Tensor) -> None:
+def _publish_twin(t32: torch.Tensor, tb: torch.Tensor, colsum: Optional[torch.Tensor] = None) -> None:
     if len(_bf16_twins) > 16:
         _bf16_twins.clear()
     try:
-        _bf16_twins[id(t32)] = (weakref.ref(t32), t32._version, tb)
+        _bf16_twins[id(t32)] = (weakref.ref(t32), t32._version, tb, colsum)
     except TypeError:
         pass
 
 
-def _cast_or_twin(dy: torch.Tensor) -> torch.Tensor:
-    """bf16 (rows, D) operand copy of the fp32 gradient `dy`."""
+def _twin_and_sum(dy: torch.Tensor):
+    """(bf16 (rows, D) operand copy of the fp32 gradient `dy`, its fp32 column sums or None).  The column sums are the bias
+    gradient of the Linear that produced the tensor `dy` is the gradient of; the LayerNorm backward that emitted `dy`
+    reduced them in the same pass (K.layernorm_bwd(want_dxsum=True))."""
     hit = _bf16_twins.pop(id(dy), None)
     if hit is not None and hit[0]() is dy and hit[1] == dy._version and hit[2].numel() == dy.numel():
-        return hit[2].view(-1, dy.shape[-1])
-    return K.cast_bf16(dy.view(-1, dy.shape[-1]))
+        return hit[2].view(-1, dy.shape[-1]), hit[3]
+    return K.cast_bf16(dy.view(-1, dy.shape[-1])), None
+
+
+def _cast_or_twin(dy: torch.Tensor) -> torch.Tensor:
+    """bf16 (rows, D) operand copy of the fp32 gradient `dy`."""
+    return _twin_and_sum(dy)[0]
 
 
 def _gate_params(weight, bias, const, H):
-    """4-row sums of gru_rel_pos_linear (8,64) / its bias, and gru_rel_pos_const as (H,) -- see RelPosGateFn."""
-    w = weight.detach().float()
-    b = bias.detach().float()
-    wab = torch.cat([w[:4].sum(0), w[4:].sum(0)]).contiguous()
-    bab = torch.stack([b[:4].sum(), b[4:].sum()]).contiguous()
-    return wab, bab, const.detach().float().reshape(H).contiguous()
+    """gru_rel_pos_linear (8,64) / its bias (8) / gru_rel_pos_const (H,) as contiguous fp32 views -- no arithmetic here: the
+    4-row sums of hf:170-173 and their transposed expansion in the backward live inside the relpos_gate kernels (they were
+    eight tiny torch launches per layer and step)."""
+    return (weight.detach().float().contiguous(), bias.detach().float().contiguous(),
+            const.detach().float().reshape(H).contiguous())
 
 
 class PreLNAttentionFn(Function):
@@ -457,20 +459,21 @@ class PreLNAttentionFn(Function):
         need = ctx.needs_input_grad
         drop_out, drop_attn = ctx.drops
         dy = dy.contiguous()
-        dyb = _masked_bf16(dy, drop_out) if drop_out is not None else _cast_or_twin(dy)
+        dyb, dysum = (_masked_bf16(dy, drop_out), None) if drop_out is not None else _twin_and_sum(dy)
         dO = K.linear_dgrad(dyb, wob)
         dwo = K.linear_wgrad(dyb, O) if need[10] else None
-        dbo = K.colsum(dyb) if need[11] else None
+        dbo = (dysum if dysum is not None else K.colsum(dyb)) if need[11] else None
         dqkv, dgate, dtable = K.attn_bwd(qkv, O, dO, lse, gate, tab, klen, B, H, T, scale, drop=drop_attn)
         dxg, dwab, dbab, dcst = K.relpos_gate_bwd(h1, wab, bab, cst, dgate, B, T, H)           # gate path into LN(x), fp32
         dx = dlnw = dlnb = None
         if need[0] or need[1] or need[2]:
             dh1 = K.linear_dgrad(dqkv, wqkv, residual=dxg.view(B * T, D))                      # QKV dgrad + gate path, one epilogue
-            dxf, dxb, dlnw, dlnb = K.layernorm_bwd(dh1.view(B, T, D), xf, mean, rstd, gamma, dres=dy, want_f32=True,
-                                                   want_bf16=need[0], want_param_grads=need[1] or need[2])
+            dxf, dxb, dlnw, dlnb, dxs = K.layernorm_bwd(dh1.view(B, T, D), xf, mean, rstd, gamma, dres=dy, want_f32=True,
+                                                        want_bf16=need[0], want_param_grads=need[1] or need[2],
+                                                        want_dxsum=need[0])
             dx = dxf if need[0] else None
             if dx is not None:
-                _publish_twin(dx, dxb)
+                _publish_twin(dx, dxb, dxs)
         dwq = dwk = dwv = dbq = dbk = dbv = None
         if need[4] or need[6] or need[8]:
             dwqkv = K.linear_wgrad(dqkv, h1.view(B * T, D))
@@ -478,8 +481,8 @@ class PreLNAttentionFn(Function):
         if need[5] or need[7] or need[9]:
             dbqkv = K.colsum(dqkv)
             dbq, dbk, dbv = dbqkv[:D], dbqkv[D:2 * D], dbqkv[2 * D:]
-        dgw = torch.cat([dwab[:64].expand(4, 64), dwab[64:].expand(4, 64)], 0) if need[12] else None
-        dgb = torch.cat([dbab[0:1].expand(4), dbab[1:2].expand(4)]) if need[13] else None
+        dgw = dwab if need[12] else None
+        dgb = dbab if need[13] else None
         dgc = dcst.view(ctx.const_shape) if need[14] else None
         return (dx, dlnw, dlnb, None, dwq, dbq, dwk, dbk, dwv, dbv, dwo, dbo, dgw, dgb, dgc,
                 dtable if need[15] else None, None, None, None, None)
@@ -511,20 +514,21 @@ class PreLNFFNFn(Function):
         D = xf.shape[-1]
         drop_act, drop_out = ctx.drops
         dy = dy.contiguous()
-        dyb = _masked_bf16(dy, drop_out) if drop_out is not None else _cast_or_twin(dy)
+        dyb, dysum = (_masked_bf16(dy, drop_out), None) if drop_out is not None else _twin_and_sum(dy)
         du = K.linear_dgrad(dyb, w2b, act=K.ACT_GELU_BWD, act_src=u, drop=drop_act)
         dx = dlnw = dlnb = None
         if need[0] or need[1] or need[2]:
             dh = K.linear_dgrad(du, w1b)
-            dxf, dxb, dlnw, dlnb = K.layernorm_bwd(dh.view(xf.shape), xf, mean, rstd, gamma, dres=dy, want_f32=True,
-                                                   want_bf16=need[0], want_param_grads=need[1] or need[2])
+            dxf, dxb, dlnw, dlnb, dxs = K.layernorm_bwd(dh.view(xf.shape), xf, mean, rstd, gamma, dres=dy, want_f32=True,
+                                                        want_bf16=need[0], want_param_grads=need[1] or need[2],
+                                                        want_dxsum=need[0])
             dx = dxf if need[0] else None
             if dx is not None:
-                _publish_twin(dx, dxb)
+                _publish_twin(dx, dxb, dxs)
         dw1 = K.linear_wgrad(du, hb.view(-1, D)) if need[4] else None
         db1 = K.colsum(du) if need[5] else None
         dw2 = K.linear_wgrad(dyb, a) if need[6] else None
-        db2 = K.colsum(dyb) if need[7] else None
+        db2 = (dysum if dysum is not None else K.colsum(dyb)) if need[7] else None
         return dx, dlnw, dlnb, None, dw1, db1, dw2, db2, None, None
 
 

@@ -212,6 +212,24 @@ def test_lstm_layer_random_recurrence_vs_torch_loop(cuda, B, T, Hs):
         assert e[k] < max(1.5 * y[k], 2e-2), (k, e, y)
 
 
+def test_lstm_counter_exchange_fallback(cuda, monkeypatch):
+    """MTASR_LSTM_NO_LL=1 selects the counter-based exchange kernels (the fallback for odd units-per-CTA): same results as
+    the flag-in-data kernels on the multi-slice shape, bit for bit in h (identical arithmetic, different plumbing)."""
+    from mtasr_b200 import kernels as K
+    torch.manual_seed(5)
+    B, T, Hs = 12, 61, 896
+    xg = torch.randn(B, T, 4 * Hs, device=cuda) * 0.5
+    W = (torch.randn(4 * Hs, 2 * Hs, device=cuda) * 0.05).to(torch.bfloat16)
+    dh = torch.randn(B, T, Hs, device=cuda)
+    h1, _, c1, g1 = K.lstm_fwd(xg, W[:, Hs:], 2 * Hs)
+    d1 = K.lstm_bwd(dh, g1, c1, W[:, Hs:], 2 * Hs)
+    monkeypatch.setenv("MTASR_LSTM_NO_LL", "1")
+    h2, _, c2, g2 = K.lstm_fwd(xg, W[:, Hs:], 2 * Hs)
+    d2 = K.lstm_bwd(dh, g2, c2, W[:, Hs:], 2 * Hs)
+    assert torch.equal(h1, h2) and torch.equal(c1, c2) and torch.equal(g1, g2)
+    assert rel(d1, d2) < 1e-3
+
+
 def test_lstm_saved_cell_state_matches_loop(cuda):
     """c_t saved by the forward kernel (input of the BPTT kernel) against the loop, B = 32 / Hs = 896."""
     from mtasr_b200 import kernels as K

@@ -10,12 +10,11 @@ def _rel(a, b):
     return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20)).item()
 
 
-@pytest.mark.parametrize("D", [512, 896, 1024, 128, 64])
+@pytest.mark.parametrize("D,rows", [(512, 777), (896, 777), (1024, 777), (128, 777), (64, 777), (768, 301), (8, 5), (1024, 1), (1024, 15968)])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
-def test_layernorm_fwd_bwd(cuda, D, dt):
+def test_layernorm_fwd_bwd(cuda, D, rows, dt):
     from mtasr_b200 import kernels as Kn
     torch.manual_seed(0)
-    rows = 777
     x = (torch.randn(rows, D, device=cuda) * 2 + 0.5).to(dt)
     gamma, beta = torch.randn(D, device=cuda), torch.randn(D, device=cuda)
     yb, yf, mean, rstd = Kn.layernorm_fwd(x, gamma, beta, 1e-5, out_bf16=True, out_f32=True)
@@ -25,10 +24,22 @@ def test_layernorm_fwd_bwd(cuda, D, dt):
     assert _rel(yf, ref) < 1e-5 and _rel(yb, ref) < 5e-3
     dy = torch.randn(rows, D, device=cuda)
     dres = torch.randn(rows, D, device=cuda)
-    dxf, dxb, dg, db = Kn.layernorm_bwd(dy, x, mean, rstd, gamma, dres=dres, want_bf16=True)
+    dxf, dxb, dg, db, dxs = Kn.layernorm_bwd(dy, x, mean, rstd, gamma, dres=dres, want_bf16=True, want_dxsum=True)
     ref.backward(dy)
     assert _rel(dxf, xr.grad + dres) < 1e-5 and _rel(dxb, xr.grad + dres) < 5e-3
     assert _rel(dg, gr.grad) < 1e-4 and _rel(db, br.grad) < 1e-4
+    assert _rel(dxs, (xr.grad + dres).sum(0)) < 1e-4        # column sums of dx: the neighbouring Linear's bias gradient
+    # the separate entry points of the same pass: no dres / no sums, bf16 upstream gradient, parameter gradients only
+    o = Kn.layernorm_bwd(dy, x, mean, rstd, gamma, want_param_grads=False)
+    assert _rel(o[0], xr.grad) < 1e-5 and o[2] is None and o[3] is None
+    dyb = dy.to(torch.bfloat16)
+    xr.grad = None; gr.grad = None; br.grad = None
+    F.layer_norm(xr, (D,), gr, br, 1e-5).backward(dyb.float())
+    o = Kn.layernorm_bwd(dyb, x, mean, rstd, gamma, want_f32=False, want_bf16=True, want_dxsum=True)
+    assert o[0] is None and _rel(o[1], xr.grad) < 5e-3 and _rel(o[2], gr.grad) < 1e-4 and _rel(o[3], br.grad) < 1e-4
+    assert _rel(o[4], xr.grad.sum(0)) < 1e-3
+    o = Kn.layernorm_bwd(dyb, x, mean, rstd, gamma, want_f32=False, want_bf16=False)
+    assert o[0] is None and o[1] is None and _rel(o[2], gr.grad) < 1e-4 and _rel(o[3], br.grad) < 1e-4
     g2, _, _, _ = Kn.layernorm_fwd(x, gamma, beta, 1e-5, post_gelu=True)
     assert _rel(g2, F.gelu(ref.detach())) < 5e-3
 

@@ -34,12 +34,13 @@ yb, _, mean, rstd = Kn.layernorm_fwd(x32, g, b, 1e-5)
 dyb = torch.randn(M, D, device=dev).to(torch.bfloat16)
 dres = torch.randn(M, D, device=dev)
 rep("ln_bwd (dy bf16, x f32)->f32", timeit(lambda: Kn.layernorm_bwd(dyb, x32, mean, rstd, g, dres=dres)), M * D * 14)
+rep("ln_bwd + bf16 twin + 3 sums", timeit(lambda: Kn.layernorm_bwd(dyb, x32, mean, rstd, g, dres=dres, want_bf16=True, want_dxsum=True)), M * D * 16)
 rep("cast f32->bf16", timeit(lambda: Kn.cast_bf16(x32)), M * D * 6)
 big = torch.randn(M, 4096, device=dev).to(torch.bfloat16)
 rep("colsum bf16 (M,4096)", timeit(lambda: Kn.colsum(big)), M * 4096 * 2)
 rep("colsum bf16 (M,1024)", timeit(lambda: Kn.colsum(xb)), M * D * 2)
 w = torch.randn(8, 64, device=dev); bb = torch.randn(8, device=dev); cst = torch.rand(1, H, 1, 1, device=dev)
-wab = torch.cat([w[:4].sum(0), w[4:].sum(0)]).contiguous(); bab = torch.stack([bb[:4].sum(), bb[4:].sum()]); c1 = cst.reshape(H).contiguous()
+wab, bab, c1 = w.contiguous(), bb.contiguous(), cst.reshape(H).contiguous()   # raw (8,64) / (8,) projection: summed in-kernel
 h3 = xb.view(B, T, D)
 rep("gate fwd", timeit(lambda: Kn.relpos_gate_fwd(h3, wab, bab, c1, B, T, H)), M * D * 2)
 dg = torch.randn(B, H, T, device=dev)
