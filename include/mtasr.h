@@ -186,10 +186,15 @@ int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void* x, int32_t
                         void* dx_bf16, float* dgamma, float* dbeta, void* stream);
 /* The same pass additionally ACCUMULATES dxsum[c] += sum_rows dx[row][c] (zero it first): the bias gradient of the Linear
  * whose output gradient this dx is (out-proj / FFN2 of the neighbouring half encoder layer, hf:355-366), so that no
- * separate column-sum pass re-reads dx.  dxsum needs dx_f32 or dx_bf16; any of dgamma / dbeta / dxsum may be NULL. */
+ * separate column-sum pass re-reads dx.  dxsum needs dx_f32 or dx_bf16; any of dgamma / dbeta / dxsum may be NULL.
+ * gate_ab (rows, D/64, 2) f32 + gate_w8 (8, 64) f32 (both or neither): the upstream gradient additionally receives the
+ * gru_rel_pos gate's path into the LayerNorm output, dy[r][c] += da[r][c/64] * wa[c%64] + db[r][c/64] * wb[c%64] with
+ * wa / wb the 4-row sums of gate_w8 (mtasr_relpos_gate_bwd with dab instead of dx) -- the rank-2-per-head term is never
+ * materialised as a (rows, D) tensor. */
 int mtasr_layernorm_bwd_sums(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
                              const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D,
-                             float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, void* stream);
+                             float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, const float* gate_ab,
+                             const float* gate_w8, void* stream);
 int mtasr_cast_f32_bf16(const float* x, void* y_bf16, int64_t n, void* stream);
 /* Label splitter of ref:utils/split_labels_by_sc.py:21-75 on the device: labels (B, L) i64 with row stride ld -> out (K, B, L) i64
  * (must arrive filled with the pad value), lens (K, B) i64, status (3) i32 = {smallest failing row, INT32_MAX if none; kind:
@@ -233,12 +238,14 @@ int mtasr_colsum(const void* x, int32_t dtype, int64_t M, int32_t N, int64_t ld,
 /* gru_rel_pos gate of hf:167-176 for every (b, t, head), head_dim 64: w8 (8,64) / b8 (8) = gru_rel_pos_linear as stored
  * (rows 0..3 and 4..7 are summed inside the kernel: view(..., 2, 4).sum(-1)), cst (H) = gru_rel_pos_const; x (B,T,H*64)
  * f32|bf16 is the attention input.  gate (B,H,T) f32 = sigmoid(a) * (sigmoid(b) * cst[h] - 1) + 2.  Backward: dx
- * (B,T,H*64) f32 written, dw8 (8,64) / db8 (8) / dcst (H) ACCUMULATED (zero them first). */
+ * (B,T,H*64) f32 and / or dab (B*T, H, 2) f32 = the gradients wrt the two pre-sigmoid sums (dx = da * wa + db * wb per head
+ * slice: consumers that can add this rank-2 term themselves take dab and pass dx = NULL) written, dw8 (8,64) / db8 (8) /
+ * dcst (H) ACCUMULATED (zero them first). */
 int mtasr_relpos_gate_fwd(const void* x, int32_t x_dtype, const float* w8, const float* b8, const float* cst, int32_t B,
                           int32_t T, int32_t H, float* gate, void* stream);
 int mtasr_relpos_gate_bwd(const void* x, int32_t x_dtype, const float* w8, const float* b8, const float* cst,
-                          const float* dgate, int32_t B, int32_t T, int32_t H, float* dx, float* dw8, float* db8, float* dcst,
-                          void* stream);
+                          const float* dgate, int32_t B, int32_t T, int32_t H, float* dx, float* dab, float* dw8, float* db8,
+                          float* dcst, void* stream);
 /* softmax(S*scale + gate[b,h,q]*table[h,k-q+T-1]) over keys k < klen[b] (hf:167-180 + hf:206-228 fused);
  * S (B,H,T,Tp) f32, gate (B,H,T) f32, table (H,2T-1) f32, klen (B) i32 or NULL, P (B,H,T,Tp) bf16. */
 int mtasr_attn_softmax_fwd(const float* S, const float* gate, const float* table, const int32_t* klen, int32_t B,

@@ -71,14 +71,14 @@ SIGNATURES = {
     "mtasr_ctc_scatter_rows": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _I64, _I64, _P, _P, _P]),
     "mtasr_layernorm_fwd": (C.c_int, [_P, _I32, _P, _P, _F, _I64, _I32, _I32, _P, _P, _P, _P, _P]),
     "mtasr_layernorm_bwd": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P]),
-    "mtasr_layernorm_bwd_sums": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P]),
+    "mtasr_layernorm_bwd_sums": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "mtasr_cast_f32_bf16": (C.c_int, [_P, _P, _I64, _P]),
     "mtasr_softmax_from_logits": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P, _P, _P]),
     "mtasr_weightnorm_fwd": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P]),
     "mtasr_weightnorm_bwd": (C.c_int, [_P, _P, _P, _P, _I64, _I32, _P, _P, _P, _P]),
     "mtasr_colsum": (C.c_int, [_P, _I32, _I64, _I32, _I64, _P, _P]),
     "mtasr_relpos_gate_fwd": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
-    "mtasr_relpos_gate_bwd": (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "mtasr_relpos_gate_bwd": (C.c_int, [_P, _I32, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "mtasr_attn_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P, C.c_uint32, C.c_uint32, _P]),
     "mtasr_attn_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _F, _P, _P, _P, _P, _P, _P, C.c_uint32, C.c_uint32, _P]),
     "mtasr_attn_softmax_fwd": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _F, _P, _P]),

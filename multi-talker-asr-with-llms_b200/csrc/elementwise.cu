@@ -227,13 +227,22 @@ __device__ __forceinline__ void cvt_raw8(int dtype, const uint4& u0, const uint4
   }
 }
 
+// entry i of the summed projection: i < 64 -> rows 0..3 of the (8, 64) weight (gate a), else rows 4..7 (gate b), hf:170-173
+__device__ __forceinline__ float gate_wsum(const float* __restrict__ w8, int i) {
+  const float* p = w8 + (i >> 6) * 256 + (i & 63);
+  return (p[0] + p[64]) + (p[128] + p[192]);
+}
+
 template <int NW>
 __global__ void __launch_bounds__(256, 2)
 layernorm_bwd_fused_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
                            const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                            const float* __restrict__ dres, long long rows, int D, float* __restrict__ dx_f32,
                            __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                           float* __restrict__ dxsum) {
+                           float* __restrict__ dxsum, const float* __restrict__ gate_ab, const float* __restrict__ gate_w8) {
+  // gate_ab (rows, D/64, 2) / gate_w8 (8, 64): the gru_rel_pos gate's gradient path into the LayerNorm OUTPUT (hf:167-176) is
+  // rank 2 per head -- dy[c] += da[row, head] * wa[c % 64] + db[row, head] * wb[c % 64] -- and is added here from the two
+  // scalars per (row, head) instead of being materialised as a (rows, D) fp32 tensor and read back by a GEMM epilogue.
   constexpr int G = NW * 32;                       // threads per row group
   constexpr int NG = NW == 3 ? 2 : 256 / G;        // row groups per CTA (blockDim.x = NG * G)
   constexpr int GC = G * 8;                        // columns a group spans
@@ -250,6 +259,19 @@ layernorm_bwd_fused_kernel(const void* __restrict__ dy, int dy_dtype, const void
   float ag[8], ab[8], ax[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) ag[j] = ab[j] = ax[j] = 0.f;
+  const bool has_gate = gate_ab != nullptr;
+  const int gH = D >> 6, ghead = c0 >> 6;
+  float gwa[8], gwb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gwa[j] = gwb[j] = 0.f;
+  if (has_gate && active) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gwa[j] = gate_wsum(gate_w8, (c0 & 63) + j);
+      gwb[j] = gate_wsum(gate_w8, 64 + (c0 & 63) + j);
+    }
+  }
+  float2 gab = make_float2(0.f, 0.f);
   const long long stride = static_cast<long long>(gridDim.x) * NG;
   long long row = static_cast<long long>(blockIdx.x) * NG + g;
   const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
@@ -260,6 +282,7 @@ layernorm_bwd_fused_kernel(const void* __restrict__ dy, int dy_dtype, const void
       ld_raw8(dy, dy_dtype, row * D + c0, ra0, ra1);
       ld_raw8(x, x_dtype, row * D + c0, rb0, rb1);
       if (has_res) ld_raw8(dres, MTASR_DT_F32, row * D + c0, rd0, rd1);
+      if (has_gate) gab = *reinterpret_cast<const float2*>(gate_ab + (row * gH + ghead) * 2);
     }
     mu = mean[row];
     rs = rstd[row];
@@ -272,12 +295,17 @@ layernorm_bwd_fused_kernel(const void* __restrict__ dy, int dy_dtype, const void
     cvt_raw8(x_dtype, rb0, rb1, b);
     cvt_raw8(MTASR_DT_F32, rd0, rd1, d);
     const float mu_c = mu, rs_c = rs;
+    if (has_gate) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += fmaf(gab.x, gwa[j], gab.y * gwb[j]);
+    }
     const long long nxt = row + stride;
     if (nxt < rows) {                               // next row's loads in flight under this row's reductions
       if (active) {
         ld_raw8(dy, dy_dtype, nxt * D + c0, ra0, ra1);
         ld_raw8(x, x_dtype, nxt * D + c0, rb0, rb1);
         if (has_res) ld_raw8(dres, MTASR_DT_F32, nxt * D + c0, rd0, rd1);
+        if (has_gate) gab = *reinterpret_cast<const float2*>(gate_ab + (nxt * gH + ghead) * 2);
       }
       mu = mean[nxt];
       rs = rstd[nxt];
@@ -625,12 +653,6 @@ __device__ __forceinline__ void gate_load32(const void* x, int x_dtype, long lon
   }
 }
 
-// entry i of the summed projection: i < 64 -> rows 0..3 of the (8, 64) weight (gate a), else rows 4..7 (gate b), hf:170-173
-__device__ __forceinline__ float gate_wsum(const float* __restrict__ w8, int i) {
-  const float* p = w8 + (i >> 6) * 256 + (i & 63);
-  return (p[0] + p[64]) + (p[128] + p[192]);
-}
-
 __global__ void __launch_bounds__(256)
 relpos_gate_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ w8, const float* __restrict__ b8,
                        const float* __restrict__ cst, int B, int T, int H, float* __restrict__ gate) {
@@ -674,7 +696,8 @@ relpos_gate_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __r
 __global__ void __launch_bounds__(128, 3)
 relpos_gate_bwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ w8, const float* __restrict__ b8,
                        const float* __restrict__ cst, const float* __restrict__ dgate, int B, int T, int H,
-                       float* __restrict__ dx, float* __restrict__ dw8, float* __restrict__ db8, float* __restrict__ dcst) {
+                       float* __restrict__ dx, float* __restrict__ dab, float* __restrict__ dw8, float* __restrict__ db8,
+                       float* __restrict__ dcst) {
   __shared__ __align__(16) float w_s[128];
   __shared__ float red_s[132];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) w_s[i] = gate_wsum(w8, i);
@@ -715,15 +738,18 @@ relpos_gate_bwd_kernel(const void* __restrict__ x, int x_dtype, const float* __r
       const float da = dg * (gb * c_h - 1.f) * ga * (1.f - ga);
       const float db = dg * ga * c_h * gb * (1.f - gb);
       if (half == 0) { dc += dg * ga * gb; dba += da; dbb += db; }
-      float* dxp = dx + row * D + h * 64 + half * 32;
+      if (dab != nullptr && half == 0) *reinterpret_cast<float2*>(dab + (row * H + h) * 2) = make_float2(da, db);
+      if (dx != nullptr) {
+        float* dxp = dx + row * D + h * 64 + half * 32;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 o;
-        o.x = fmaf(da, wa[c * 4 + 0], db * wb[c * 4 + 0]);
-        o.y = fmaf(da, wa[c * 4 + 1], db * wb[c * 4 + 1]);
-        o.z = fmaf(da, wa[c * 4 + 2], db * wb[c * 4 + 2]);
-        o.w = fmaf(da, wa[c * 4 + 3], db * wb[c * 4 + 3]);
-        reinterpret_cast<float4*>(dxp)[c] = o;
+        for (int c = 0; c < 8; ++c) {
+          float4 o;
+          o.x = fmaf(da, wa[c * 4 + 0], db * wb[c * 4 + 0]);
+          o.y = fmaf(da, wa[c * 4 + 1], db * wb[c * 4 + 1]);
+          o.z = fmaf(da, wa[c * 4 + 2], db * wb[c * 4 + 2]);
+          o.w = fmaf(da, wa[c * 4 + 3], db * wb[c * 4 + 3]);
+          reinterpret_cast<float4*>(dxp)[c] = o;
+        }
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -968,8 +994,11 @@ extern "C" int mtasr_layernorm_fwd(const void* x, int32_t x_dtype, const float* 
 
 static int layernorm_bwd_launch(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
                                 const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D,
-                                float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, cudaStream_t st) {
+                                float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, const float* gate_ab,
+                                const float* gate_w8, cudaStream_t st) {
   MTASR_CHECK_ARG(dy && x && mean && rstd && gamma && rows > 0 && (dx_f32 || dx_bf16 || dgamma || dbeta), "layernorm_bwd: bad arguments");
+  MTASR_CHECK_ARG((gate_ab == nullptr) == (gate_w8 == nullptr), "layernorm_bwd: gate_ab and gate_w8 come together");
+  MTASR_CHECK_ARG(!gate_ab || (D % 64 == 0 && (dx_f32 || dx_bf16)), "layernorm_bwd: the gate path needs D %% 64 == 0 and a dx output");
   MTASR_CHECK_ARG(D % 8 == 0 && D <= 32 * MAXV, "layernorm_bwd: D=%d must be a multiple of 8 and <= 1024", D);
   MTASR_CHECK_ARG(!dxsum || dx_f32 || dx_bf16, "layernorm_bwd: dxsum needs a dx output");
   if (dx_f32 || dx_bf16) {
@@ -980,7 +1009,7 @@ static int layernorm_bwd_launch(const void* dy, int32_t dy_dtype, const void* x,
     if (g > num_sms() * 2) g = num_sms() * 2;
     const unsigned grid = static_cast<unsigned>(g), block = static_cast<unsigned>(ng * nw * 32);
     __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
-#define MTASR_LNB(NW) layernorm_bwd_fused_kernel<NW><<<grid, block, 0, st>>>(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres, rows, D, dx_f32, dxb, dgamma, dbeta, dxsum)
+#define MTASR_LNB(NW) layernorm_bwd_fused_kernel<NW><<<grid, block, 0, st>>>(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres, rows, D, dx_f32, dxb, dgamma, dbeta, dxsum, gate_ab, gate_w8)
     switch (nw) {
       case 1: MTASR_LNB(1); break;
       case 2: MTASR_LNB(2); break;
@@ -1006,14 +1035,15 @@ extern "C" int mtasr_layernorm_bwd(const void* dy, int32_t dy_dtype, const void*
                                    const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D,
                                    float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, void* stream) {
   return layernorm_bwd_launch(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres, rows, D, dx_f32, dx_bf16, dgamma, dbeta, nullptr,
-                              static_cast<cudaStream_t>(stream));
+                              nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mtasr_layernorm_bwd_sums(const void* dy, int32_t dy_dtype, const void* x, int32_t x_dtype, const float* mean,
                                         const float* rstd, const float* gamma, const float* dres, int64_t rows, int32_t D,
-                                        float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, void* stream) {
+                                        float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, float* dxsum, const float* gate_ab,
+                                        const float* gate_w8, void* stream) {
   return layernorm_bwd_launch(dy, dy_dtype, x, x_dtype, mean, rstd, gamma, dres, rows, D, dx_f32, dx_bf16, dgamma, dbeta, dxsum,
-                              static_cast<cudaStream_t>(stream));
+                              gate_ab, gate_w8, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int mtasr_cast_f32_bf16(const float* x, void* y, int64_t n, void* stream) {
@@ -1112,17 +1142,17 @@ extern "C" int mtasr_relpos_gate_fwd(const void* x, int32_t x_dtype, const float
 }
 
 extern "C" int mtasr_relpos_gate_bwd(const void* x, int32_t x_dtype, const float* w8, const float* b8, const float* cst,
-                                     const float* dgate, int32_t B, int32_t T, int32_t H, float* dx, float* dw8, float* db8,
-                                     float* dcst, void* stream) {
+                                     const float* dgate, int32_t B, int32_t T, int32_t H, float* dx, float* dab, float* dw8,
+                                     float* db8, float* dcst, void* stream) {
   const float *wab = w8, *bab = b8;
   float *dwab = dw8, *dbab = db8;
-  MTASR_CHECK_ARG(x && wab && bab && cst && dgate && dx && dwab && dbab && dcst && B > 0 && T > 0 && H > 0 && H <= 32,
+  MTASR_CHECK_ARG(x && wab && bab && cst && dgate && (dx || dab) && dwab && dbab && dcst && B > 0 && T > 0 && H > 0 && H <= 32,
                   "relpos_gate_bwd: bad arguments");
   MTASR_CHECK_ARG(H <= 16, "relpos_gate_bwd: H=%d > 16 heads not supported", H);
   long long g = (static_cast<long long>(B) * T + 15) / 16;
   if (g > num_sms() * 3) g = num_sms() * 3;
   relpos_gate_bwd_kernel<<<static_cast<unsigned>(g), 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, x_dtype, wab, bab, cst, dgate, B, T, H, dx, dwab, dbab, dcst);
+      x, x_dtype, wab, bab, cst, dgate, B, T, H, dx, dab, dwab, dbab, dcst);
   MTASR_COUNT_LAUNCH();
   MTASR_CHECK_LAUNCH("relpos_gate_bwd");
   return MTASR_OK;

@@ -217,9 +217,12 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor, *,
                   dres: Optional[torch.Tensor] = None, want_f32: bool = True, want_bf16: bool = False,
-                  want_param_grads: bool = True, want_dxsum: bool = False):
+                  want_param_grads: bool = True, want_dxsum: bool = False, gate_ab: Optional[torch.Tensor] = None,
+                  gate_w8: Optional[torch.Tensor] = None):
     """-> dx_f32, dx_bf16, dgamma, dbeta[, dxsum].  One kernel: dx (+ dres) and every requested column reduction
-    (dxsum = sum over rows of dx, the bias gradient of the Linear that produced the tensor dx is the gradient of)."""
+    (dxsum = sum over rows of dx, the bias gradient of the Linear that produced the tensor dx is the gradient of).
+    gate_ab (rows, D/64, 2) + gate_w8 (8, 64): dy additionally receives the gru_rel_pos gate's rank-2-per-head path
+    (relpos_gate_bwd(want_dx=False))."""
     D = x.shape[-1]
     rows = x.numel() // D
     dy = dy.contiguous()
@@ -231,7 +234,8 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: t
     dg, db = (sums[0], sums[1]) if want_param_grads else (None, None)
     dxs = sums[nsum - 1] if want_dxsum else None
     check(_lib.load().mtasr_layernorm_bwd_sums(_p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma), _p(dres), rows, D,
-                                               _p(dxf), _p(dxb), _p(dg), _p(db), _p(dxs), _stream()), "mtasr_layernorm_bwd_sums")
+                                               _p(dxf), _p(dxb), _p(dg), _p(db), _p(dxs), _p(gate_ab), _p(gate_w8), _stream()),
+          "mtasr_layernorm_bwd_sums")
     if want_dxsum:
         return dxf, dxb, dg, db, dxs
     return dxf, dxb, dg, db
@@ -359,14 +363,16 @@ def relpos_gate_fwd(x, w8, b8, cst, B, T, H):
     return gate
 
 
-def relpos_gate_bwd(x, w8, b8, cst, dgate, B, T, H):
-    """-> dx (B,T,H*64) f32, dw8 (8,64), db8 (8), dcst (H)."""
-    dx = torch.empty(B, T, H * 64, device=x.device, dtype=torch.float32)
+def relpos_gate_bwd(x, w8, b8, cst, dgate, B, T, H, want_dx: bool = True):
+    """-> dx (B,T,H*64) f32, dw8 (8,64), db8 (8), dcst (H); with want_dx=False the first result is dab (B*T, H, 2) f32 instead
+    (the gradients wrt the two pre-sigmoid sums; layernorm_bwd(gate_ab=dab, gate_w8=w8) adds da * wa + db * wb itself)."""
+    dx = torch.empty(B, T, H * 64, device=x.device, dtype=torch.float32) if want_dx else None
+    dab = None if want_dx else torch.empty(B * T, H, 2, device=x.device, dtype=torch.float32)
     acc = torch.zeros(512 + 8 + H, device=x.device, dtype=torch.float32)                            # one fill for the three
     dw8, db8, dcst = acc[:512].view(8, 64), acc[512:520], acc[520:520 + H]
-    check(_lib.load().mtasr_relpos_gate_bwd(_p(x), _dt(x), _p(w8), _p(b8), _p(cst), _p(dgate), B, T, H, _p(dx), _p(dw8),
+    check(_lib.load().mtasr_relpos_gate_bwd(_p(x), _dt(x), _p(w8), _p(b8), _p(cst), _p(dgate), B, T, H, _p(dx), _p(dab), _p(dw8),
                                             _p(db8), _p(dcst), _stream()), "mtasr_relpos_gate_bwd")
-    return dx, dw8, db8, dcst
+    return (dx if want_dx else dab), dw8, db8, dcst
 
 
 def attn_fwd(qkv, gate, table, klen, B, H, T, scale, drop=None):

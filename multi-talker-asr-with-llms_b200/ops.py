@@ -464,13 +464,14 @@ class PreLNAttentionFn(Function):
         dwo = K.linear_wgrad(dyb, O) if need[10] else None
         dbo = (dysum if dysum is not None else K.colsum(dyb)) if need[11] else None
         dqkv, dgate, dtable = K.attn_bwd(qkv, O, dO, lse, gate, tab, klen, B, H, T, scale, drop=drop_attn)
-        dxg, dwab, dbab, dcst = K.relpos_gate_bwd(h1, wab, bab, cst, dgate, B, T, H)           # gate path into LN(x), fp32
+        # gate path into LN(x): only the two scalars per (frame, head); the LayerNorm backward expands da * wa + db * wb itself
+        dab, dwab, dbab, dcst = K.relpos_gate_bwd(h1, wab, bab, cst, dgate, B, T, H, want_dx=False)
         dx = dlnw = dlnb = None
         if need[0] or need[1] or need[2]:
-            dh1 = K.linear_dgrad(dqkv, wqkv, residual=dxg.view(B * T, D))                      # QKV dgrad + gate path, one epilogue
+            dh1 = K.linear_dgrad(dqkv, wqkv)
             dxf, dxb, dlnw, dlnb, dxs = K.layernorm_bwd(dh1.view(B, T, D), xf, mean, rstd, gamma, dres=dy, want_f32=True,
                                                         want_bf16=need[0], want_param_grads=need[1] or need[2],
-                                                        want_dxsum=need[0])
+                                                        want_dxsum=need[0], gate_ab=dab, gate_w8=wab)
             dx = dxf if need[0] else None
             if dx is not None:
                 _publish_twin(dx, dxb, dxs)

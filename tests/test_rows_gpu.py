@@ -129,6 +129,35 @@ def test_relpos_gate_fwd_bwd(cuda, B, T, H, dt):
         assert _rel(a, b) < 1e-4
 
 
+@pytest.mark.parametrize("B,T,H", [(2, 37, 2), (3, 199, 16), (1, 50, 12)])
+def test_gate_path_inside_layernorm_bwd(cuda, B, T, H):
+    """relpos_gate_bwd(want_dx=False) + layernorm_bwd(gate_ab=, gate_w8=): the rank-2-per-head gate path added inside the
+    LayerNorm backward equals adding the materialised dx of the gate to the upstream gradient first."""
+    from mtasr_b200 import kernels as Kn
+    torch.manual_seed(11)
+    D = H * 64
+    x = torch.randn(B, T, D, device=cuda) * 2 + 0.3
+    gamma, beta = torch.randn(D, device=cuda), torch.randn(D, device=cuda)
+    h1, _, mean, rstd = Kn.layernorm_fwd(x, gamma, beta, 1e-5)
+    w8, b8 = torch.randn(8, 64, device=cuda) * 0.2, torch.randn(8, device=cuda) * 0.1
+    cst = torch.rand(H, device=cuda) + 0.5
+    dgate = torch.randn(B, H, T, device=cuda)
+    dxg, dw_a, db_a, dc_a = Kn.relpos_gate_bwd(h1, w8, b8, cst, dgate, B, T, H)
+    dab, dw_b, db_b, dc_b = Kn.relpos_gate_bwd(h1, w8, b8, cst, dgate, B, T, H, want_dx=False)
+    assert dab.shape == (B * T, H, 2)
+    assert _rel(dw_a, dw_b) < 1e-5 and _rel(db_a, db_b) < 1e-5 and _rel(dc_a, dc_b) < 1e-5
+    wa, wb = w8[:4].sum(0), w8[4:].sum(0)
+    expand = dab[:, :, 0:1] * wa.view(1, 1, 64) + dab[:, :, 1:2] * wb.view(1, 1, 64)             # (B*T, H, 64)
+    assert _rel(expand.reshape(B, T, D), dxg) < 1e-5
+    dy = torch.randn(B, T, D, device=cuda).to(torch.bfloat16)
+    dres = torch.randn(B, T, D, device=cuda)
+    ref = Kn.layernorm_bwd(dy.float() + dxg, x, mean, rstd, gamma, dres=dres, want_bf16=True, want_dxsum=True)
+    got = Kn.layernorm_bwd(dy, x, mean, rstd, gamma, dres=dres, want_bf16=True, want_dxsum=True, gate_ab=dab, gate_w8=w8)
+    assert _rel(got[0], ref[0]) < 1e-5 and _rel(got[1], ref[1]) < 5e-3
+    for a, b in zip(got[2:], ref[2:]):
+        assert _rel(a, b) < 1e-4
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,N", [(1000, 1024), (15968, 3072), (77, 40), (333, 129)])
 def test_colsum_shapes(cuda, M, N, dt):
