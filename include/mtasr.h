@@ -265,8 +265,9 @@ int mtasr_attn_fwd(const void* qkv_bf16, const float* gate, const float* table, 
                    int32_t T, float scale, void* out_bf16, float* lse, const void* drop_seed, uint32_t drop_site,
                    uint32_t drop_keep16, void* stream);
 /* Fused attention backward.  out / dout (B*T, H*64) bf16 are the forward output and its gradient; lse from the forward.
- * Writes dqkv (B*T, 3*H*64) bf16 = [dq | dk | dv].  dq32 (B*T, H*64) f32, dgate (B,H,T) f32 and dtable (H,2T-1) f32 are
- * ACCUMULATED (zero them first); delta (B,H,T) f32 is scratch. */
+ * Writes dqkv (B*T, 3*H*64) bf16 = [dq | dk | dv], dgate (B,H,T) f32 and dtable (H,2T-1) f32; dq32 (B*T, H*64) f32
+ * (16-byte aligned) and delta (B,H,T) f32 are scratch.  dq32 / dgate / dtable are zeroed by the call itself (inside the
+ * delta pre-pass) and then accumulated into by the backward kernel: the caller does not pre-zero them. */
 int mtasr_attn_bwd(const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, const float* lse, const float* gate,
                    const float* table, const int32_t* klen, int32_t B, int32_t H, int32_t T, float scale, void* dqkv_bf16,
                    float* dq32, float* delta, float* dgate, float* dtable, const void* drop_seed, uint32_t drop_site,

@@ -1,5 +1,6 @@
 // Library-wide plumbing of the C ABI: version, thread-local error string, device properties.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -49,6 +50,14 @@ int num_units(int ncta) {
   const int total = sm_count();
   const int pairs = (total - 2 * (total - usable)) / 2;
   return pairs > 1 ? pairs : 1;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MTASR_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
 }
 
 }  // namespace mtasr

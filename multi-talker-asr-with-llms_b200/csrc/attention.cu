@@ -89,6 +89,7 @@ template <bool DROP>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* q_s = smem;                                   // 16 KB
   uint8_t* kv_s = q_s + AT_TILE;                         // 4 x 16 KB
@@ -132,6 +133,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // PDL (common.cuh): the set-up above overlaps the predecessor's tail; q/k/v, gate and table are its results
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_s[2] = {tmem_base, tmem_base + 128};
   const uint32_t tm_o = tmem_base + 256;
@@ -386,6 +388,7 @@ template <bool DROP>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* q_s = smem;                                   // 2 x 16 KB: the next item's Q tile is prefetched
   uint8_t* kv_s = q_s + 2 * AT_TILE;                     // 4 x 16 KB
@@ -429,6 +432,7 @@ attn_fwd_sp_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnFwdP 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // PDL (common.cuh): the set-up above overlaps the predecessor's tail; q/k/v, gate and table are its results
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_s[2] = {tmem_base, tmem_base + 128};
   const uint32_t tm_o = tmem_base + 256;         // accumulator of key tile j: tm_o + 64 j
@@ -731,6 +735,7 @@ template <bool DROP>
 __global__ void __launch_bounds__(ATB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do, const AttnBwdP p) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  pdl_trigger();
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* k_s = smem;                          // 16 KB
   uint8_t* v_s = k_s + AT_TILE;                 // 16 KB
@@ -773,6 +778,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // PDL (common.cuh): everything read below (q/k/v, O-gradient, lse, delta, zeroed accumulators) is a predecessor's result
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_s = tmem_base, tm_dp = tmem_base + 128, tm_dv = tmem_base + 256, tm_dk = tmem_base + 320,
                  tm_dq = tmem_base + 384;
@@ -1125,9 +1131,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 }
 
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]  (the softmax-backward row term), one thread per (b,q,h)
+// The same launch zeroes the three accumulation targets of the backward kernel that follows it (dQ scratch, gate and table
+// gradients): they were two fill launches per layer in front of this kernel.
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, int B, int T, int H,
-                                  float* __restrict__ delta) {
+                                  float* __restrict__ delta, float4* __restrict__ zero4, long long n_zero4,
+                                  float* __restrict__ zero_a, long long n_zero_a, float* __restrict__ zero_b, long long n_zero_b) {
+  pdl_trigger();
   const long long n = static_cast<long long>(B) * T * H;
+  const long long tid0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = tid0; i < n_zero4; i += nthr) zero4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = tid0; i < n_zero_a; i += nthr) zero_a[i] = 0.f;
+  for (long long i = tid0; i < n_zero_b; i += nthr) zero_b[i] = 0.f;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int h = static_cast<int>(i % H);
@@ -1152,6 +1167,7 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 // y[r][0..cols) (bf16, row stride ldy) = x[r][0..cols) (fp32, row stride ldx): dQ scratch -> the q block of dqkv
 __global__ void cast2d_kernel(const float* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy, long long rows,
                               int cols8) {
+  pdl_trigger();
   const long long n = rows * cols8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -1242,7 +1258,8 @@ extern "C" int mtasr_attn_fwd(const void* qkv, const float* gate, const float* t
     auto kern = drop ? attn_fwd_sp_kernel<true> : attn_fwd_sp_kernel<false>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
       return set_error(MTASR_ERR_LAUNCH, "attn_fwd: cannot set the shared-memory attribute");
-    kern<<<grid, AT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map, p);
+    if (launch_pdl(kern, dim3(grid), dim3(AT_THREADS), smem, static_cast<cudaStream_t>(stream), map, p) != cudaSuccess)
+      return set_error(MTASR_ERR_LAUNCH, "attn_fwd: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     MTASR_COUNT_LAUNCH();
     MTASR_CHECK_LAUNCH("attn_fwd");
     return MTASR_OK;
@@ -1252,7 +1269,8 @@ extern "C" int mtasr_attn_fwd(const void* qkv, const float* gate, const float* t
   auto kern2 = drop ? attn_fwd_kernel<true> : attn_fwd_kernel<false>;
   if (cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return set_error(MTASR_ERR_LAUNCH, "attn_fwd: cannot set the shared-memory attribute");
-  kern2<<<grid, AT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(map, p);
+  if (launch_pdl(kern2, dim3(grid), dim3(AT_THREADS), smem, static_cast<cudaStream_t>(stream), map, p) != cudaSuccess)
+    return set_error(MTASR_ERR_LAUNCH, "attn_fwd: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   MTASR_COUNT_LAUNCH();
   MTASR_CHECK_LAUNCH("attn_fwd");
   return MTASR_OK;
@@ -1269,8 +1287,10 @@ extern "C" int mtasr_attn_bwd(const void* qkv, const void* out, const void* dout
   const long long n = static_cast<long long>(B) * T * H;
   long long g = (n + 255) / 256;
   if (g > num_sms() * 8) g = num_sms() * 8;
-  attn_delta_kernel<<<static_cast<unsigned>(g), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(out),
-                                                                reinterpret_cast<const __nv_bfloat16*>(dout), B, T, H, delta);
+  MTASR_CHECK_ARG((reinterpret_cast<uintptr_t>(dq32) & 15) == 0, "attn_bwd: dq32 must be 16-byte aligned");
+  attn_delta_kernel<<<static_cast<unsigned>(g), 256, 0, st>>>(
+      reinterpret_cast<const __nv_bfloat16*>(out), reinterpret_cast<const __nv_bfloat16*>(dout), B, T, H, delta,
+      reinterpret_cast<float4*>(dq32), n * (AT_D / 4), dgate, n, dtable, static_cast<long long>(H) * (2 * T - 1));
   MTASR_COUNT_LAUNCH();
   CUtensorMap mq, mdo;
   if (int rc = encode_heads_map(&mq, qkv, B, T, 3 * H, 3LL * H * AT_D, "qkv")) return rc;
@@ -1293,7 +1313,8 @@ extern "C" int mtasr_attn_bwd(const void* qkv, const void* out, const void* dout
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
     return set_error(MTASR_ERR_LAUNCH, "attn_bwd: cannot set the shared-memory attribute");
   const int grid = p.n_items < num_sms() ? p.n_items : num_sms();
-  kern<<<grid, ATB_THREADS, smem, st>>>(mq, mdo, p);
+  if (launch_pdl(kern, dim3(grid), dim3(ATB_THREADS), smem, st, mq, mdo, p) != cudaSuccess)
+    return set_error(MTASR_ERR_LAUNCH, "attn_bwd: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
   MTASR_COUNT_LAUNCH();
   // dQ scratch (fp32) -> q block of dqkv (bf16)
   const long long rows = static_cast<long long>(B) * T;

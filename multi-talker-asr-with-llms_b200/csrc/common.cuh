@@ -32,6 +32,35 @@ int num_units(int ncta);   // CTAs or TPC-safe CTA pairs available to a persiste
 extern std::atomic<long long> g_launches;
 #define MTASR_COUNT_LAUNCH() ::mtasr::g_launches.fetch_add(1)
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------
+// Kernel-to-kernel latency inside the step's CUDA graph is ~1 us and PDL does not shorten it (tools/micro/pdl_gap.cu, B200:
+// 1.10 -> 0.96 us per empty launch); what PDL hides is the PROLOGUE of the dependent kernel.  The tcgen05 kernels (GEMM,
+// fused attention: 386 launches per cfg2 step) spend 1.5-2 us per launch on tensor-map prefetch, mbarrier init, the TMEM
+// allocation and a cluster / CTA barrier before they touch global memory; launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization they run that part while the predecessor drains and block in
+// `griddepcontrol.wait` (pdl_wait) until the predecessor grid has completed and flushed.  Every kernel of the library
+// issues `griddepcontrol.launch_dependents` (pdl_trigger) as its first instruction so that a PDL successor may be
+// scheduled as early as its resources allow; that is harmless without such a successor, and correctness never depends on
+// it: only kernels whose prologue ends in pdl_wait() are launched with the attribute.  MTASR_PDL=0 switches it off.
+bool pdl_enabled();   // api.cu
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Launch of a kernel whose prologue ends in pdl_wait(): with the programmatic-serialization attribute when PDL is on.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }
 

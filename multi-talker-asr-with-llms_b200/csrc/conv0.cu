@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(128)
 conv0_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
              const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int B, int S, int L0, int C0,
              int k, int stride, int mode, __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32) {
+  pdl_trigger();
   extern __shared__ float wsm[];  // [k][C0] transposed weights, then bias/gamma/beta [3][C0]
   float* bsm = wsm + k * C0;
   float* gsm = bsm + C0;

@@ -77,6 +77,7 @@ ctc_alpha_kernel(const float* __restrict__ glog, const float* __restrict__ lse, 
                  const long long* __restrict__ hlens, const long long* __restrict__ ylens, int B, int T, int Lp,
                  int ys_ld, int CH, float* __restrict__ alpha_ws, double* __restrict__ coff_ws, float* __restrict__ nll_out,
                  double* __restrict__ nll_raw) {
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char ctc_smem[];
   constexpr int SP = 32 * NS;
   const int lane = threadIdx.x & 31;
@@ -211,6 +212,7 @@ ctc_beta_grad_kernel(const float* __restrict__ glog, const float* __restrict__ l
                      int ys_ld, int CH, const float* __restrict__ alpha_ws, const double* __restrict__ coff_ws,
                      const double* __restrict__ nll_raw, const float* __restrict__ gout, float* __restrict__ dG,
                      float* __restrict__ rowscale) {
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char ctc_smem[];
   constexpr int SP = 32 * NS;
   const int lane = threadIdx.x & 31;
@@ -343,6 +345,7 @@ ctc_beta_grad_kernel(const float* __restrict__ glog, const float* __restrict__ l
 // Combine the per-N-tile {max, sumexp, argmax} partials written by the vocab GEMM (mode 1).  One warp per row.
 __global__ void lse_finalize_kernel(const float4* __restrict__ part, int rows, int n_tiles, float* __restrict__ lse,
                                     long long* __restrict__ argmax) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -460,6 +463,7 @@ __global__ void ctc_gather_rows_kernel(const __nv_bfloat16* __restrict__ w, cons
                                        const long long* __restrict__ ys, const long long* __restrict__ ylens, int B,
                                        int Lp, int D, int ys_ld, long long blank, long long V,
                                        __nv_bfloat16* __restrict__ wg, float* __restrict__ bg) {
+  pdl_trigger();
   const int b = blockIdx.x / Lp, c = blockIdx.x % Lp;
   const int L = clamp_label_len(ylens[b], Lp, ys_ld);
   long long v = -1;
@@ -480,6 +484,7 @@ __global__ void ctc_scatter_rows_kernel(const float* __restrict__ dwg, const flo
                                         const long long* __restrict__ ys, const long long* __restrict__ ylens, int B,
                                         int Lp, int D, int ys_ld, long long blank, long long V,
                                         float* __restrict__ dw, float* __restrict__ db) {
+  pdl_trigger();
   const int b = blockIdx.x / Lp, c = blockIdx.x % Lp;
   const int L = clamp_label_len(ylens[b], Lp, ys_ld);
   if (c > L) return;

@@ -41,6 +41,7 @@ layernorm_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __res
                      const float* __restrict__ beta, float eps, long long rows, int D, int post_gelu,
                      __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
@@ -99,6 +100,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const void* __re
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                      const float* __restrict__ dres, long long rows, int D, float* __restrict__ dx_f32,
                      __nv_bfloat16* __restrict__ dx_bf16) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
@@ -154,6 +156,7 @@ __global__ void __launch_bounds__(256)
 layernorm_bwd_param_kernel(const void* __restrict__ dy, int dy_dtype, const void* __restrict__ x, int x_dtype,
                            const float* __restrict__ mean, const float* __restrict__ rstd, long long rows, int D,
                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_trigger();
   __shared__ float redg[8][32][9], redb[8][32][9];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + cx) * 8;
@@ -240,6 +243,7 @@ layernorm_bwd_fused_kernel(const void* __restrict__ dy, int dy_dtype, const void
                            const float* __restrict__ dres, long long rows, int D, float* __restrict__ dx_f32,
                            __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma, float* __restrict__ dbeta,
                            float* __restrict__ dxsum, const float* __restrict__ gate_ab, const float* __restrict__ gate_w8) {
+  pdl_trigger();
   // gate_ab (rows, D/64, 2) / gate_w8 (8, 64): the gru_rel_pos gate's gradient path into the LayerNorm OUTPUT (hf:167-176) is
   // rank 2 per head -- dy[c] += da[row, head] * wa[c % 64] + db[row, head] * wb[c % 64] -- and is added here from the two
   // scalars per (row, head) instead of being materialised as a (rows, D) fp32 tensor and read back by a GEMM epilogue.
@@ -370,6 +374,7 @@ layernorm_bwd_fused_kernel(const void* __restrict__ dy, int dy_dtype, const void
 
 // ------------------------------------------------------------------------------------------------ cast / colsum
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n8) {
+  pdl_trigger();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float t[8];
@@ -425,6 +430,7 @@ __global__ void __launch_bounds__(256) pcgrad_project_kernel(float* __restrict__
 // stand-alone dropout pass (one thread per element; the fused sites live in the GEMM / attention kernels)
 __global__ void dropout_kernel(const void* __restrict__ x, int x_dtype, long long rows, long long cols, DropP d, void* __restrict__ y,
                                int y_dtype) {
+  pdl_trigger();
   const uint32_t s0 = __ldg(d.seed), s1 = __ldg(d.seed + 1);
   const long long n = rows * cols;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -472,6 +478,7 @@ __global__ void __launch_bounds__(256)
 softmax_from_logits_kernel(const __half* __restrict__ lg, const float* __restrict__ lse, const float* __restrict__ rowscale,
                            long long rows, int V, long long ld, long long rows_per_group, __nv_bfloat16* __restrict__ P,
                            float* __restrict__ colsum) {
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;     // 8-column piece
   if (i * 8 >= V) return;
   const long long r0 = blockIdx.y * rows_per_group;
@@ -574,6 +581,7 @@ __global__ void wn_dg_kernel(const float* __restrict__ dot, const float* __restr
 // thread; CTA partials are combined in smem and added with one atomic per column.
 __global__ void __launch_bounds__(256)
 colsum_vec_kernel(const void* __restrict__ x, int dtype, long long M, int N, long long ld, float* __restrict__ out) {
+  pdl_trigger();
   __shared__ float red[8][32][9];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + cx) * 8;
@@ -656,6 +664,7 @@ __device__ __forceinline__ void gate_load32(const void* x, int x_dtype, long lon
 __global__ void __launch_bounds__(256)
 relpos_gate_fwd_kernel(const void* __restrict__ x, int x_dtype, const float* __restrict__ w8, const float* __restrict__ b8,
                        const float* __restrict__ cst, int B, int T, int H, float* __restrict__ gate) {
+  pdl_trigger();
   __shared__ __align__(16) float w_s[128];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) w_s[i] = gate_wsum(w8, i);
   __syncthreads();
@@ -698,6 +707,7 @@ relpos_gate_bwd_kernel(const void* __restrict__ x, int x_dtype, const float* __r
                        const float* __restrict__ cst, const float* __restrict__ dgate, int B, int T, int H,
                        float* __restrict__ dx, float* __restrict__ dab, float* __restrict__ dw8, float* __restrict__ db8,
                        float* __restrict__ dcst) {
+  pdl_trigger();
   __shared__ __align__(16) float w_s[128];
   __shared__ float red_s[132];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) w_s[i] = gate_wsum(w8, i);
@@ -901,6 +911,7 @@ attn_softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __rest
 // y[b][pad_l + t][:] = bf16(x[b][t][:]) with zero rows on both sides (pos-conv / adapter "same" padding).
 __global__ void pad_cast_kernel(const void* __restrict__ x, int x_dtype, int B, int T, int D, int pad_l, int Tpad,
                                 const int* __restrict__ vlen, __nv_bfloat16* __restrict__ y) {
+  pdl_trigger();
   const long long n8 = static_cast<long long>(B) * Tpad * (D >> 3);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -917,6 +928,7 @@ __global__ void pad_cast_kernel(const void* __restrict__ x, int x_dtype, int B, 
 // GLU over the channel halves of a channels-last row: y[r][c] = a[r][c] * sigmoid(a[r][C + c]).
 __global__ void glu_fwd_kernel(const void* __restrict__ x, int x_dtype, long long rows, int C,
                                __nv_bfloat16* __restrict__ y_bf16, float* __restrict__ y_f32) {
+  pdl_trigger();
   const long long n8 = rows * (C >> 3);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -957,6 +969,7 @@ __global__ void glu_bwd_kernel(const void* __restrict__ x, int x_dtype, const vo
 // du = dy * act'(src): act 3 = GELU'(pre-activation), act 4 = ReLU (src = activation output).
 __global__ void act_bwd_kernel(const void* __restrict__ dy, int dy_dtype, const __nv_bfloat16* __restrict__ src, int act,
                                long long n8, __nv_bfloat16* __restrict__ du) {
+  pdl_trigger();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float d[8], u[8], o[8];

@@ -71,6 +71,7 @@ struct GemmKP {
   const float* row_scale;
   float4* lse_part;
   DropP drop;                          // fused dropout (seed == nullptr: off)
+  int dbg;                             // timing experiments only (MTASR_GEMM_DBG, WRONG results): 1 skip the staging store-read wait, 2 skip the bias load, 4 skip fence + TMA stores
 };
 
 __device__ __forceinline__ void load8(const void* base, int dtype, long long idx, int nv, float (&o)[8]) {
@@ -263,7 +264,7 @@ __device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMa
   uint8_t* stg_r = stg + (p.stg_res > 0 ? p.stg_res : 0) * STG_BYTES;
   if (tma_out) {
     // the previous group's bulk stores must have finished READING the staging buffers before they are rewritten
-    if (lane == 0) bulk_wait_read<0>();
+    if (lane == 0 && !(p.dbg & 1)) bulk_wait_read<0>();
     if (res_tma) fence_proxy_async();   // this warp's generic reads of the residual box precede its async overwrite
   }
   __syncwarp();
@@ -280,7 +281,7 @@ __device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMa
 #pragma unroll
     for (int j = 0; j < GW / 32; ++j) {
       const int col = col0 + j * 32 + lane;
-      bias_s[j * 32 + lane] = col < p.N ? __ldg(bias + col) : 0.f;
+      bias_s[j * 32 + lane] = (col < p.N && !(p.dbg & 2)) ? __ldg(bias + col) : 0.f;
     }
   }
   tmem_ld_wait();
@@ -409,7 +410,7 @@ __device__ __forceinline__ void epilogue_group(const GemmKP& p, const CUtensorMa
     if (tma) stg_store8(stg_c, p.c_dtype, lane, GW, c8, v);
     else if (row_ok) store8(p.c, p.c_dtype, c_off + col, nv, v);
   }
-  if (tma_out) {
+  if (tma_out && !(p.dbg & 4)) {
     fence_proxy_async();   // generic-proxy smem writes -> visible to the TMA (async proxy)
     __syncwarp();
     if (lane == 0) {
@@ -579,6 +580,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // SWIZZLE_128B atoms need 1024-byte alignment.  The kernel has no static shared memory, so the dynamic window starts
   // 1024-aligned; this is checked (trap) rather than paid for with a 1 KB slack that would cost a pipeline stage.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  pdl_trigger();
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* stg_base = smem + p.stages * p.stage_bytes;                       // 1024-aligned (stage_bytes % 1024 == 0)
@@ -634,6 +636,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above is independent of the predecessor kernel and overlaps its tail (PDL, common.cuh); nothing below may
+  // run before the predecessor grid has completed: operands, bias, residual and the pre-zeroed split-K output are its results
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -1004,6 +1009,8 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
   p.act = d->act; p.alpha = d->alpha; p.accumulate = d->accumulate; p.mode = d->mode;
   p.row_vec = d->row_vec; p.row_scale = d->row_scale;
   p.lse_part = reinterpret_cast<float4*>(d->lse_part);
+  p.dbg = 0;
+  if (const char* dbg_env = getenv("MTASR_GEMM_DBG")) p.dbg = atoi(dbg_env);
   p.drop.seed = nullptr;
   if (d->drop_seed != nullptr) {
     MTASR_CHECK_ARG(d->mode == 0 && d->drop_keep16 > 0 && d->drop_keep16 <= 65536, "gemm: fused dropout needs mode 0 and keep16 in (0, 65536]");
@@ -1190,23 +1197,30 @@ extern "C" int mtasr_gemm_bf16(const mtasr_gemm_desc* d, void* stream) {
     rec.flops = 2.0 * d->M * static_cast<double>(d->N) * d->K * d->batch0 * d->batch1;
     cudaEventRecord(rec.e0, st);
   }
-  if (ncta == 2) {
+  {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (ncta == 2) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (pdl_enabled()) {   // the kernel's prologue ends in pdl_wait()
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, ma, mb, mc, maux, mr, p);
-    if (le != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "gemm: cluster launch failed: %s", cudaGetErrorString(le));
-  } else {
-    kernel<<<grid, threads, smem_bytes, st>>>(ma, mb, mc, maux, mr, p);
+    if (le != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "gemm: launch failed: %s", cudaGetErrorString(le));
   }
   g_launches.fetch_add(1);
   if (prof) {

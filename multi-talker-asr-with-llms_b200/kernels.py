@@ -218,7 +218,7 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor, gamma: torch.Tensor, *,
                   dres: Optional[torch.Tensor] = None, want_f32: bool = True, want_bf16: bool = False,
                   want_param_grads: bool = True, want_dxsum: bool = False, gate_ab: Optional[torch.Tensor] = None,
-                  gate_w8: Optional[torch.Tensor] = None):
+                  gate_w8: Optional[torch.Tensor] = None, zeroed: Optional[torch.Tensor] = None):
     """-> dx_f32, dx_bf16, dgamma, dbeta[, dxsum].  One kernel: dx (+ dres) and every requested column reduction
     (dxsum = sum over rows of dx, the bias gradient of the Linear that produced the tensor dx is the gradient of).
     gate_ab (rows, D/64, 2) + gate_w8 (8, 64): dy additionally receives the gru_rel_pos gate's rank-2-per-head path
@@ -230,7 +230,12 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, mean: torch.Tensor, rstd: t
     dxb = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
     want_dxsum = want_dxsum and (want_f32 or want_bf16)
     nsum = (2 if want_param_grads else 0) + (1 if want_dxsum else 0)
-    sums = torch.zeros(nsum, D, device=x.device, dtype=torch.float32) if nsum else None   # one fill for all reductions
+    # one fill for all reductions -- or none: `zeroed` is a caller-provided ZERO fp32 buffer of >= nsum * D elements (a
+    # block's backward zeroes the accumulators of all its row kernels with a single fill)
+    if nsum and zeroed is not None:
+        sums = zeroed[:nsum * D].view(nsum, D)
+    else:
+        sums = torch.zeros(nsum, D, device=x.device, dtype=torch.float32) if nsum else None
     dg, db = (sums[0], sums[1]) if want_param_grads else (None, None)
     dxs = sums[nsum - 1] if want_dxsum else None
     check(_lib.load().mtasr_layernorm_bwd_sums(_p(dy), _dt(dy), _p(x), _dt(x), _p(mean), _p(rstd), _p(gamma), _p(dres), rows, D,
@@ -363,12 +368,16 @@ def relpos_gate_fwd(x, w8, b8, cst, B, T, H):
     return gate
 
 
-def relpos_gate_bwd(x, w8, b8, cst, dgate, B, T, H, want_dx: bool = True):
+GATE_ACC = 520      # floats of the gate kernels' accumulator in front of the H per-head constants
+
+
+def relpos_gate_bwd(x, w8, b8, cst, dgate, B, T, H, want_dx: bool = True, zeroed: Optional[torch.Tensor] = None):
     """-> dx (B,T,H*64) f32, dw8 (8,64), db8 (8), dcst (H); with want_dx=False the first result is dab (B*T, H, 2) f32 instead
     (the gradients wrt the two pre-sigmoid sums; layernorm_bwd(gate_ab=dab, gate_w8=w8) adds da * wa + db * wb itself)."""
     dx = torch.empty(B, T, H * 64, device=x.device, dtype=torch.float32) if want_dx else None
     dab = None if want_dx else torch.empty(B * T, H, 2, device=x.device, dtype=torch.float32)
-    acc = torch.zeros(512 + 8 + H, device=x.device, dtype=torch.float32)                            # one fill for the three
+    # one fill for the three -- or the caller's ZERO fp32 buffer of >= GATE_ACC + H elements (see layernorm_bwd)
+    acc = zeroed[:GATE_ACC + H] if zeroed is not None else torch.zeros(GATE_ACC + H, device=x.device, dtype=torch.float32)
     dw8, db8, dcst = acc[:512].view(8, 64), acc[512:520], acc[520:520 + H]
     check(_lib.load().mtasr_relpos_gate_bwd(_p(x), _dt(x), _p(w8), _p(b8), _p(cst), _p(dgate), B, T, H, _p(dx), _p(dab), _p(dw8),
                                             _p(db8), _p(dcst), _stream()), "mtasr_relpos_gate_bwd")
@@ -391,10 +400,10 @@ def attn_bwd(qkv, out, dout, lse, gate, table, klen, B, H, T, scale, drop=None):
     dev = qkv.device
     D = H * 64
     dqkv = torch.empty(B * T, 3 * D, device=dev, dtype=torch.bfloat16)
-    dq32 = torch.zeros(B * T, D, device=dev, dtype=torch.float32)
+    dq32 = torch.empty(B * T, D, device=dev, dtype=torch.float32)            # zeroed by the call (delta pre-pass), like acc
     delta = torch.empty(B, H, T, device=dev, dtype=torch.float32)
     n_g = (B * H * T + 3) // 4 * 4
-    acc = torch.zeros(n_g + H * (2 * T - 1), device=dev, dtype=torch.float32)                       # one fill for both
+    acc = torch.empty(n_g + H * (2 * T - 1), device=dev, dtype=torch.float32)
     dgate, dtable = acc[:B * H * T].view(B, H, T), acc[n_g:].view(H, 2 * T - 1)
     ds, dsite, dk = (_p(drop[0]), int(drop[1]), int(drop[2])) if drop is not None else (None, 0, 65536)
     check(_lib.load().mtasr_attn_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(gate), _p(table), _p(klen), B, H, T, scale, _p(dqkv),

@@ -26,6 +26,16 @@ _FUSED_LAYERS = os.environ.get("MTASR_FUSED_LAYERS", "1") not in ("", "0")
 # CTC head: keep the fp16 logits of the forward vocabulary GEMM for the backward (2 B x B*T x V per head, 4.1 GB at cfg2)
 # instead of regenerating the softmax with a second vocabulary GEMM.  "0" = memory-lean recompute path.
 _CTC_KEEP_LOGITS = os.environ.get("MTASR_CTC_KEEP_LOGITS", "1") not in ("", "0")
+# Row pitch of the (B*T, V) logits / softmax matrices of the CTC head, in elements.  A multiple of 64 two-byte elements makes
+# every row start on a 128-byte line, so each 128-byte row of a TMA box (fp16 logits store in the forward, bf16 softmax
+# operand loads in the two gradient GEMMs) is exactly one L2 line and four full sectors; with the minimal pitch (multiple of
+# 8 = the 16-byte stride rule of tensor maps) V = 128259 gives rows 16 bytes off the line grid: five sectors per box row and
+# partially written lines at every tile border.  Pad columns are never read (the tensor maps clip at V).
+_VP_ALIGN = max(8, int(os.environ.get("MTASR_VP_ALIGN", "64")) // 8 * 8)
+
+
+def _vocab_pitch(V: int) -> int:
+    return (V + _VP_ALIGN - 1) // _VP_ALIGN * _VP_ALIGN
 
 
 _CAPTURING = False      # inside graphs.GraphedTrainStep capture: parameter-derived operands must be produced BY graph nodes
@@ -465,13 +475,16 @@ class PreLNAttentionFn(Function):
         dbo = (dysum if dysum is not None else K.colsum(dyb)) if need[11] else None
         dqkv, dgate, dtable = K.attn_bwd(qkv, O, dO, lse, gate, tab, klen, B, H, T, scale, drop=drop_attn)
         # gate path into LN(x): only the two scalars per (frame, head); the LayerNorm backward expands da * wa + db * wb itself
-        dab, dwab, dbab, dcst = K.relpos_gate_bwd(h1, wab, bab, cst, dgate, B, T, H, want_dx=False)
+        # the accumulators of this block's row kernels (gate kernel: 520 + H floats, LayerNorm backward: 3 x D) share ONE fill
+        n_gate = (K.GATE_ACC + H + 3) // 4 * 4
+        zbuf = torch.zeros(n_gate + 3 * D, device=dy.device, dtype=F32)
+        dab, dwab, dbab, dcst = K.relpos_gate_bwd(h1, wab, bab, cst, dgate, B, T, H, want_dx=False, zeroed=zbuf)
         dx = dlnw = dlnb = None
         if need[0] or need[1] or need[2]:
             dh1 = K.linear_dgrad(dqkv, wqkv)
             dxf, dxb, dlnw, dlnb, dxs = K.layernorm_bwd(dh1.view(B, T, D), xf, mean, rstd, gamma, dres=dy, want_f32=True,
                                                         want_bf16=need[0], want_param_grads=need[1] or need[2],
-                                                        want_dxsum=need[0], gate_ab=dab, gate_w8=wab)
+                                                        want_dxsum=need[0], gate_ab=dab, gate_w8=wab, zeroed=zbuf[n_gate:])
             dx = dxf if need[0] else None
             if dx is not None:
                 _publish_twin(dx, dxb, dxs)
@@ -733,7 +746,7 @@ class CTCHeadFn(Function):
         bf = bias.detach().float()
         nt = K.gemm_n_tiles(V)
         part = torch.empty(B * T, nt, 4, device=hs.device, dtype=F32)
-        Vp = (V + 7) // 8 * 8
+        Vp = _vocab_pitch(V)
         keep = _CTC_KEEP_LOGITS and any(ctx.needs_input_grad[:3])
         logits16 = torch.empty(B * T, Vp, device=hs.device, dtype=torch.float16) if keep else None
         K.gemm(K.Operand(hb, D), K.Operand(wb, D), B * T, V, D, K.Out(logits16, Vp) if keep else None, bias=bf, mode=1, lse_part=part)
@@ -762,7 +775,7 @@ class CTCHeadFn(Function):
         dev = gout.device
         dG, rowscale = K.ctc_beta_bwd(glog, lse, ys, hlens, ylens, Lmax, alpha, coff, nll_raw, gout.contiguous().float())
         dGb = K.cast_bf16(dG)
-        Vp = (V + 7) // 8 * 8
+        Vp = _vocab_pitch(V)
         need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         db_dense = None
         if logits16 is not None:                                               # softmax * upstream from the kept logits
