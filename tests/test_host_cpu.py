@@ -205,3 +205,16 @@ def test_composite_state_dict_matches_reference_and_unsupported_options_raise():
             SpeechEncoderDecoderModelLlama(make_composite_config(40, **opt))
     with pytest.raises(Exception):           # the product path has no CPU fallback
         model(inputs=torch.zeros(1, 4000), labels=torch.tensor([[3, 40, 4]]))
+
+
+def test_vocabulary_row_pitch_is_line_aligned():
+    """The (rows, V) logits / softmax matrices of the CTC head use a row pitch that is a multiple of 64 two-byte elements
+    (every row starts on a 128-byte line) and never narrower than V; MTASR_VP_ALIGN is rounded to the
+    16-byte stride rule of tensor maps."""
+    from mtasr_b200 import ops
+    for V in (17, 515, 4099, 128259, 128320):
+        p = ops._vocab_pitch(V)
+        assert p >= V and p % ops._VP_ALIGN == 0 and p - V < ops._VP_ALIGN
+    assert ops._VP_ALIGN % 8 == 0
+    if os.environ.get("MTASR_VP_ALIGN") is None:
+        assert ops._VP_ALIGN == 64 and ops._vocab_pitch(128259) == 128320
