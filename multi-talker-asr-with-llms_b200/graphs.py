@@ -9,7 +9,8 @@ synchronisation (lengths stay on the device, the loss is read after the step), f
     step = GraphedTrainStep(lambda w, m, y0, y1, n0, n1: model(w, attention_mask=m, label_spks=[y0, y1],
                                                                label_spks_lengths=[n0, n1]), example_tensors, params)
     loss = step(w, m, y0, y1, n0, n1)       # copies into the static inputs, replays, returns the static loss tensor
-    optimizer.step()                        # gradients are in p.grad (static tensors, rewritten by every replay)
+    optimizer.step()                        # gradients are in p.grad (static tensors, rewritten by every replay and
+                                            # re-attached if the caller cleared them with zero_grad(set_to_none=True))
 
 What capture changes, and how it is kept correct:
   * parameter-derived operands (bf16 copies, the fused QKV weight) are normally cached per parameter version OUTSIDE the
@@ -66,6 +67,10 @@ class GraphedTrainStep:
             with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 self.static_loss = self._body()
         self.launches_per_replay = K.launch_count() - l0    # kernels of this package inside one replay
+        # the tensors every replay writes the gradients into: re-attached after each replay, so a caller that clears
+        # gradients between steps (`optimizer.zero_grad()` / `model.zero_grad()` set `.grad = None` by default, as the HF
+        # trainer does, ref:src/trainer_seq2seq.py:1037-1141) still finds them in `.grad` after the next step
+        self.static_grads = [p.grad for p in self.params]
 
     def _body(self) -> torch.Tensor:
         for p in self.params:
@@ -94,4 +99,7 @@ class GraphedTrainStep:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        for p, g in zip(self.params, self.static_grads):
+            if p.grad is not g:
+                p.grad = g
         return self.static_loss

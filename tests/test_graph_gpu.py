@@ -82,6 +82,13 @@ def test_graphed_step_matches_eager_and_tracks_weight_updates(cuda):
     assert abs(l_e3.item() - l_e.item()) > 1e-5 * abs(l_e.item())
     assert abs(l_g3.item() - l_e3.item()) < 1e-5 * abs(l_e3.item())
     _compare([None if p.grad is None else p.grad.clone() for p in params_l], g_e3)
+    # a caller that clears the gradients between steps (optimizer.zero_grad(): set_to_none) finds them again after the replay
+    # -- NOT the tensors of an eager step that ran in between (which is what _eager leaves behind above)
+    for p in params_l:
+        p.grad = None
+    step(*inputs)
+    assert all(p.grad is g for p, g in zip(step.params, step.static_grads))
+    _compare([None if p.grad is None else p.grad.clone() for p in params_l], g_e3)
     with pytest.raises(ValueError):
         step(*[t[:1] for t in inputs])
 
