@@ -695,7 +695,10 @@ struct LstmLlP {
 };
 
 // KPER > 0: every warp owns exactly KPER k-steps (fully unrolled, all fragment loads of a step in flight at once).
-template <int KPER>
+// KREG > 0: the weight fragments (MMA A operands) of the warp's first KREG k-steps stay in REGISTERS for all T steps.  The
+// per-step product is bound by streaming the CTA's 200 KB weight slice out of shared memory through ldmatrix (0.8 us at
+// 128 B/clk); the register file (256 KB per SM, one CTA per SM) is otherwise idle, so part of the slice lives there.
+template <int KPER, int KREG = 0>
 __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_ll_kernel(const LstmLlP p) {
   extern __shared__ __align__(16) uint8_t lsm[];
   const int Hs = p.Hs, T = p.T, U = p.U, G = p.G;
@@ -735,6 +738,24 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_ll_kernel(const LstmLlP 
   unsigned long long* const out0 = p.ll + (static_cast<long long>(s) * RB + pb) * wpr + ll_word(u0 + pu);
   const long long par_stride = static_cast<long long>(S) * RB * wpr;
 
+  // register-resident weight fragments: k-steps k_lo .. k_lo + KREG - 1 of this warp's (up to) four m-tiles
+  uint32_t wreg[KREG > 0 ? KREG : 1][4][4];
+  if constexpr (KPER > 0 && KREG > 0) {
+#pragma unroll
+    for (int i = 0; i < KREG; ++i) {
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi) {
+        const int mt = mt_lo + mi;
+        wreg[i][mi][0] = wreg[i][mi][1] = wreg[i][mi][2] = wreg[i][mi][3] = 0u;
+        if (mi < mt_half && mt < m_tiles) {
+          const int row = min(mt * 16 + (lane & 15), M - 1);
+          ldsm_x4(smem_addr(Ws + row * rs + (k_lo + i) * 16 + (lane >> 4) * 8), wreg[i][mi][0], wreg[i][mi][1], wreg[i][mi][2],
+                  wreg[i][mi][3]);
+        }
+      }
+    }
+  }
+
   for (int t = 0; t < T; ++t) {
     float xv[4] = {0.f, 0.f, 0.f, 0.f};
     if (has_pair) {
@@ -766,10 +787,15 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_fwd_ll_kernel(const LstmLlP 
           for (int mi = 0; mi < 4; ++mi) {
             const int mt = mt_lo + mi;
             if (mi < mt_half && mt < m_tiles) {
-              const int row = min(mt * 16 + (lane & 15), M - 1);
-              uint32_t a0, a1, a2, a3;
-              ldsm_x4(smem_addr(Ws + row * rs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
-              mma16816(acc[mi], a0, a1, a2, a3, static_cast<uint32_t>(fa[i]), static_cast<uint32_t>(fb[i]));
+              if (i < KREG) {
+                mma16816(acc[mi], wreg[i][mi][0], wreg[i][mi][1], wreg[i][mi][2], wreg[i][mi][3], static_cast<uint32_t>(fa[i]),
+                         static_cast<uint32_t>(fb[i]));
+              } else {
+                const int row = min(mt * 16 + (lane & 15), M - 1);
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4(smem_addr(Ws + row * rs + k0 + (lane >> 4) * 8), a0, a1, a2, a3);
+                mma16816(acc[mi], a0, a1, a2, a3, static_cast<uint32_t>(fa[i]), static_cast<uint32_t>(fb[i]));
+              }
             }
           }
         }
@@ -897,7 +923,8 @@ __global__ void __launch_bounds__(LTHREADS, 1) lstm_bwd_ll_kernel(const LstmLlP 
 #pragma unroll
           for (int q = 0; q < 4; ++q) acc[a][b][q] = 0.f;
       if constexpr (KPER > 0) {
-        // gate chunk g + 1's fragments are requested before chunk g's MMAs
+        // gate chunk g + 1's fragments are requested before chunk g's MMAs (requesting chunks 1..3 all at once after chunk 0
+        // has arrived was measured slower: 4.88 -> 5.09 us per step)
         unsigned long long fa[2][KPER], fb[2][KPER];
 #pragma unroll
         for (int i = 0; i < KPER; ++i) {
@@ -1020,6 +1047,14 @@ static int lstm_bs_pick(int B, int Hs, bool bwd, size_t* smem_out) {
   return 0;
 }
 
+// MTASR_LSTM_WREG: 0 = all weight fragments of the forward from shared memory, 1 / 2 (default) = 6 / 8 of every warp's 14
+// k-steps register-resident (measured at cfg2: 4.36 -> 4.08 -> 3.98 us per step; the same trick does nothing for the
+// backward -- 4.98 us per step either way, it waits on the per-gate-chunk exchange, not on ldmatrix -- and is not applied there).
+static int lstm_wreg_mode() {
+  const char* e = getenv("MTASR_LSTM_WREG");
+  return e ? atoi(e) : 2;
+}
+
 // The flag-in-data kernels apply when the batch-sliced partition exists, U is even (unit pairs never straddle CTAs) and
 // their shared-memory layout (weights + double-buffered partials, no staging tile) fits.
 static int lstm_ll_pick(int B, int Hs, bool bwd, size_t* smem_out) {
@@ -1101,7 +1136,9 @@ extern "C" int mtasr_lstm_fwd(const float* xg, const void* whh_bf16, int32_t ldw
       q.ll = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(barrier) + LL_OFFSET);
       q.B = B; q.T = T; q.Hs = Hs; q.ldw = ldw; q.G = G; q.U = Hs / G;
       q.spin_limit = lstm_spin_limit();
-      void (*kern)(const LstmLlP) = (Hs == 896) ? lstm_fwd_ll_kernel<14> : lstm_fwd_ll_kernel<0>;
+      const int wreg = lstm_wreg_mode();
+      void (*kern)(const LstmLlP) = (Hs == 896) ? (wreg == 0 ? lstm_fwd_ll_kernel<14> : wreg == 1 ? lstm_fwd_ll_kernel<14, 6> : lstm_fwd_ll_kernel<14, 8>)
+                                                : lstm_fwd_ll_kernel<0>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_ll)) != cudaSuccess)
         return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: cannot set smem attribute");
       if (cudaMemsetAsync(q.ll, 0, lstm_ll_bytes(B, Hs, false), st0) != cudaSuccess) return set_error(MTASR_ERR_LAUNCH, "lstm_fwd: memset failed");
