@@ -215,9 +215,24 @@ class WavLMModel(WavLMPreTrainedModel):
         self.feature_extractor._freeze_parameters()
 
     def _conv_lengths(self, n: torch.Tensor) -> torch.Tensor:
-        for k, s in zip(self.config.conv_kernel, self.config.conv_stride):
-            n = torch.div(n - k, s, rounding_mode="floor") + 1
-        return n
+        """hf:640-659 (`L <- floor((L - k) / s) + 1` per conv layer) in closed form: floor((L + C) / S) with S the product of
+        the strides and C = sum_i (s_i - k_i) * prod_{j<i} s_j.  Exact for every integer L: each step is
+        floor((L + s - k) / s) and floor((floor(a / m) + b) / n) = floor((a + b m) / (m n)) for positive m, n -- two tiny
+        launches instead of three per conv layer (21 per call, several calls per step)."""
+        return self._length_chain(n, zip(self.config.conv_kernel, self.config.conv_stride))
+
+    def _conv_adapter_lengths(self, n: torch.Tensor, adapter_layers: int) -> torch.Tensor:
+        """conv stack followed by `adapter_layers` steps `floor((L - 1) / stride) + 1` (hf:655-657), one closed form."""
+        chain = list(zip(self.config.conv_kernel, self.config.conv_stride)) + [(1, self.config.adapter_stride)] * adapter_layers
+        return self._length_chain(n, chain)
+
+    @staticmethod
+    def _length_chain(n: torch.Tensor, kernel_stride_pairs) -> torch.Tensor:
+        C, S = 0, 1
+        for k, s in kernel_stride_pairs:
+            C += (s - k) * S
+            S *= s
+        return torch.div(n + C, S, rounding_mode="floor")
 
     @staticmethod
     def _prefix_mask(lengths: torch.Tensor, T: int) -> torch.Tensor:
@@ -227,10 +242,7 @@ class WavLMModel(WavLMPreTrainedModel):
         """hf:661-679 restated without the (B, S) int64 cumulative sums (only their last element is used there): valid
         length -> conv-stack (+ adapter) length arithmetic -> prefix mask."""
         add_adapter = self.config.add_adapter if add_adapter is None else add_adapter
-        n = self._conv_lengths(attention_mask.sum(dim=-1))
-        if add_adapter:
-            for _ in range(self.config.num_adapter_layers):
-                n = torch.div(n - 1, self.config.adapter_stride, rounding_mode="floor") + 1
+        n = self._conv_adapter_lengths(attention_mask.sum(dim=-1), self.config.num_adapter_layers if add_adapter else 0)
         return self._prefix_mask(n, feature_vector_length)
 
     def _get_feature_vector_attention_mask_x0(self, feature_vector_length: int, attention_mask, add_adapter=None):
@@ -241,11 +253,7 @@ class WavLMModel(WavLMPreTrainedModel):
     def _get_feat_extract_output_lengths_x4(self, input_lengths, add_adapter: Optional[bool] = None):
         """ref:models/modeling_wavlm.py:536-557 -- conv stack + (num_adapter_layers - 1) stride-2 steps."""
         add_adapter = self.config.add_adapter if add_adapter is None else add_adapter
-        n = self._conv_lengths(input_lengths)
-        if add_adapter:
-            for _ in range(self.config.num_adapter_layers - 1):
-                n = torch.div(n - 1, self.config.adapter_stride, rounding_mode="floor") + 1
-        return n
+        return self._conv_adapter_lengths(input_lengths, max(self.config.num_adapter_layers - 1, 0) if add_adapter else 0)
 
     def _get_feature_vector_attention_mask_x4(self, feature_vector_length: int, attention_mask, add_adapter=None):
         n = self._get_feat_extract_output_lengths_x4(attention_mask.sum(dim=-1), add_adapter=add_adapter)

@@ -218,3 +218,19 @@ def test_vocabulary_row_pitch_is_line_aligned():
     assert ops._VP_ALIGN % 8 == 0
     if os.environ.get("MTASR_VP_ALIGN") is None:
         assert ops._VP_ALIGN == 64 and ops._vocab_pitch(128259) == 128320
+
+
+def test_length_arithmetic_closed_form_equals_the_layer_loop():
+    """`WavLMModel._length_chain` (one floor division) against the per-layer loop of hf:640-659 / hf:655-657 for every
+    input length, the WavLM conv stack with 0..3 adapter steps, and random kernel / stride stacks (negative intermediate
+    lengths included: floor semantics)."""
+    from mtasr_b200.modeling_wavlm import WavLMModel
+    rs = np.random.RandomState(0)
+    L = torch.arange(-64, 500000, dtype=torch.int64)
+    stacks = [list(zip((10, 3, 3, 3, 3, 2, 2), (5, 2, 2, 2, 2, 2, 2))) + [(1, 2)] * a for a in range(4)]
+    stacks += [[(int(rs.randint(1, 13)), int(rs.randint(1, 7))) for _ in range(rs.randint(1, 9))] for _ in range(50)]
+    for st in stacks:
+        n = L.clone()
+        for k, s in st:
+            n = torch.div(n - k, s, rounding_mode="floor") + 1
+        assert torch.equal(WavLMModel._length_chain(L, st), n), st
